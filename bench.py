@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the 3-DOF closed-loop control tick (BASELINE.json metric: closed-loop env-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE config 3): 1,048,576 episodes PER GPU (weak scaling), each the
+main_3dof.py scenario (trim 10 m/s, sinusoid task, RLS 9x7 gamma=1 cov0=1e4, agents of main_3dof.py:20-46,
+weights ~ N(0, sigma_w)), excitation.npy applied for ticks < 1000.  One bench "step" = ONE fused kernel
+launch that advances every episode by --ticks ticks.  The phase switch (main_3dof.py:127-137: PID
+collective -> collective agent) is placed at the midpoint of the timed region, so the timed steps are half
+phase-1 launches and half phase-2 launches like the reference's 6000 + 6000 ticks; per-phase rates are
+reported next to the whole-region value.  env-steps are COUNTED (sum of per-episode tick counters from the
+kernel's statistics epilogue), so terminated episodes stop counting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# literal-reference operation counts per tick
+FLOP_PHASE1, FLOP_PHASE2 = 1582, 2341
+STATE_WORDS = 337
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--episodes", type=int, default=1 << 20, help="episodes per GPU")
+    ap.add_argument("--ticks", type=int, default=200, help="ticks per launch (= per bench step)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "mixed", "f32"])
+    ap.add_argument("--store", type=int, default=0, help="0 default, 1 local arrays, 2 shared-memory tile")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-episodes", type=int, default=4096)
+    ap.add_argument("--cpu-ticks", type=int, default=300)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle; the only place besides tests/ and smoke() that may execute oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def _oracle_chunk(args):
+    n, n_ticks, seed, switch = args
+    import numpy as _np
+    from oracle import heli3dof_np as O
+    from tests import helpers as H
+    cfg = O.default_config()
+    cfg["switch_step"] = switch
+    cfg["excitation"] = H.excitation_closed_form()
+    S = O.init_state(n, v_initial=10.0, cfg=cfg, seed=seed)
+    t0 = time.perf_counter()
+    O.run(S, cfg, n_ticks, "all64")
+    dt = time.perf_counter() - t0
+    return float(S["step"].sum()), dt
+
+
+def cpu_oracle_rate(n, n_ticks, procs=1):
+    """env-steps/s of the NumPy oracle on `procs` host processes, same workload shape (half the ticks in
+    each phase)."""
+    switch = n_ticks // 2
+    if procs <= 1:
+        steps, dt = _oracle_chunk((n, n_ticks, 0, switch))
+        return steps / dt, dt
+    import multiprocessing as mp
+    per = max(1, n // procs)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_oracle_chunk, [(8, 2, 0, 1)] * procs)         # warm the workers (imports)
+        t0 = time.perf_counter()
+        res = pool.map(_oracle_chunk, [(per, n_ticks, i, switch) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    return sum(r[0] for r in res) / wall, wall
+
+
+def run_reference_arm(a):
+    """--impl reference: the reference's algorithm for this path on the host cores.  The reference is
+    pure Python (NumPy + torch-CPU) and cannot travel to the GPU box, so this leg runs its pinned CPU
+    restatement (oracle/heli3dof_np.py, `kind: port`) on every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n, n_ticks = a.cpu_episodes * cores, a.cpu_ticks
+    vals = []
+    for i in range(a.warmup + a.steps):
+        v, wall = cpu_oracle_rate(n, n_ticks, procs=cores)
+        if i >= a.warmup:
+            vals.append((v, wall))
+    v = float(np.mean([x[0] for x in vals]))
+    wall = float(np.mean([x[1] for x in vals]))
+    sample = "%d episodes x %d ticks per step over %d processes (NumPy oracle, fp64)" % (n, n_ticks, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "closed-loop env-steps/sec (model+RLS+actor-critic)", "value": v,
+        "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config3: 3-DOF closed-loop (RLS + IDHP actor-critic), CPU sample", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_workload(h3, torch, n, precision, device, seed, store, ticks):
+    edt = torch.float32 if precision == "f32" else torch.float64
+    ndt = torch.float64 if precision == "f64" else torch.float32
+    dt = 0.01
+    env = h3.Helicopter3DOF(dt=dt, t_max=120, n_envs=n, device=device, dtype=edt)
+    env.task = "sinusoid"
+    env.pid_weights = (0, 0, 0)                 # config_3dof.json:34
+    env.ref = 20
+    env.reset(v_initial=10)
+    rls = h3.RecursiveLeastSquares(state_size=7, action_size=2, gamma=1, covariance=10 ** 4, constant=False,
+                                   n_envs=n, device=device, dtype=edt)
+    pid = h3.CollectivePID3DOF(h_ref=5, dt=dt)
+    gen = torch.Generator().manual_seed(seed)
+    col = h3.DHPAgent(control_channel='col', discount_factor=0.9, n_hidden_actor=10, nn_stdev_actor=0.1,
+                      learning_rate_actor=0.1, action_scaling=5, action_network_final_layer='tanh',
+                      n_hidden_critic=10, nn_stdev_critic=0.1, learning_rate_critic=0.1, tau_target_critic=0.01,
+                      tracked_state=1, ac_states=[3], reward_weight=0.01, n_envs=n, device=device, dtype=ndt,
+                      init="batched", generator=gen)
+    lon = h3.DHPAgent(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                      learning_rate_actor=0.2, action_scaling=15, action_network_final_layer='tanh',
+                      n_hidden_critic=6, nn_stdev_critic=0.2, learning_rate_critic=0.2, tau_target_critic=1,
+                      tracked_state=4, ac_states=[5], n_envs=n, device=device, dtype=ndt, init="batched",
+                      generator=gen)
+    loop = h3.ClosedLoop3DOF(env, pid, rls, col, lon, excitation=h3.excitation_signal(1000), switch_step=6000,
+                             ticks_per_launch=ticks, store_policy=store)
+    return loop
+
+
+def state_tensors(loop):
+    """Every mutable per-episode tensor of the loop (what a host-resident batch consists of)."""
+    env, rls = loop.env, loop.rls
+    return [env.state, env.t_ep, loop.ref2, env.corr_u, loop.pid.hdot_corr, rls._W, rls._cov, rls.x, rls.u,
+            rls._skip, loop.agent_col.net, loop.agent_lon.net, env.step_count, env.flags, env.term_step, loop.acc]
+
+
+def fma_peak(h3, torch, dtype_code, device):
+    import ctypes as C
+    lib = h3.lib()
+    scratch = torch.zeros(16, dtype=torch.float64, device=device)
+    flops = C.c_double()
+    best = 0.0
+    stream = h3._lib.stream_ptr(device)
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h3._lib.check(lib.h3_fma_peak(dtype_code, 20000, h3._lib.ptr(scratch), C.byref(flops), stream))
+        e1.record()
+        torch.cuda.synchronize(device)
+        if it:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3))
+    return best
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+    import torch
+    import torch.distributed as dist
+    import msc_thesis_b200 as h3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    h3.lib()
+
+    n, T, K, W = a.episodes, a.ticks, a.steps, a.warmup
+    loop = make_workload(h3, torch, n, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
+    # phase switch at the midpoint of the timed region
+    k_switch = (W + K // 2) * T
+    loop.switch_step = k_switch
+    info1, info2 = loop.info(phase2=False), loop.info(phase2=True)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(W):
+        loop.run(T)
+    barrier()
+    ticks_before = loop.stats()["sum_ticks"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(K):
+        loop.run(T)
+        evs[i + 1].record()
+    loop.allreduce_stats()              # the only collective of the path: per-batch statistics (NCCL)
+    barrier()
+    clocks = sampler.stop() if sampler is not None else None
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    total_ms = evs[0].elapsed_time(evs[K])
+    stats_all = dict(zip(h3._lib.STATS_FIELDS, loop.stats_dev.cpu().tolist()))
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tb = torch.tensor([ticks_before], dtype=torch.float64, device=device)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        ticks_before = float(tb.item())
+    total_ms_max = float(tmax.item())
+    env_steps = stats_all["sum_ticks"] - ticks_before            # whole job, counted by the kernels
+    value = env_steps / (total_ms_max * 1e-3)
+
+    # per-phase numbers on this rank (per-launch CUDA events)
+    half = K // 2
+    alive_frac = stats_all["n_alive"] / max(stats_all["n"], 1.0)
+    p1_ms = float(np.mean(step_ms[:half])) if half else None
+    p2_ms = float(np.mean(step_ms[half:]))
+    rate1 = n * T / (p1_ms * 1e-3) if half else None
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant (only) kernel: FP64/FP32 pipe; HBM beside it ----
+        code = h3._lib.H3_F32 if a.precision == "f32" else h3._lib.H3_F64
+        peak = fma_peak(h3, torch, code, device)
+        flops_step = n * T * (FLOP_PHASE1 * half + FLOP_PHASE2 * (K - half)) / K      # nominal per launch
+        exec_frac = env_steps / (world * n * T * K)
+        launch_s = float(np.mean(step_ms)) * 1e-3
+        achieved = flops_step * exec_frac / launch_s
+        word = 4 if a.precision == "f32" else 8
+        bytes_launch = 2.0 * STATE_WORDS * word * n
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback"
+        if os.path.exists(peaks_file):
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
+        roofline = {"bound": "fp64" if a.precision != "f32" else "fp32", "achieved": achieved / 1e12,
+                    "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "FMA-chain microbenchmark in this run (h3_fma_peak, 2 flop/FMA)",
+                    "flops_per_env_step": {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2,
+                                           "note": "literal reference operator count; transcendental calls "
+                                                   "(46 / 86 per tick) not folded in"},
+                    "hbm": {"achieved": bytes_launch / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": bytes_launch / launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                            "bytes_per_env_step": 2.0 * STATE_WORDS * word / T}}
+        out = {
+            "metric": "closed-loop env-steps/sec (model+RLS+actor-critic)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"f64": "f64", "mixed": "f64 model/RLS + f32 networks", "f32": "f32"}[a.precision],
+            "data": "synthetic",
+            "config": {"workload": "config3: 3-DOF closed-loop training (RLS incremental model + IDHP actor-critic "
+                                   "online update), %d episodes per GPU" % n,
+                       "episodes_per_gpu": n, "ticks_per_launch": T, "switch_step": k_switch,
+                       "phase_mix": "%d phase-1 + %d phase-2 launches timed" % (half, K - half),
+                       "excitation": "excitation.npy closed form, ticks < 1000", "nh_lon": 6, "nh_col": 10,
+                       "l2": "inputs (%.2f GB of episode state per GPU) larger than L2" % (bytes_launch / 2e9),
+                       "kernel_phase1": info1, "kernel_phase2": info2},
+            "phase1_env_steps_per_s_rank0": rate1, "phase2_ms_per_launch_rank0": p2_ms,
+            "phase1_ms_per_launch_rank0": p1_ms, "alive_fraction_end": alive_frac,
+            "env_steps_timed": env_steps, "stats": stats_all,
+            "roofline": roofline, "clocks": clocks, "gpu_launches": K,
+        }
+
+    # ---- e2e: same metric through the public API from HOST buffers (H2D + launch + D2H every step) ----
+    if not a.no_e2e:
+        tensors = state_tensors(loop)
+        loop2 = make_workload(h3, torch, n, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
+        loop2.switch_step = T // 2
+        dev_t = state_tensors(loop2)
+        del loop, tensors
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in dev_t]
+        res_dev = [loop2.acc, loop2.env.flags, loop2.env.term_step, loop2.env.step_count, loop2.stats_dev]
+        res_host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res_dev]
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        d2h = sum(t.numel() * t.element_size() for t in res_host)
+        t0_host = loop2.env.t
+
+        def e2e_step():
+            for h, d in zip(host, dev_t):
+                d.copy_(h, non_blocking=True)
+            loop2.k = 0
+            loop2.env.t = t0_host
+            loop2.run(T)
+            for h, d in zip(res_host, res_dev):
+                h.copy_(d, non_blocking=True)
+
+        for _ in range(max(1, min(W, 2))):
+            e2e_step()
+        barrier()
+        ke = max(2, min(K, 4))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        steps_e2e = 0.0
+        for _ in range(ke):
+            e2e_step()
+        e1.record()
+        barrier()
+        steps_e2e = float(res_host[4][7].item()) * ke            # sum_ticks of one step (identical steps)
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        se = torch.tensor([steps_e2e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            out["e2e"] = {"value": float(se.item()) / (float(ems.item()) * 1e-3), "unit": "env-steps/s",
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
+                          "ms_per_step": float(ems.item()) / ke,
+                          "what": "pinned host batch -> device, one %d-tick launch (switch at tick %d), "
+                                  "per-episode returns/flags/term_step/step + statistics -> host" % (T, T // 2)}
+        del loop2
+
+    # ---- CPU baseline: the oracle on one host core, bounded sample ----
+    if rank == 0:
+        if not a.no_cpu and world == 1:
+            v, wall = cpu_oracle_rate(a.cpu_episodes, a.cpu_ticks, procs=1)
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                   "sample": "%d episodes x %d ticks, NumPy oracle (oracle/heli3dof_np.py), "
+                                             "1 process, %.1f s" % (a.cpu_episodes, a.cpu_ticks, wall),
+                                   "host_cores": os.cpu_count()}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+"""The fused fast path: the tick loop of the reference's main_3dof.py:122-197 for N episodes in lockstep,
+n_ticks per kernel launch, every episode's state resident on chip inside a launch.
+
+ClosedLoop3DOF owns nothing but bookkeeping: it borrows the SoA tensors of the five reference-API objects
+(Helicopter3DOF, CollectivePID3DOF, RecursiveLeastSquares, 2 x DHPAgent) and launches h3_closed_loop on
+them, so the per-object methods stay usable between runs.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._config import build_batch, build_config, byref
+
+TRAJ_COLUMNS = ("x", "z", "u", "w", "theta", "q", "lambda_i", "reference", "collective", "cyclic", "r1", "r2",
+                "alive")
+
+
+def sinusoid_ref_table(t0, dt, n_ticks, amp=10.0, period=10.0):
+    """Host-made reference for a lockstep launch (heli_models.py:218-237 evaluated with numpy, so the values
+    are the reference's own bit for bit).  Entry j is the reference that becomes current after local tick
+    j: get_ref() at t_{j+1} = t0 + (j+1) dt (accumulated like heli_models.py:206), which evaluates
+    t_{j+1} + dt.  Returns (table (n_ticks,), t after n_ticks)."""
+    t = float(t0)
+    out = np.empty(n_ticks, dtype=np.float64)
+    for j in range(n_ticks):
+        t = t + dt
+        x = np.pi * (t + dt) / period
+        out[j] = np.deg2rad(amp / 1.76 * (np.sin(x) + np.sin(2 * x)))
+    return out, t
+
+
+class ClosedLoop3DOF:
+    def __init__(self, env, pid, rls, agent_col, agent_lon, excitation=None, switch_step=6000,
+                 score_window=(0, 0), ticks_per_launch=1000, store_policy=0, ref=None):
+        self.env, self.pid, self.rls = env, pid, rls
+        self.agent_col, self.agent_lon = agent_col, agent_lon
+        self.n = n = env.n_envs
+        self.device = env.device
+        for obj in (rls, agent_col, agent_lon):
+            if obj.n_envs != n or obj.device != env.device:
+                raise ValueError("all objects of a closed loop must share n_envs and device")
+        if rls.dtype != env.dtype or agent_col.dtype != agent_lon.dtype:
+            raise ValueError("env/RLS share one dtype, the two agents share one dtype")
+        if (env.dtype, agent_lon.dtype) not in ((torch.float64, torch.float64), (torch.float64, torch.float32),
+                                                 (torch.float32, torch.float32)):
+            raise ValueError("supported precision pairs (env, nets): (f64,f64), (f64,f32), (f32,f32)")
+        self.switch_step = int(switch_step)
+        self.score_window = tuple(int(x) for x in score_window)
+        self.ticks_per_launch = int(ticks_per_launch)
+        self.store_policy = int(store_policy)
+        self.excitation = None
+        if excitation is not None:
+            e = np.asarray(excitation, dtype=np.float64)[:, :2].copy()      # columns [col, lon] of excitation.npy
+            self.excitation = torch.as_tensor(e, device=self.device).contiguous()
+        pid._ensure(n, env.dtype, self.device)
+        # main_3dof.py:62: ref = env.get_ref() before the loop (velocity task: integrates corr_u once)
+        if ref is None:
+            ref = env.get_ref()
+        self.ref2 = ref[[1, 4]].to(env.dtype).contiguous() if ref.shape[0] == 7 else ref.to(env.dtype).contiguous()
+        self.acc = torch.zeros(3, n, dtype=torch.float64, device=self.device)
+        self.stats_dev = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
+        nbytes = 16 + ((n + 31) // 32) * L.N_STATS * 8
+        self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+        self.k = 0                  # host copy of the lockstep tick index (None: heterogeneous batch)
+        self.launches = 0
+
+    # -- state ------------------------------------------------------------------------------------------
+    def set_heterogeneous(self):
+        """Episodes no longer share tick index / clock (e.g. after loading per-episode snapshots): launches use
+        each episode's own step counter and evaluate the sinusoid reference in the kernel."""
+        self.k = None
+        self.env.uniform_clock = False
+
+    def _batch(self, col_hyper, lon_hyper):
+        env, rls = self.env, self.rls
+        return build_batch(self.n, state=env.state, t=env.t_ep, ref=self.ref2, corr_u=env.corr_u,
+                           trim=env.trimmed_controls, theta_trim=env._theta_trim(), ref_par=env.ref_params,
+                           pid_corr=self.pid.hdot_corr, rls_W=rls._W, rls_cov=rls._cov, rls_x=rls.x, rls_u=rls.u,
+                           rls_skip=rls._skip, col_net=self.agent_col.net, lon_net=self.agent_lon.net,
+                           col_hyper=col_hyper, lon_hyper=lon_hyper, step=env.step_count, flags=env.flags,
+                           term_step=env.term_step, acc=self.acc)
+
+    def _config(self, ref_mode):
+        return build_config(env=self.env, pid=self.pid, rls=self.rls, col=self.agent_col, lon=self.agent_lon,
+                            switch_step=self.switch_step, ref_mode=ref_mode, window=self.score_window,
+                            store_policy=self.store_policy)
+
+    def plan(self, n_ticks):
+        """Launch plan [(first tick, ticks)] : split at the phase switch so that phase-1 launches never load
+        the collective agent's networks, and at ticks_per_launch."""
+        k0 = self.k if self.k is not None else 0
+        cuts = [0, n_ticks]
+        if self.k is not None and k0 < self.switch_step < k0 + n_ticks:
+            cuts.append(self.switch_step - k0)
+        cuts = sorted(set(cuts))
+        out = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            j = a
+            while j < b:
+                m = min(self.ticks_per_launch, b - j)
+                out.append((j, m))
+                j += m
+        return out
+
+    def run(self, n_ticks, record=0, want_stats=True):
+        """Advance every live episode by n_ticks ticks.  record = R > 0 returns the per-tick log rows of
+        main_3dof.py:164-175 for the first R episodes as a (n_ticks, 13, R) tensor (TRAJ_COLUMNS)."""
+        env = self.env
+        n_ticks = int(n_ticks)
+        lockstep = self.k is not None and env.uniform_clock
+        per_ep_ref = env.ref_params is not None
+        table_mode = lockstep and env.task == "sinusoid" and not per_ep_ref
+        cfg = self._config(L.REF_TABLE if table_mode else L.REF_KERNEL)
+        col_hyper, lon_hyper = self.agent_col._hyper_rows(), self.agent_lon._hyper_rows()
+        b = self._batch(col_hyper, lon_hyper)
+        traj = None
+        if record:
+            traj = torch.zeros(n_ticks, L.TRAJ_ROWS, record, dtype=env.dtype, device=self.device)
+        stream = L.stream_ptr(self.device)
+        lib = L.lib()
+        plan = self.plan(n_ticks)
+        for j0, m in plan:
+            table = None
+            if table_mode:
+                tab, t_end = sinusoid_ref_table(env.t, env.dt, m, env.ref_amplitude, env.ref_period)
+                table = torch.as_tensor(tab).to(self.device, non_blocking=False)
+            else:
+                t_end = env.t
+                for _ in range(m):
+                    t_end = t_end + env.dt
+            tr = None
+            if traj is not None:
+                tr = L.H3Traj()
+                tr.out = traj[j0:j0 + m].data_ptr()
+                tr.n_traj = record
+                tr.ld_traj = record
+            last = (j0 + m == n_ticks)
+            stats = self.stats_dev if (want_stats and last) else None
+            L.check(lib.h3_closed_loop(byref(cfg), byref(b), self.k + j0 if lockstep else -1, L.ptr(table),
+                                       L.ptr(self.excitation),
+                                       0 if self.excitation is None else self.excitation.shape[0], m,
+                                       byref(tr) if tr is not None else None, L.ptr(stats),
+                                       L.ptr(self._scratch) if stats is not None else None, stream))
+            env.t = t_end
+            self.launches += 1
+        if self.k is not None:
+            self.k += n_ticks
+        return traj
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def stats(self):
+        """This rank's batch statistics of the last run() as a dict (synchronises)."""
+        v = self.stats_dev.cpu().tolist()
+        return dict(zip(L.STATS_FIELDS, v))
+
+    def allreduce_stats(self, group=None):
+        """Sum the statistics vector over all ranks (NCCL all-reduce on the compute stream; gloo on CPU)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.stats_dev, op=dist.ReduceOp.SUM, group=group)
+        return self.stats_dev
+
+    def info(self, phase2=True):
+        """Occupancy facts of the kernel variant run() would launch (block, smem, blocks/SM, registers)."""
+        cfg = self._config(L.REF_TABLE)
+        vals = [C.c_int32() for _ in range(4)]
+        L.check(L.lib().h3_closed_loop_info(byref(cfg), 1 if phase2 else 0, *[C.byref(v) for v in vals]))
+        return dict(zip(("block", "smem_bytes", "blocks_per_sm", "regs"), (v.value for v in vals)))

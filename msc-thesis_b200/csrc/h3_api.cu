@@ -1,0 +1,735 @@
+// C ABI of libheli3dof.so (include/heli3dof.h) and the un-fused per-object kernels that back the
+// step-by-step methods of the Python classes (Helicopter3DOF.step, CollectivePID3DOF.__call__,
+// RecursiveLeastSquares.update, DHPAgent.get_action / update_networks).  The fused path is
+// h3_closed_loop (h3_closed_loop.cuh).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "h3_launch.cuh"
+
+namespace h3 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int check_launch(const char* what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(err));
+        return H3_E_CUDA;
+    }
+    return H3_OK;
+}
+
+constexpr int SMALL_BLOCK = 128;
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + SMALL_BLOCK - 1) / SMALL_BLOCK); }
+
+// ---------------------------------------------------------------------------------------------
+// Helicopter3DOF._trim (heli_models.py:293-328)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMALL_BLOCK) trim_kernel(H3EnvParams E, const double* __restrict__ v, double* trim,
+                                                           double* state, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    const double vt = v[e];
+    const double weight = E.mass * E.g;                                 // :302
+    const double drag = 0.5 * E.rho * vt * vt * E.cds;                  // :303
+    const double thrust = ::sqrt(drag * drag + weight * weight);        // :304
+    const double c_t = thrust / (E.rho * E.v_tip * E.v_tip * E.area);   // :305
+    const double theta_f = ::atan2(-drag, weight);                      // :308
+    double sf, cf;
+    ::sincos(theta_f, &sf, &cf);
+    const double mu = vt / E.v_tip;                                     // :314
+    // quartic 4 l^4 + b3 l^3 + b2 l^2 - c_t^2 = 0 (:315-318).  For l > 0 the polynomial is increasing and
+    // convex (b3, b2 >= 0), so it has exactly one positive root and Newton from the hover value
+    // sqrt(c_t / 2) -- where the polynomial is >= 0 -- descends onto it monotonically.
+    const double b3 = 8.0 * mu * ::sin(drag / weight);
+    const double b2 = 4.0 * mu * mu;
+    const double c0 = c_t * c_t;
+    double l = ::sqrt(c_t * 0.5);
+    for (int it = 0; it < 64; ++it) {
+        const double f = ((4.0 * l + b3) * l + b2) * l * l - c0;
+        const double df = ((16.0 * l + 3.0 * b3) * l + 2.0 * b2) * l;
+        const double ln = l - f / df;
+        if (!(ln < l)) break;
+        l = ln;
+    }
+    // 2x2 solve (:321-324): [[a, b], [c, d]] [cyclic, collective]^T = [r0, r1]^T
+    const double a = 1.0 + 1.5 * mu * mu, b = -8.0 / 3.0 * mu, c = -mu, d = 2.0 / 3.0 + mu * mu;
+    const double r0 = -2.0 * mu * mu * drag / weight - 2.0 * mu * l;
+    const double r1 = 4.0 / E.blade_solidity * c_t / E.cl_alpha + mu * drag / weight + l;
+    const double det = a * d - b * c;
+    const double cyclic = (r0 * d - b * r1) / det;
+    const double collective = (a * r1 - c * r0) / det;
+    trim[e] = collective;
+    trim[ld + e] = cyclic;
+    state[e] = 0.0;
+    state[ld + e] = 0.0;
+    state[2 * ld + e] = vt * cf;
+    state[3 * ld + e] = vt * sf;
+    state[4 * ld + e] = theta_f;
+    state[5 * ld + e] = 0.0;
+    state[6 * ld + e] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Helicopter3DOF.step, open loop, n_ticks per launch (BASELINE config 2)
+// ---------------------------------------------------------------------------------------------
+template <typename ET>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    env_step_kernel(EnvK<ET> K, double dt, ET* state, double* t, int32_t* step, int32_t* flags, int32_t* term_step,
+                    const double* __restrict__ trim, const ET* __restrict__ actions,
+                    const double* __restrict__ excitation, int exc_len, int n_ticks, ET* states_out, int64_t n_out,
+                    int64_t ld_out, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    ET s[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) s[i] = state[i * ld + e];
+    ET a0, a1;
+    if (actions != nullptr) {
+        a0 = actions[e];
+        a1 = actions[ld + e];
+    } else {
+        a0 = (ET)trim[e];
+        a1 = (ET)trim[ld + e];
+    }
+    int k = step[e], f = flags[e], ts = term_step[e];
+    double tt = t[e];
+    for (int j = 0; j < n_ticks && f == 0; ++j) {
+        ET col = a0, cyc = a1;
+        if (excitation != nullptr && k < exc_len) {
+            col += (ET)excitation[2 * k];
+            cyc += (ET)excitation[2 * k + 1];
+        }
+        ET sth, cth;
+        Math<ET>::sincos_(s[4], &sth, &cth);
+        bool done;
+        env_step(K, s, col, cyc, sth, cth, done);
+        tt += dt;
+        if (states_out != nullptr && e < n_out) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) states_out[((int64_t)j * 7 + i) * ld_out + e] = s[i];
+        }
+        const bool nan_act = (col != col) || (cyc != cyc);
+        const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
+        if (nf) {
+            f = nf;
+            ts = k;
+        }
+        k += 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) state[i * ld + e] = s[i];
+    t[e] = tt;
+    step[e] = k;
+    flags[e] = f;
+    term_step[e] = ts;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Helicopter3DOF.get_ref
+// ---------------------------------------------------------------------------------------------
+template <typename ET>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    get_ref_kernel(EnvK<ET> K, int task, double dt, double amp0, double period0, const ET* __restrict__ state,
+                   const double* __restrict__ t, ET* ref, ET* corr_u, const double* __restrict__ theta_trim,
+                   const double* __restrict__ ref_par, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    if (task == H3_TASK_SINUSOID) {
+        double amp = amp0, period = period0;
+        if (ref_par != nullptr) {
+            amp = ref_par[e];
+            period = ref_par[ld + e];
+        }
+        ref[e] = (ET)-0.0;
+        ref[ld + e] = (ET)sinusoid_ref(t[e] + dt, amp, period);
+    } else if (task == H3_TASK_VELOCITY) {
+        ET cu = corr_u[e];
+        ref[e] = (ET)0;
+        ref[ld + e] = velocity_ref(K, state[2 * ld + e], cu);
+        corr_u[e] = cu;
+    } else {
+        ref[e] = (ET)0;
+        ref[ld + e] = stop_over_point_ref(K, state[e], state[2 * ld + e], (ET)theta_trim[e]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CollectivePID3DOF.__call__
+// ---------------------------------------------------------------------------------------------
+template <typename ET>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    pid_kernel(EnvK<ET> K, const ET* __restrict__ state, ET* pid_corr, ET* out, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    ET s[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) s[i] = state[i * ld + e];
+    ET sth, cth;
+    Math<ET>::sincos_(s[4], &sth, &cth);
+    ET corr = pid_corr[e];
+    out[e] = pid_collective(K, s, sth, cth, corr);
+    pid_corr[e] = corr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RecursiveLeastSquares.update / predict -- state kept in global memory (un-fused path)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct GlobalVec {
+    T* p;
+    int64_t ld;
+    H3_DEV T& operator[](int i) { return p[(int64_t)i * ld]; }
+};
+
+template <typename ET>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    rls_update_kernel(EnvK<ET> K, int sym, ET* W, ET* cov, ET* xp, ET* up, int32_t* skip, const ET* __restrict__ state,
+                      const ET* __restrict__ action, const ET* __restrict__ next_state, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    ET st[7], ns[7], ac[2];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        st[i] = state[i * ld + e];
+        ns[i] = next_state[i * ld + e];
+    }
+    ac[0] = action[e];
+    ac[1] = action[ld + e];
+    if (skip[e]) {                                  // model.py:34-39
+        skip[e] = 0;
+    } else {
+        ET X[9], Y[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            X[i] = st[i] - xp[i * ld + e];
+            Y[i] = ns[i] - st[i];
+        }
+        X[7] = ac[0] - up[e];
+        X[8] = ac[1] - up[ld + e];
+        WMat<ET, GlobalVec<ET>> Wm;
+        Wm.v.p = W + e;
+        Wm.v.ld = ld;
+        // the un-fused path always uses the literal (non-symmetric) update of model.py:53-59
+        CovFull<ET, GlobalVec<ET>> C;
+        C.v.p = cov + e;
+        C.v.ld = ld;
+        (void)sym;
+        rls_update(K, Wm, C, X, Y);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) xp[i * ld + e] = st[i];
+    up[e] = ac[0];
+    up[ld + e] = ac[1];
+}
+
+template <typename ET>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    rls_predict_kernel(const ET* __restrict__ W, const ET* __restrict__ xp, const ET* __restrict__ up,
+                       const ET* __restrict__ state, const ET* __restrict__ action, ET* out, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    ET X[9];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) X[i] = state[i * ld + e] - xp[i * ld + e];      // model.py:65-66
+    X[7] = action[e] - up[e];
+    X[8] = action[ld + e] - up[ld + e];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        ET a = state[j * ld + e];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a += W[(i * 7 + j) * ld + e] * X[i];        // :67
+        out[j * ld + e] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DHPAgent.get_action / update_networks on global-memory weights
+// ---------------------------------------------------------------------------------------------
+template <typename ET, typename NT, int NH>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_action_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
+                        const ET* __restrict__ ref, NT* out, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    double w_r;
+    const AgentH<NT> H = load_hyper<NT>(h, hyper, ld, e, w_r);
+    NetAcc<NT, NH, GlobalVec<NT>> N;
+    N.v.p = net + e;
+    N.v.ld = ld;
+    const int ri = (h.tracked_state == 1) ? 0 : 1;
+    const NT s0 = (NT)state[h.ac_state * ld + e];
+    const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
+    NT hh[NH], f;
+    out[e] = actor_forward<NT, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
+}
+
+template <typename ET, typename NT, int NH>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_update_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
+                        const ET* __restrict__ next_state, const ET* __restrict__ ref,
+                        const ET* __restrict__ next_ref, const NT* __restrict__ dr_ds, const NT* __restrict__ Fm,
+                        const NT* __restrict__ Gm, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    double w_r;
+    const AgentH<NT> H = load_hyper<NT>(h, hyper, ld, e, w_r);
+    NetAcc<NT, NH, GlobalVec<NT>> N;
+    N.v.p = net + e;
+    N.v.ld = ld;
+    const int ri = (h.tracked_state == 1) ? 0 : 1;
+    const int ia = h.ac_state, it = h.tracked_state;
+    const NT s0 = (NT)state[ia * ld + e];
+    const NT s1 = (NT)(state[it * ld + e] - ref[ri * ld + e]);
+    const NT n0 = (NT)next_state[ia * ld + e];
+    const NT n1 = (NT)(next_state[it * ld + e] - next_ref[ri * ld + e]);
+    NT F[2][2], G[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) F[i][j] = Fm[(i * 2 + j) * ld + e];
+        G[i] = Gm[i * ld + e];
+    }
+    NT hh[NH], f;
+    (void)actor_forward<NT, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
+    agent_update<NT, NH, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f);
+}
+
+// get_reward (agents.py:123-128) and get_transition_matrices (agents.py:130-140)
+template <typename ET, typename NT>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_reward_kernel(H3AgentHyper h, const double* __restrict__ hyper, const ET* __restrict__ next_state,
+                        const ET* __restrict__ ref, ET* reward, NT* dr_ds, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    const ET w_r = (ET)(hyper != nullptr ? hyper[H3_HYPER_REWARD_WEIGHT * ld + e] : h.reward_weight);
+    const int ri = (h.tracked_state == 1) ? 0 : 1;
+    const ET e_tr = next_state[h.tracked_state * ld + e] - ref[ri * ld + e];
+    reward[e] = -(e_tr * e_tr) * w_r;
+    dr_ds[e] = (NT)0;
+    dr_ds[ld + e] = (NT)((ET)-2 * e_tr * w_r);
+}
+
+template <typename ET, typename NT>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_transition_kernel(H3AgentHyper h, const ET* __restrict__ W, NT* Fm, NT* Gm, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    const int idx[2] = {h.ac_state, h.tracked_state};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Fm[(i * 2 + j) * ld + e] = (NT)W[(idx[j] * 7 + idx[i]) * ld + e];
+        Gm[i * ld + e] = (NT)W[((7 + h.channel) * 7 + idx[i]) * ld + e];
+    }
+}
+
+struct AgentArgs {
+    const void *state, *next_state, *ref, *next_ref, *dr_ds, *F, *G;
+    void* out;
+};
+
+template <typename ET, typename NT>
+static int dispatch_agent(bool update, const H3AgentHyper& h, const double* hyper, void* net, const AgentArgs& a,
+                          int64_t n, int64_t ld, cudaStream_t st) {
+#define H3_AGENT_CASE(NH)                                                                                      \
+    case NH:                                                                                                   \
+        if (update)                                                                                            \
+            agent_update_kernel<ET, NT, NH><<<grid_for(n), SMALL_BLOCK, 0, st>>>(                               \
+                h, hyper, (NT*)net, (const ET*)a.state, (const ET*)a.next_state, (const ET*)a.ref,             \
+                (const ET*)a.next_ref, (const NT*)a.dr_ds, (const NT*)a.F, (const NT*)a.G, n, ld);             \
+        else                                                                                                   \
+            agent_action_kernel<ET, NT, NH><<<grid_for(n), SMALL_BLOCK, 0, st>>>(                               \
+                h, hyper, (NT*)net, (const ET*)a.state, (const ET*)a.ref, (NT*)a.out, n, ld);                  \
+        break;
+    switch (h.n_hidden) {
+        H3_AGENT_CASE(4)
+        H3_AGENT_CASE(6)
+        H3_AGENT_CASE(8)
+        H3_AGENT_CASE(10)
+        H3_AGENT_CASE(12)
+        H3_AGENT_CASE(16)
+        default:
+            set_error("agent kernels are compiled for n_hidden in {4,6,8,10,12,16}, got %d", h.n_hidden);
+            return H3_E_UNSUPPORTED;
+    }
+#undef H3_AGENT_CASE
+    return check_launch(update ? "agent_update_kernel" : "agent_action_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// FMA-chain peak (roofline denominator): 8 independent chains per thread
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, T* out) {
+    T a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (T)(threadIdx.x + i) * (T)1e-3;
+    const T b = (T)0.999999, c = (T)1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = a[i] * b + c;
+    }
+    T s = (T)0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == (T)123456789) out[0] = s;      // never true; keeps the chains alive
+}
+
+static bool dtype_ok(int d) { return d == H3_F64 || d == H3_F32; }
+
+}  // namespace h3
+
+using namespace h3;
+
+extern "C" {
+
+int h3_version(void) { return H3_VERSION; }
+
+const char* h3_last_error(void) { return g_err; }
+
+void h3_env_params_default(H3EnvParams* out, double dt) {
+    // heli_models.py:117-130
+    out->g = 9.81;
+    out->cl_alpha = 5.7;
+    out->blade_solidity = 0.075;
+    out->lock_number = 6;
+    out->cds = 1.5;
+    out->mass = 2200;
+    out->rho = 1.225;
+    out->v_tip = 200;
+    out->rotor_radius = 7.32;
+    out->iy = 10615;
+    out->mast = 1;
+    out->omega = out->v_tip / out->rotor_radius;
+    out->area = 3.14159265358979323846 * out->rotor_radius * out->rotor_radius;
+    out->tau = 0.1;
+    out->dt = dt;
+}
+
+int h3_trim(const H3EnvParams* env, const double* v, double* trim, double* state, int64_t n, int64_t ld,
+            void* stream) {
+    if (!env || !v || !trim || !state || ld < n) {
+        set_error("h3_trim: bad argument");
+        return H3_E_ARG;
+    }
+    if (n <= 0) return H3_OK;
+    trim_kernel<<<grid_for(n), SMALL_BLOCK, 0, (cudaStream_t)stream>>>(*env, v, trim, state, n, ld);
+    return check_launch("trim_kernel");
+}
+
+int h3_env_step(const H3Config* cfg, const H3Batch* b, const void* actions, const double* excitation,
+                int32_t exc_len, int32_t n_ticks, void* states_out, int64_t n_out, int64_t ld_out, void* stream) {
+    if (!cfg || !b || !b->state || !b->t || !b->step || !b->flags || !b->term_step || (!actions && !b->trim) ||
+        !dtype_ok(cfg->env_dtype) || b->ld < b->n) {
+        set_error("h3_env_step: bad argument");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0 || n_ticks <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->env_dtype == H3_F64)
+        env_step_kernel<double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<double>(*cfg), cfg->env.dt, (double*)b->state, b->t, b->step, b->flags, b->term_step, b->trim,
+            (const double*)actions, excitation, exc_len, n_ticks, (double*)states_out, n_out, ld_out, b->n, b->ld);
+    else
+        env_step_kernel<float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<float>(*cfg), cfg->env.dt, (float*)b->state, b->t, b->step, b->flags, b->term_step, b->trim,
+            (const float*)actions, excitation, exc_len, n_ticks, (float*)states_out, n_out, ld_out, b->n, b->ld);
+    return check_launch("env_step_kernel");
+}
+
+int h3_get_ref(const H3Config* cfg, const H3Batch* b, void* stream) {
+    if (!cfg || !b || !b->state || !b->t || !b->ref || !dtype_ok(cfg->env_dtype) ||
+        (cfg->task == H3_TASK_VELOCITY && !b->corr_u) || (cfg->task == H3_TASK_STOP_OVER_POINT && !b->theta_trim) ||
+        cfg->task < 0 || cfg->task > 2) {
+        set_error("h3_get_ref: bad argument");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->env_dtype == H3_F64)
+        get_ref_kernel<double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<double>(*cfg), cfg->task, cfg->env.dt, cfg->ref_amp, cfg->ref_period, (const double*)b->state,
+            b->t, (double*)b->ref, (double*)b->corr_u, b->theta_trim, b->ref_par, b->n, b->ld);
+    else
+        get_ref_kernel<float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<float>(*cfg), cfg->task, cfg->env.dt, cfg->ref_amp, cfg->ref_period, (const float*)b->state,
+            b->t, (float*)b->ref, (float*)b->corr_u, b->theta_trim, b->ref_par, b->n, b->ld);
+    return check_launch("get_ref_kernel");
+}
+
+int h3_pid_collective(const H3Config* cfg, const H3Batch* b, void* collective_out, void* stream) {
+    if (!cfg || !b || !b->state || !b->pid_corr || !collective_out || !dtype_ok(cfg->env_dtype)) {
+        set_error("h3_pid_collective: bad argument");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->env_dtype == H3_F64)
+        pid_kernel<double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(make_envk<double>(*cfg), (const double*)b->state,
+                                                                   (double*)b->pid_corr, (double*)collective_out,
+                                                                   b->n, b->ld);
+    else
+        pid_kernel<float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(make_envk<float>(*cfg), (const float*)b->state,
+                                                                  (float*)b->pid_corr, (float*)collective_out, b->n,
+                                                                  b->ld);
+    return check_launch("pid_kernel");
+}
+
+int h3_rls_update(const H3Config* cfg, const H3Batch* b, const void* state, const void* action,
+                  const void* next_state, void* stream) {
+    if (!cfg || !b || !b->rls_W || !b->rls_cov || !b->rls_x || !b->rls_u || !b->rls_skip || !state || !action ||
+        !next_state || !dtype_ok(cfg->env_dtype)) {
+        set_error("h3_rls_update: bad argument");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->env_dtype == H3_F64)
+        rls_update_kernel<double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<double>(*cfg), cfg->rls_symmetric, (double*)b->rls_W, (double*)b->rls_cov, (double*)b->rls_x,
+            (double*)b->rls_u, b->rls_skip, (const double*)state, (const double*)action, (const double*)next_state,
+            b->n, b->ld);
+    else
+        rls_update_kernel<float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            make_envk<float>(*cfg), cfg->rls_symmetric, (float*)b->rls_W, (float*)b->rls_cov, (float*)b->rls_x,
+            (float*)b->rls_u, b->rls_skip, (const float*)state, (const float*)action, (const float*)next_state, b->n,
+            b->ld);
+    return check_launch("rls_update_kernel");
+}
+
+int h3_rls_predict(const H3Config* cfg, const H3Batch* b, const void* state, const void* action, void* out,
+                   void* stream) {
+    if (!cfg || !b || !b->rls_W || !b->rls_x || !b->rls_u || !state || !action || !out || !dtype_ok(cfg->env_dtype)) {
+        set_error("h3_rls_predict: bad argument");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->env_dtype == H3_F64)
+        rls_predict_kernel<double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            (const double*)b->rls_W, (const double*)b->rls_x, (const double*)b->rls_u, (const double*)state,
+            (const double*)action, (double*)out, b->n, b->ld);
+    else
+        rls_predict_kernel<float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+            (const float*)b->rls_W, (const float*)b->rls_x, (const float*)b->rls_u, (const float*)state,
+            (const float*)action, (float*)out, b->n, b->ld);
+    return check_launch("rls_predict_kernel");
+}
+
+static bool agent_desc_ok(const H3AgentHyper& h) {
+    return h.tracked_state >= 0 && h.tracked_state <= 6 && h.ac_state >= 0 && h.ac_state <= 6 && h.channel >= 0 &&
+           h.channel <= 1;
+}
+
+// precision pair -> 0: (f64,f64), 1: (f64,f32), 2: (f32,f32), -1: unsupported
+static int precision_pair(const H3Config* cfg) {
+    if (cfg->env_dtype == H3_F64 && cfg->net_dtype == H3_F64) return 0;
+    if (cfg->env_dtype == H3_F64 && cfg->net_dtype == H3_F32) return 1;
+    if (cfg->env_dtype == H3_F32 && cfg->net_dtype == H3_F32) return 2;
+    set_error("unsupported precision pair (env %d, net %d)", cfg->env_dtype, cfg->net_dtype);
+    return -1;
+}
+
+static int agent_call(bool update, const H3Config* cfg, const H3Batch* b, int32_t which, const AgentArgs& a,
+                      void* stream) {
+    const char* name = update ? "update" : "action";
+    if (!cfg || !b || !a.state || !a.ref || (which != 0 && which != 1) ||
+        (update && (!a.next_state || !a.next_ref || !a.dr_ds || !a.F || !a.G)) || (!update && !a.out)) {
+        set_error("h3_agent_%s: bad argument", name);
+        return H3_E_ARG;
+    }
+    const H3AgentHyper& h = which == 0 ? cfg->col : cfg->lon;
+    void* net = which == 0 ? b->col_net : b->lon_net;
+    const double* hyper = which == 0 ? b->col_hyper : b->lon_hyper;
+    if (!net || !agent_desc_ok(h)) {
+        set_error("h3_agent_%s: bad agent description", name);
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (precision_pair(cfg)) {
+        case 0: return dispatch_agent<double, double>(update, h, hyper, net, a, b->n, b->ld, st);
+        case 1: return dispatch_agent<double, float>(update, h, hyper, net, a, b->n, b->ld, st);
+        case 2: return dispatch_agent<float, float>(update, h, hyper, net, a, b->n, b->ld, st);
+    }
+    return H3_E_UNSUPPORTED;
+}
+
+int h3_agent_action(const H3Config* cfg, const H3Batch* b, int32_t which, const void* state, const void* ref,
+                    void* action_out, void* stream) {
+    AgentArgs a = {state, nullptr, ref, nullptr, nullptr, nullptr, nullptr, action_out};
+    return agent_call(false, cfg, b, which, a, stream);
+}
+
+int h3_agent_update(const H3Config* cfg, const H3Batch* b, int32_t which, const void* state,
+                    const void* next_state, const void* ref, const void* next_ref, const void* dr_ds, const void* F,
+                    const void* G, void* stream) {
+    AgentArgs a = {state, next_state, ref, next_ref, dr_ds, F, G, nullptr};
+    return agent_call(true, cfg, b, which, a, stream);
+}
+
+int h3_agent_reward(const H3Config* cfg, const H3Batch* b, int32_t which, const void* next_state, const void* ref,
+                    void* reward_out, void* dr_ds_out, void* stream) {
+    if (!cfg || !b || !next_state || !ref || !reward_out || !dr_ds_out || (which != 0 && which != 1)) {
+        set_error("h3_agent_reward: bad argument");
+        return H3_E_ARG;
+    }
+    const H3AgentHyper& h = which == 0 ? cfg->col : cfg->lon;
+    const double* hyper = which == 0 ? b->col_hyper : b->lon_hyper;
+    if (!agent_desc_ok(h)) {
+        set_error("h3_agent_reward: bad agent description");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (precision_pair(cfg)) {
+        case 0:
+            agent_reward_kernel<double, double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, hyper, (const double*)next_state, (const double*)ref, (double*)reward_out, (double*)dr_ds_out, b->n,
+                b->ld);
+            break;
+        case 1:
+            agent_reward_kernel<double, float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, hyper, (const double*)next_state, (const double*)ref, (double*)reward_out, (float*)dr_ds_out, b->n,
+                b->ld);
+            break;
+        case 2:
+            agent_reward_kernel<float, float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, hyper, (const float*)next_state, (const float*)ref, (float*)reward_out, (float*)dr_ds_out, b->n,
+                b->ld);
+            break;
+        default: return H3_E_UNSUPPORTED;
+    }
+    return check_launch("agent_reward_kernel");
+}
+
+int h3_agent_transition(const H3Config* cfg, const H3Batch* b, int32_t which, void* F_out, void* G_out,
+                        void* stream) {
+    if (!cfg || !b || !b->rls_W || !F_out || !G_out || (which != 0 && which != 1)) {
+        set_error("h3_agent_transition: bad argument");
+        return H3_E_ARG;
+    }
+    const H3AgentHyper& h = which == 0 ? cfg->col : cfg->lon;
+    if (!agent_desc_ok(h)) {
+        set_error("h3_agent_transition: bad agent description");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (precision_pair(cfg)) {
+        case 0:
+            agent_transition_kernel<double, double><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, (const double*)b->rls_W, (double*)F_out, (double*)G_out, b->n, b->ld);
+            break;
+        case 1:
+            agent_transition_kernel<double, float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, (const double*)b->rls_W, (float*)F_out, (float*)G_out, b->n, b->ld);
+            break;
+        case 2:
+            agent_transition_kernel<float, float><<<grid_for(b->n), SMALL_BLOCK, 0, st>>>(
+                h, (const float*)b->rls_W, (float*)F_out, (float*)G_out, b->n, b->ld);
+            break;
+        default: return H3_E_UNSUPPORTED;
+    }
+    return check_launch("agent_transition_kernel");
+}
+
+static int loop_dispatch(const H3Config* cfg, const H3Batch* b, int32_t step0, const double* ref_table,
+                         const double* excitation, int32_t exc_len, int32_t n_ticks, const H3Traj* traj,
+                         double* stats, void* stats_scratch, void* stream, int force_phase2, LoopInfo* info) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (precision_pair(cfg)) {
+        case 0:
+            return launch_closed_loop<double, double>(*cfg, *b, step0, ref_table, excitation, exc_len, n_ticks, traj,
+                                                      stats, stats_scratch, st, force_phase2, info);
+        case 1:
+            return launch_closed_loop<double, float>(*cfg, *b, step0, ref_table, excitation, exc_len, n_ticks, traj,
+                                                     stats, stats_scratch, st, force_phase2, info);
+        case 2:
+            return launch_closed_loop<float, float>(*cfg, *b, step0, ref_table, excitation, exc_len, n_ticks, traj,
+                                                    stats, stats_scratch, st, force_phase2, info);
+    }
+    return H3_E_UNSUPPORTED;
+}
+
+int h3_closed_loop(const H3Config* cfg, const H3Batch* b, int32_t step0, const double* ref_table,
+                   const double* excitation, int32_t exc_len, int32_t n_ticks, const H3Traj* traj, double* stats,
+                   void* stats_scratch, void* stream) {
+    if (!cfg || !b) {
+        set_error("h3_closed_loop: null config / batch");
+        return H3_E_ARG;
+    }
+    if (!b->state || !b->t || !b->ref || !b->corr_u || !b->trim || !b->theta_trim || !b->pid_corr || !b->rls_W ||
+        !b->rls_cov || !b->rls_x || !b->rls_u || !b->rls_skip || !b->col_net || !b->lon_net || !b->step ||
+        !b->flags || !b->term_step || !b->acc || b->ld < b->n) {
+        set_error("h3_closed_loop: H3Batch has a null field or ld < n");
+        return H3_E_ARG;
+    }
+    if (cfg->task < 0 || cfg->task > 2 || (cfg->task == H3_TASK_SINUSOID && cfg->ref_mode == H3_REF_TABLE &&
+                                           (step0 < 0 || ref_table == nullptr))) {
+        set_error("h3_closed_loop: H3_REF_TABLE needs a lockstep launch (step0 >= 0) and a reference table");
+        return H3_E_ARG;
+    }
+    if (!agent_desc_ok(cfg->col) || !agent_desc_ok(cfg->lon)) {
+        set_error("h3_closed_loop: bad agent description");
+        return H3_E_ARG;
+    }
+    if (excitation == nullptr) exc_len = 0;
+    return loop_dispatch(cfg, b, step0, ref_table, excitation, exc_len, n_ticks, traj, stats, stats_scratch, stream,
+                         -1, nullptr);
+}
+
+int64_t h3_stats_scratch_bytes(int64_t n) {
+    const int64_t blocks = (n + 31) / 32;
+    return 16 + blocks * H3_N_STATS * (int64_t)sizeof(double);
+}
+
+int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int32_t* smem_bytes,
+                        int32_t* blocks_per_sm, int32_t* regs) {
+    if (!cfg) {
+        set_error("h3_closed_loop_info: null config");
+        return H3_E_ARG;
+    }
+    LoopInfo info;
+    H3Batch dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    int rc = loop_dispatch(cfg, &dummy, 0, nullptr, nullptr, 0, 1, nullptr, nullptr, nullptr, nullptr,
+                           phase2 ? 1 : 0, &info);
+    if (rc != H3_OK) return rc;
+    if (block) *block = info.block;
+    if (smem_bytes) *smem_bytes = info.smem_bytes;
+    if (blocks_per_sm) *blocks_per_sm = info.blocks_per_sm;
+    if (regs) *regs = info.regs;
+    return H3_OK;
+}
+
+int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_out, void* stream) {
+    if (!dtype_ok(dtype) || iters <= 0 || !scratch_out) {
+        set_error("h3_fma_peak: bad argument");
+        return H3_E_ARG;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    if (dtype == H3_F64)
+        fma_peak_kernel<double><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (double*)scratch_out);
+    else
+        fma_peak_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (float*)scratch_out);
+    if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    return check_launch("fma_peak_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// Host-side dispatch of the fused closed-loop kernel; one translation unit per precision pair
+// instantiates launch_closed_loop<ET, NT> (h3_loop_*.cu) so the variants compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "h3_closed_loop.cuh"
+
+namespace h3 {
+
+void set_error(const char* fmt, ...);
+
+struct LoopInfo {
+    int block, smem_bytes, blocks_per_sm, regs;
+};
+
+template <typename ET, typename NT>
+int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const double* ref_table,
+                       const double* excitation, int exc_len, int n_ticks, const H3Traj* traj, double* stats,
+                       void* stats_scratch, cudaStream_t stream, int force_phase2, LoopInfo* info_only);
+
+#ifdef H3_LOOP_IMPL
+
+constexpr int BLOCK_LOCAL = 64;
+constexpr int BLOCK_SMEM = 32;
+
+template <typename ET, typename NT>
+struct KernelSel {
+    void (*fn)(const LoopParams<ET, NT>);
+    int block;
+    size_t smem;
+};
+
+// Kernel variants (a pruned cross product, see closed_loop_kernel's template flags):
+//   FAST    : symmetric covariance, launch-uniform hyper-parameters, tau_lon == 1   (main_3dof.py config)
+//   SWEEP   : symmetric covariance, per-episode (or tau_lon != 1) hyper-parameters  (main.py-style sweeps)
+//   GENERAL : covariance not known symmetric (model.py:53-54 literally), any hyper-parameters
+enum { VAR_FAST = 0, VAR_SWEEP = 1, VAR_GENERAL = 2 };
+
+template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L>
+static KernelSel<ET, NT> sel_store(int store) {
+    KernelSel<ET, NT> k;
+    constexpr int NCOV = SYM ? 45 : 81;
+    if (store == STORE_SMEM) {
+        k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, STORE_SMEM, BLOCK_SMEM, 1>;
+        k.block = BLOCK_SMEM;
+        k.smem = loop_smem_bytes<ET, NCOV>(BLOCK_SMEM, STORE_SMEM, COL, NHC, sizeof(NT));
+    } else {
+        k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, STORE_LOCAL, BLOCK_LOCAL, 1>;
+        k.block = BLOCK_LOCAL;
+        k.smem = loop_smem_bytes<ET, NCOV>(BLOCK_LOCAL, STORE_LOCAL, COL, NHC, sizeof(NT));
+    }
+    return k;
+}
+
+template <typename ET, typename NT, int NHL, int NHC, bool COL>
+static KernelSel<ET, NT> sel_variant(int variant, int store) {
+    if (variant == VAR_FAST) return sel_store<ET, NT, NHL, NHC, COL, true, false, true>(store);
+    if (variant == VAR_SWEEP) return sel_store<ET, NT, NHL, NHC, COL, true, true, false>(STORE_SMEM);
+    return sel_store<ET, NT, NHL, NHC, COL, false, true, false>(store);
+}
+
+template <typename ET, typename NT, int NHL, int NHC>
+static KernelSel<ET, NT> sel_flags(bool col, int variant, int store) {
+    return col ? sel_variant<ET, NT, NHL, NHC, true>(variant, store)
+               : sel_variant<ET, NT, NHL, NHC, false>(variant, store);
+}
+
+template <typename ET, typename NT>
+int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const double* ref_table,
+                       const double* excitation, int exc_len, int n_ticks, const H3Traj* traj, double* stats,
+                       void* stats_scratch, cudaStream_t stream, int force_phase2, LoopInfo* info_only) {
+    const int nhl = cfg.lon.n_hidden, nhc = cfg.col.n_hidden;
+    // the collective agent's networks are only touched by ticks >= switch_step (main_3dof.py:127-137)
+    bool col = true;
+    if (step0 >= 0 && (int64_t)step0 + n_ticks <= (int64_t)cfg.switch_step) col = false;
+    if (force_phase2 >= 0) col = force_phase2 != 0;
+    const bool per_ep = b.col_hyper != nullptr || b.lon_hyper != nullptr;
+    const int variant = (cfg.rls_symmetric == 0) ? VAR_GENERAL
+                                                 : ((per_ep || cfg.lon.tau != 1.0) ? VAR_SWEEP : VAR_FAST);
+    const int store = (cfg.store_policy == 1) ? STORE_LOCAL : STORE_SMEM;
+    KernelSel<ET, NT> k;
+    if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant, store);
+#ifndef H3_FAST_BUILD
+    else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant, store);
+#endif
+    else {
+        set_error("h3_closed_loop: hidden widths (lon %d, col %d) not compiled in (have 6/10, 8/8)", nhl, nhc);
+        return H3_E_UNSUPPORTED;
+    }
+    cudaError_t err = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
+    if (err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem=%zu): %s", k.smem, cudaGetErrorString(err));
+        return H3_E_CUDA;
+    }
+    if (info_only != nullptr) {
+        cudaFuncAttributes fa;
+        err = cudaFuncGetAttributes(&fa, k.fn);
+        if (err != cudaSuccess) {
+            set_error("cudaFuncGetAttributes: %s", cudaGetErrorString(err));
+            return H3_E_CUDA;
+        }
+        int nb = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.fn, k.block, k.smem);
+        if (err != cudaSuccess) {
+            set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor: %s", cudaGetErrorString(err));
+            return H3_E_CUDA;
+        }
+        info_only->block = k.block;
+        info_only->smem_bytes = (int)k.smem;
+        info_only->blocks_per_sm = nb;
+        info_only->regs = fa.numRegs;
+        return H3_OK;
+    }
+    if (b.n <= 0 || n_ticks <= 0) return H3_OK;
+    LoopParams<ET, NT> P;
+    P.K = make_envk<ET>(cfg);
+    P.n = b.n;
+    P.ld = b.ld;
+    P.state = (ET*)b.state;
+    P.ref = (ET*)b.ref;
+    P.corr_u = (ET*)b.corr_u;
+    P.pid_corr = (ET*)b.pid_corr;
+    P.rls_W = (ET*)b.rls_W;
+    P.rls_cov = (ET*)b.rls_cov;
+    P.rls_x = (ET*)b.rls_x;
+    P.rls_u = (ET*)b.rls_u;
+    P.t = b.t;
+    P.acc = b.acc;
+    P.trim = b.trim;
+    P.theta_trim = b.theta_trim;
+    P.ref_par = b.ref_par;
+    P.col_hyper = b.col_hyper;
+    P.lon_hyper = b.lon_hyper;
+    P.rls_skip = b.rls_skip;
+    P.step = b.step;
+    P.flags = b.flags;
+    P.term_step = b.term_step;
+    P.col_net = (NT*)b.col_net;
+    P.lon_net = (NT*)b.lon_net;
+    P.ref_table = ref_table;
+    P.excitation = excitation;
+    P.exc_len = exc_len;
+    P.n_ticks = n_ticks;
+    P.step0 = step0;
+    P.task = cfg.task;
+    P.ref_mode = cfg.ref_mode;
+    P.switch_step = cfg.switch_step;
+    P.update_lon = cfg.update_lon;
+    P.win_lo = cfg.win_lo;
+    P.win_hi = cfg.win_hi;
+    P.ref_amp = cfg.ref_amp;
+    P.ref_period = cfg.ref_period;
+    P.dt = cfg.env.dt;
+    P.col = cfg.col;
+    P.lon = cfg.lon;
+    const H3AgentHyper* hs[2] = {&cfg.col, &cfg.lon};
+    AgentH<NT>* hd[2] = {&P.col_h, &P.lon_h};
+    for (int a = 0; a < 2; ++a) {
+        hd[a]->gamma = (NT)hs[a]->gamma;
+        hd[a]->lr_a = (NT)hs[a]->lr_actor;
+        hd[a]->lr_c = (NT)hs[a]->lr_critic;
+        hd[a]->tau = (NT)hs[a]->tau;
+        hd[a]->scale = (NT)hs[a]->scale;
+    }
+    P.col_wr = (ET)cfg.col.reward_weight;
+    P.lon_wr = (ET)cfg.lon.reward_weight;
+    P.traj = (traj != nullptr) ? (ET*)traj->out : nullptr;
+    P.n_traj = (traj != nullptr) ? traj->n_traj : 0;
+    P.ld_traj = (traj != nullptr) ? traj->ld_traj : 0;
+    const int64_t grid = (b.n + k.block - 1) / k.block;
+    P.stats = stats;
+    P.ticket = nullptr;
+    P.partials = nullptr;
+    if (stats != nullptr) {
+        if (stats_scratch == nullptr) {
+            set_error("h3_closed_loop: stats requested without scratch");
+            return H3_E_ARG;
+        }
+        P.ticket = (unsigned int*)stats_scratch;
+        P.partials = (double*)((char*)stats_scratch + 16);
+        err = cudaMemsetAsync(stats_scratch, 0, 16, stream);
+        if (err != cudaSuccess) {
+            set_error("cudaMemsetAsync: %s", cudaGetErrorString(err));
+            return H3_E_CUDA;
+        }
+    }
+    k.fn<<<(unsigned)grid, k.block, k.smem, stream>>>(P);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("closed_loop_kernel launch (grid %lld, block %d, smem %zu): %s", (long long)grid, k.block, k.smem,
+                  cudaGetErrorString(err));
+        return H3_E_CUDA;
+    }
+    return H3_OK;
+}
+
+#endif  // H3_LOOP_IMPL
+
+}  // namespace h3

@@ -1,0 +1,362 @@
+// Device functions of one closed-loop control tick, per episode (one thread = one episode).
+// Every function cites the reference statement it restates; nothing here is translated line by
+// line -- trig is shared between model, PID and reference, the incremental model uses one
+// reciprocal and (optionally) the symmetry of the covariance, the IDHP update is in closed form
+// (no autograd) and re-uses the actor forward pass of get_action.
+#pragma once
+#include "../../include/heli3dof.h"
+#include "h3_math.cuh"
+
+namespace h3 {
+
+// ----------------------------------------------------------------------------------------------
+// launch-uniform constants, precomputed on the host in fp64 and cast to the compute type
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+struct EnvK {
+    T dt, g, inv_omega, inv_vtip, k_a1_q, k_bem, k_thrust, k_drag, inv_mass, k_q, inv_tau;
+    T pid_kp, pid_ki, pid_kd, pid_href, pid_hi;
+    T env_kp, env_ki, env_kd, env_ref;
+    T rls_gamma, rls_inv_gamma;
+    T rad2deg;
+};
+
+template <typename T>
+__host__ inline EnvK<T> make_envk(const H3Config& c) {
+    const H3EnvParams& e = c.env;
+    EnvK<T> k;
+    k.dt = (T)e.dt;
+    k.g = (T)e.g;
+    k.inv_omega = (T)(1.0 / e.omega);
+    k.inv_vtip = (T)(1.0 / e.v_tip);
+    k.k_a1_q = (T)(-16.0 / e.lock_number);
+    k.k_bem = (T)(e.cl_alpha * e.blade_solidity / 4.0);
+    k.k_thrust = (T)(e.rho * e.v_tip * e.v_tip * e.area);
+    k.k_drag = (T)(e.cds * 0.5 * e.rho / e.mass);
+    k.inv_mass = (T)(1.0 / e.mass);
+    k.k_q = (T)(e.mast / e.iy);
+    k.inv_tau = (T)(1.0 / e.tau);
+    k.pid_kp = (T)c.pid_kp;
+    k.pid_ki = (T)c.pid_ki;
+    k.pid_kd = (T)c.pid_kd;
+    k.pid_href = (T)c.pid_href;
+    k.pid_hi = (T)(10.0 * (3.14159265358979323846 / 180.0));
+    k.env_kp = (T)c.env_kp;
+    k.env_ki = (T)c.env_ki;
+    k.env_kd = (T)c.env_kd;
+    k.env_ref = (T)c.env_ref;
+    k.rls_gamma = (T)c.rls_gamma;
+    k.rls_inv_gamma = (T)(1.0 / c.rls_gamma);
+    k.rad2deg = (T)(180.0 / 3.14159265358979323846);
+    return k;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Helicopter3DOF.step  (heli_models.py:157-198, :210-213)
+//   sth/cth = sin/cos(theta) of the pre-step state (shared with the PID).
+//   atan2 is eliminated: cos/sin(alpha_c) with alpha_c = cyc - atan2(w,u) are expanded with
+//   cos(atan2(w,u)) = u/V, sin(atan2(w,u)) = w/V, so v_diml*cos(alpha_c) = (u cos cyc + w sin cyc)/v_tip.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+H3_DEV void env_step(const EnvK<T>& K, T (&s)[7], T col, T cyc, T sth, T cth, bool& done) {
+    typedef Math<T> M;
+    const T u = s[2], w = s[3], q = s[5], li = s[6];
+    const T q_diml = q * K.inv_omega;                       // :159
+    const T V = M::sqrt_(u * u + w * w);                    // :160  (vv, :175)
+    T sc, cc;
+    M::sincos_(cyc, &sc, &cc);
+    const T mu = (u * cc + w * sc) * K.inv_vtip;            // :163
+    const T lc = (u * sc - w * cc) * K.inv_vtip;            // :164
+    const T lsum = lc + li;
+    const T a1 = (K.k_a1_q * q_diml + (T)(8.0 / 3.0) * mu * col - (T)2 * mu * lsum) /
+                 ((T)1 - mu * mu * (T)0.5);                 // :167
+    const T ct_bem = K.k_bem * ((T)(2.0 / 3.0) * col * ((T)1 + (T)1.5 * mu * mu) - lsum);   // :170
+    T s1, c1;
+    M::sincos_(cyc - a1, &s1, &c1);
+    const T gx = (u * c1 + w * s1) * K.inv_vtip;            // v_diml cos(alpha_c - a1)
+    const T gy = (u * s1 - w * c1) * K.inv_vtip + li;       // v_diml sin(alpha_c - a1) + lambda_i
+    const T ct_glau = (T)2 * li * M::sqrt_(gx * gx + gy * gy);   // :171
+    const T thrust = ct_bem * K.k_thrust;                   // :174
+    const T tm = thrust * K.inv_mass;
+    const T dr = K.k_drag * V;
+    const T x_dot = u * cth + w * sth;                      // :176
+    const T z_dot = -(u * sth - w * cth);                   // :177
+    const T u_dot = -K.g * sth - dr * u + tm * s1 - q * w;  // :178-181
+    const T w_dot = K.g * cth - dr * w - tm * c1 + q * u;   // :182-185
+    const T q_dot = -thrust * K.k_q * s1;                   // :187
+    const T li_dot = (ct_bem - ct_glau) * K.inv_tau;        // :188
+    s[0] += x_dot * K.dt;                                   // :191-198 explicit Euler
+    s[1] += z_dot * K.dt;
+    s[2] += u_dot * K.dt;
+    s[3] += w_dot * K.dt;
+    s[4] += q * K.dt;
+    s[5] += q_dot * K.dt;
+    s[6] += li_dot * K.dt;
+    done = M::abs_(s[4] * K.rad2deg) > (T)90;               // :210-213
+}
+
+// ----------------------------------------------------------------------------------------------
+// CollectivePID3DOF.__call__  (PID.py:16-24)
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+H3_DEV T pid_collective(const EnvK<T>& K, const T (&s)[7], T sth, T cth, T& corr) {
+    const T hdot_ref = K.pid_kd * (K.pid_href + s[1]);      // h_ref - -obs[1]
+    const T hdot = s[2] * sth - s[3] * cth;
+    const T err = hdot_ref - hdot;
+    const T col = ((T)5 + K.pid_kp * err + K.pid_ki * corr) * (T)(3.14159265358979323846 / 180.0);
+    corr += K.dt * err;                                     // integrator AFTER use (:23)
+    return clip_nan(col, (T)0, K.pid_hi);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Helicopter3DOF.get_ref  (heli_models.py:217-255).  Reference generation always runs in fp64
+// (t is accumulated in fp64 for every precision path).
+// ----------------------------------------------------------------------------------------------
+H3_DEV double sinusoid_ref(double t_plus_dt, double amp, double period) {
+    const double x = 3.14159265358979323846 * t_plus_dt / period;
+    double sx, cx;
+    ::sincos(x, &sx, &cx);
+    // sin x + sin 2x = sin x (1 + 2 cos x)
+    return (amp / 1.76 * (sx * (1.0 + 2.0 * cx))) * (3.14159265358979323846 / 180.0);
+}
+
+template <typename T>
+H3_DEV T velocity_ref(const EnvK<T>& K, T u, T& corr_u) {   // :239-243 incl. the integrator side effect
+    const T u_err = K.env_ref - u;
+    const T th = (K.env_kp * u_err + K.env_ki * corr_u) * (T)(3.14159265358979323846 / 180.0);
+    corr_u += u_err * K.dt;
+    return th;
+}
+
+template <typename T>
+H3_DEV T stop_over_point_ref(const EnvK<T>& K, T x, T u, T theta_trim) {    // :245-250
+    const T x_err = K.env_ref - x;
+    const T th = (K.env_kp * x_err + K.env_kd * u) * (T)(3.14159265358979323846 / 180.0);
+    return (theta_trim > th) ? theta_trim : th;             // python max(th, trim): NaN th stays
+}
+
+// ----------------------------------------------------------------------------------------------
+// RecursiveLeastSquares.update  (model.py:41-59), n = 9 regressors, m = 7 outputs.
+//   Wm(i,j): weight accessor (9x7).  Cv: covariance accessor -- full (9x9) or symmetric-packed.
+// ----------------------------------------------------------------------------------------------
+template <typename T, typename WAcc, typename CAcc>
+H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7]) {
+    T err[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) err[j] = Y[j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) err[j] -= X[i] * Wm(i, j);          // :49-50
+    T covX[9], Xcov[9];
+    Cv.matvec(X, covX, Xcov);                                           // :53-54
+    T d = K.rls_gamma;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) d += Xcov[j] * X[j];                    // :55
+    const T inv_d = (T)1 / d;
+    T g[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) Wm(i, j) += g[i] * err[j];          // :58
+    Cv.downdate(g, Xcov, K.rls_inv_gamma);                              // :59
+}
+
+// covariance policies ------------------------------------------------------------------------
+// Element storage is delegated to `Vec` (operator[](int) -> T&), so the same code runs on a
+// register/local array or on a strided shared-memory column.
+template <typename T, typename Vec>
+struct CovFull {            // model.py:53-54 literally: cov.X and X^T.cov computed separately
+    Vec v;                  // 81 elements, row-major
+    H3_DEV void matvec(const T (&X)[9], T (&covX)[9], T (&Xcov)[9]) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { covX[i] = (T)0; Xcov[i] = (T)0; }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const T c = v[i * 9 + j];
+                covX[i] += c * X[j];
+                Xcov[j] += X[i] * c;
+            }
+    }
+    H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[i * 9 + j] = (v[i * 9 + j] - g[i] * Xcov[j]) * inv_gamma;
+    }
+};
+
+template <typename T, typename Vec>
+struct CovSym {             // upper triangle only (45 elements): cov == cov^T is an invariant of
+    Vec v;                  // model.py:59 when it holds initially (model.py:85: identity * c)
+    static H3_DEV constexpr int idx(int i, int j) { return i * 9 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+    H3_DEV void matvec(const T (&X)[9], T (&covX)[9], T (&Xcov)[9]) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) covX[i] = (T)0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                const T c = v[idx(i, j)];
+                covX[i] += c * X[j];
+                if (j != i) covX[j] += c * X[i];
+            }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Xcov[i] = covX[i];
+    }
+    H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) v[idx(i, j)] = (v[idx(i, j)] - g[i] * Xcov[j]) * inv_gamma;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// IDHP agent (agents.py).  Net: accessor with a1(k,i) a2(k) c1(k,i) c2(j,k) t1(k,i) t2(j,k).
+// ----------------------------------------------------------------------------------------------
+template <typename NT>
+struct AgentH {             // hyper-parameters in network precision
+    NT gamma, lr_a, lr_c, tau, scale;
+};
+
+// DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
+template <typename NT, int NH, typename Net>
+H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, NT (&h)[NH], NT& f) {
+    typedef Math<NT> M;
+    NT y = (NT)0;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        h[k] = M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
+        y += net.a2(k) * h[k];
+    }
+    f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
+    return scale * f;
+}
+
+// get_reward + get_transition_matrices + update_networks (agents.py:123-196), closed form.
+//   s0,s1 = augmented state of (obs, ref); n0,n1 = augmented state of (next_obs, next_ref);
+//   dr_ds = [dr0, dr] (get_reward: dr0 = 0, dr = -2 e w_r, already in network precision); F[i][j], G[i] from the POST-update RLS weights;
+//   h_a, f = actor forward of the same (obs, ref) with the pre-update actor (== get_action's pass).
+//   TAU1: tau_target_critic == 1 for every episode of the launch -> the target critic IS the critic after
+//   every update (agents.py:196: 1*p + 0*t), so its rows are neither kept on chip nor updated; lambda_t2
+//   is evaluated with the critic's (pre-update) weights, which are the target's.
+template <typename NT, int NH, bool TAU1, typename Net>
+H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
+                         const NT (&F)[2][2], const NT (&G)[2], const NT (&h_a)[NH], NT f) {
+    typedef Math<NT> M;
+    // critic(s) and target_critic(s')  (:170-171)
+    NT h_c[NH], lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0};
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        h_c[k] = M::tanh_(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
+        lam1[0] += net.c2(0, k) * h_c[k];
+        lam1[1] += net.c2(1, k) * h_c[k];
+        if (TAU1) {
+            const NT h_t = M::tanh_(net.c1(k, 0) * n0 + net.c1(k, 1) * n1);
+            lam2[0] += net.c2(0, k) * h_t;
+            lam2[1] += net.c2(1, k) * h_t;
+        } else {
+            const NT h_t = M::tanh_(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
+            lam2[0] += net.t2(0, k) * h_t;
+            lam2[1] += net.t2(1, k) * h_t;
+        }
+    }
+    // action.backward() (:174): delta = da/dy, p = da/d(pre-activation of hidden k)
+    const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);
+    NT p[NH], da_ds[2] = {(NT)0, (NT)0};
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        p[k] = delta * net.a2(k) * ((NT)1 - h_a[k] * h_a[k]);
+        da_ds[0] += net.a1(k, 0) * p[k];
+        da_ds[1] += net.a1(k, 1) * p[k];
+    }
+    // target = dr_ds + gamma * lambda_t2 ; error_critic = lambda_t1 - target (F + G da_ds)  (:178-179)
+    const NT tg0 = dr0 + H.gamma * lam2[0];     // dr_ds[0] is 0 in get_reward (agents.py:124)
+    const NT tg1 = dr + H.gamma * lam2[1];
+    NT e_c[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        e_c[j] = lam1[j] - (tg0 * (F[0][j] + G[0] * da_ds[j]) + tg1 * (F[1][j] + G[1] * da_ds[j]));
+    // SGD (:184-188): wa += lr_a (target.G) da/dwa ; wc -= lr_c dL/dwc, then soft target update (:195-196)
+    const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
+    const NT one_m_tau = (NT)1 - H.tau;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        const NT back = (net.c2(0, k) * e_c[0] + net.c2(1, k) * e_c[1]) * ((NT)1 - h_c[k] * h_c[k]);
+        // actor
+        net.a1(k, 0) += ka * (p[k] * s0);
+        net.a1(k, 1) += ka * (p[k] * s1);
+        net.a2(k) += ka * (delta * h_a[k]);
+        // critic
+        const NT c10 = net.c1(k, 0) - H.lr_c * (back * s0);
+        const NT c11 = net.c1(k, 1) - H.lr_c * (back * s1);
+        const NT c20 = net.c2(0, k) - H.lr_c * (e_c[0] * h_c[k]);
+        const NT c21 = net.c2(1, k) - H.lr_c * (e_c[1] * h_c[k]);
+        net.c1(k, 0) = c10;
+        net.c1(k, 1) = c11;
+        net.c2(0, k) = c20;
+        net.c2(1, k) = c21;
+        // target critic
+        if (!TAU1) {
+            net.t1(k, 0) = H.tau * c10 + one_m_tau * net.t1(k, 0);
+            net.t1(k, 1) = H.tau * c11 + one_m_tau * net.t1(k, 1);
+            net.t2(0, k) = H.tau * c20 + one_m_tau * net.t2(0, k);
+            net.t2(1, k) = H.tau * c21 + one_m_tau * net.t2(1, k);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// element storage policies
+// ----------------------------------------------------------------------------------------------
+template <typename T, int N>
+struct LocalVec {           // registers / local memory (compile-time indices after unrolling)
+    T v[N];
+    H3_DEV T& operator[](int i) { return v[i]; }
+    H3_DEV void load(const T* g, int64_t ld) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = g[(int64_t)i * ld];
+    }
+    H3_DEV void store(T* g, int64_t ld) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) g[(int64_t)i * ld] = v[i];
+    }
+};
+
+template <typename T, int N, int STRIDE>
+struct SmemVec {            // column of a [N][STRIDE] shared-memory tile; bank-conflict free per warp
+    T* p;                   // already offset by the thread index
+    H3_DEV T& operator[](int i) { return p[i * STRIDE]; }
+    H3_DEV void load(const T* g, int64_t ld) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i * STRIDE] = g[(int64_t)i * ld];
+    }
+    H3_DEV void store(T* g, int64_t ld) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) g[(int64_t)i * ld] = p[i * STRIDE];
+    }
+};
+
+template <typename T, typename Vec>
+struct WMat {               // RLS weights (9,7) row-major
+    Vec v;
+    H3_DEV T& operator()(int i, int j) { return v[i * 7 + j]; }
+};
+
+template <typename NT, int NH, typename Vec>
+struct NetAcc {             // rows of the `[11*nh][ld]` network block (include/heli3dof.h)
+    Vec v;
+    H3_DEV NT& a1(int k, int i) { return v[2 * k + i]; }
+    H3_DEV NT& a2(int k) { return v[2 * NH + k]; }
+    H3_DEV NT& c1(int k, int i) { return v[3 * NH + 2 * k + i]; }
+    H3_DEV NT& c2(int j, int k) { return v[5 * NH + j * NH + k]; }
+    H3_DEV NT& t1(int k, int i) { return v[7 * NH + 2 * k + i]; }
+    H3_DEV NT& t2(int j, int k) { return v[9 * NH + j * NH + k]; }
+};
+
+}  // namespace h3

@@ -1,0 +1,64 @@
+"""CPU, world_size 2, gloo: the N>1 path of the closed loop is "shard the episodes, all-reduce the per-batch
+statistics" (DESIGN.md section 6).  Each rank builds the statistics vector of ITS shard (with the oracle standing
+in for the kernel epilogue, same field order), all-reduces it through the package's helper, and the result
+must equal the single-process statistics of the whole batch -- independent of the partition."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+N_TOTAL, N_TICKS = 48, 30
+
+
+def _problem():
+    from oracle import heli3dof_np as O
+    cfg = O.default_config()
+    cfg["switch_step"] = 10
+    v = np.linspace(5.0, 25.0, N_TOTAL)             # a function of the GLOBAL episode index
+    S = O.init_state(N_TOTAL, v_initial=v, cfg=cfg, seed=7)
+    return S, cfg
+
+
+def _stats_vector(S):
+    f = S["flags"]
+    return torch.tensor([len(f), (f == 0).sum(), ((f & 1) != 0).sum(), ((f & 2) != 0).sum(), S["ret"][0].sum(),
+                         S["ret"][1].sum(), 0.0, S["step"].sum()], dtype=torch.float64)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import msc_thesis_b200 as h3
+    from oracle import heli3dof_np as O
+    S, cfg = _problem()
+    lo, hi = h3.shard_range(N_TOTAL, rank, world)
+    shard = {k: (v[..., lo:hi].copy() if isinstance(v, np.ndarray) else v) for k, v in S.items()}
+    O.run(shard, cfg, N_TICKS, "all64")
+    stats = _stats_vector(shard)
+    h3.allreduce_stats(stats)
+    if rank == 0:
+        torch.save(stats, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_statistics_allreduce_matches_single_process(tmp_path):
+    from oracle import heli3dof_np as O
+    import msc_thesis_b200 as h3
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "stats.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    S, cfg = _problem()
+    O.run(S, cfg, N_TICKS, "all64")
+    want = _stats_vector(S)
+    assert torch.equal(got[:4], want[:4]) and got[7] == want[7]        # counts bit-exact
+    assert torch.allclose(got[4:7], want[4:7], rtol=1e-12, atol=0)
+    d = h3.distributed.summarize(got)
+    assert d["n"] == N_TOTAL and 0.0 <= d["success_rate"] <= 1.0

@@ -1,0 +1,322 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libheli3dof.so) against the oracle and the
+golden fixtures generated from the unmodified reference.  Tolerances: fp64 path 1e-9 relative per tick
+(north_star); integer bookkeeping (step, flags, term_step, rls_skip) bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import heli3dof_np as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def h3():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import msc_thesis_b200 as m
+    m.lib()     # fails loudly if the CUDA library was not built
+    return m
+
+
+# ------------------------------------------------------------------------------------------------------
+# trim and open-loop model step (BASELINE config 2)
+# ------------------------------------------------------------------------------------------------------
+def test_trim_matches_reference(h3):
+    g = H.load("trim.npz")
+    env = h3.Helicopter3DOF(n_envs=len(g["v"]))
+    state, trim = env.reset(v_initial=torch.as_tensor(g["v"]))
+    assert H.relerr(trim.cpu().numpy().T, g["trim"]) < 1e-12
+    assert H.relerr(state.cpu().numpy().T, g["state"], floor=1e-9) < 1e-12
+
+
+def test_open_loop_step_vs_oracle(h3):
+    """Integrator-only correctness: 2048 episodes with v ~ U(5,25), trim + excitation.npy, 1200 ticks,
+    every tick of the first 256 episodes against the oracle's env_step."""
+    n, n_rec, n_ticks = 2048, 256, 1200
+    gen = torch.Generator().manual_seed(0)
+    v = 5 + 20 * torch.rand(n, generator=gen, dtype=torch.float64)
+    env = h3.Helicopter3DOF(n_envs=n)
+    state0, trim = env.reset(v_initial=v)
+    tr_o, st_o = O.trim(v.numpy())
+    assert H.relerr(trim.cpu().numpy(), tr_o) < 1e-12
+    exc = H.excitation()
+    out = env.rollout(n_ticks, excitation=exc, record=n_rec).cpu().numpy()
+    s = st_o[:, :n_rec].copy()
+    worst = 0.0
+    for k in range(n_ticks):
+        a = tr_o[:, :n_rec] + (exc[k][:, None] if k < len(exc) else 0.0)
+        s, done = O.env_step(s, a, 0.01)
+        worst = max(worst, float(np.max(np.abs(out[k] - s) / np.maximum(np.abs(s), 1e-6))))
+        assert not done.any()
+    assert worst < TOL64, worst
+    assert int(env.step_count.min()) == n_ticks and int(env.flags.max()) == 0
+    assert abs(env.t - float(env.t_ep[0])) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# teacher-forced single ticks against the reference's own post-tick snapshots
+# ------------------------------------------------------------------------------------------------------
+def _groups(g):
+    n = g["pre_step"].shape[0]
+    keys = {}
+    for i in range(n):
+        key = (int(g["task"][i]), int(g["switch_step"][i]), int(g["exc_on"][i]), g["hyper"][i].tobytes(),
+               g["env_gains"][i].tobytes())
+        keys.setdefault(key, []).append(i)
+    return keys
+
+
+@pytest.mark.parametrize("mode,variant", [("all64", "fast"), ("all64", "general"), ("all64", "local"),
+                                          ("ref32", "fast")])
+def test_teacher_forced_ticks(h3, mode, variant):
+    g = H.load("ticks_%s.npz" % mode)
+    tol = TOL64 if mode == "all64" else 1e-5
+    exc = H.excitation()
+    total = 0
+    flagged = 0
+    for key, idx in _groups(g).items():
+        i0 = idx[0]
+        cfg = H.cfg_for(g["task"][i0], g["switch_step"][i0], exc if g["exc_on"][i0] else None, g["hyper"][i0],
+                        g["env_gains"][i0])
+        pre = H.snaps_from(g, "pre_", idx)
+        post = H.snaps_from(g, "post_", idx)
+        S = O.state_from_snapshots(pre, mode)
+        S["theta_trim"] = g["theta_trim"][idx].copy()
+        loop = H.make_loop(S, cfg, mode, heterogeneous=True, assume_symmetric=(variant != "general"),
+                           store_policy=1 if variant == "local" else 0)
+        traj = loop.run(1, record=len(idx))
+        got = H.loop_state(loop)
+        want = O.state_from_snapshots(post, mode)
+        want["flags"] = g["flags"][idx].astype(np.int64)
+        want["term_step"] = np.where(want["flags"] != 0, S["step"], -1)
+        want["rls_skip"] = np.zeros(len(idx), np.int64)
+        H.compare_states(got, want, tol, what="group %r" % (key[:3],))
+        tr = traj.cpu().numpy()[0]
+        acts, rews = tr[8:10].T, tr[10:12].T
+        for a, b in ((acts, g["actions"][idx]), (rews, g["rewards"][idx])):
+            ok = (np.abs(a - b) <= tol * np.maximum(np.abs(b), 1e-3)) | (np.isnan(a) & np.isnan(b))
+            assert ok.all()
+        total += len(idx)
+        flagged += int((want["flags"] != 0).sum())
+    assert total == g["pre_step"].shape[0] and flagged >= 2
+
+
+# ------------------------------------------------------------------------------------------------------
+# main_3dof.py scenario, free running (BASELINE config 1 as the parity case)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,mode,stable", [("seed2_all64.npz", "all64", 6000), ("seed2_all64_w32.npz", "all64", 4500),
+                                              ("seed2_ref32.npz", "ref32", 4500)])
+def test_scenario_free_running(h3, name, mode, stable):
+    g = H.load(name)
+    snaps = H.snaps_from(g, "snap_")
+    ticks = [int(x) for x in g["snap_ticks"]]
+    S = O.state_from_snapshots([snaps[0]], mode)
+    S["theta_trim"][:] = snaps[0]["state"][4]
+    cfg = O.default_config()
+    loop = H.make_loop(S, cfg, mode, ticks_per_launch=500)
+    n = int(g["ticks_run"])
+    tol = TOL64 if mode == "all64" else 2e-4
+    traj = []
+    k = 0
+    for stop in [t for t in ticks if 0 < t <= stable] + [n]:
+        traj.append(loop.run(stop - k, record=1).cpu().numpy()[:, :, 0])
+        k = stop
+        if stop in ticks and stop <= stable:
+            got = H.loop_state(loop)
+            want = O.state_from_snapshots([snaps[ticks.index(stop)]], mode)
+            want["flags"] = np.zeros(1, np.int64)
+            want["term_step"] = np.full(1, -1, np.int64)
+            H.compare_states(got, want, tol, what="tick %d" % stop)
+    traj = np.concatenate(traj)
+    alive = traj[:, 12] > 0
+    assert int(alive.sum()) == n
+    m = min(stable, n)
+    scale = np.maximum(np.abs(g["state"][:m, :6]), 1e-3)
+    assert float(np.max(np.abs(traj[:m, :6] - g["state"][:m, :6]) / scale)) <= tol
+    assert float(np.max(np.abs(traj[:m, 8:10] - g["actions"][:m]))) <= tol
+    assert float(np.max(np.abs(traj[:m, 10:12] - g["rewards"][:m]))) <= tol * 10
+    assert float(np.max(np.abs(traj[:m, 7] - g["ref"][:m, 1]))) <= 1e-15
+    # bit-exact termination bookkeeping (pitch > 90 deg ends two of the three scenarios)
+    assert int(loop.env.step_count[0]) == int(g["ticks_run"])
+    assert int(loop.env.flags[0]) == int(g["flags"])
+    assert int(loop.env.term_step[0]) == int(g["term_step"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# un-fused reference API: the statements of main_3dof.py:131-161 against the batched classes
+# ------------------------------------------------------------------------------------------------------
+def test_main_3dof_statements_drop_in(h3, tmp_path):
+    import json
+    g = H.load("seed2_ref32.npz")
+    cfgfile = tmp_path / "config_3dof.json"
+    cfgfile.write_text(json.dumps({"dt": 0.01, "training": {"trim_speed": 10}, "env": {"tasks": {
+        "sinusoid": {"kp": 0, "ki": 0, "kd": 0, "ref": 20, "period": 30}}}}))
+    torch.manual_seed(2)
+    np.random.seed(2)
+    agent_parameters = {
+        'col': dict(control_channel='col', discount_factor=0.9, n_hidden_actor=10, nn_stdev_actor=0.1,
+                    learning_rate_actor=0.1, action_scaling=5, n_hidden_critic=10, nn_stdev_critic=0.1,
+                    learning_rate_critic=0.1, tau_target_critic=0.01, tracked_state=1, ac_states=[3],
+                    reward_weight=0.01),
+        'lon': dict(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                    learning_rate_actor=0.2, action_scaling=15, n_hidden_critic=6, nn_stdev_critic=0.2,
+                    learning_rate_critic=0.2, tau_target_critic=1, tracked_state=4, ac_states=[5])}
+    rls_parameters = {'state_size': 7, 'action_size': 2, 'gamma': 1, 'covariance': 10 ** 4, 'constant': False}
+    dt, t_max = 0.01, 120
+    # ---- main_3dof.py:59-71 verbatim (modulo the module prefix) ----
+    env = h3.Helicopter3DOF(dt=dt, t_max=t_max)
+    env.setup_from_config(task="sinusoid", config_path=str(cfgfile))
+    obs, trim_action = env.reset(v_initial=10)
+    ref = env.get_ref()
+    RLS = h3.RecursiveLeastSquares(**rls_parameters)
+    collective_pid = h3.CollectivePID3DOF(h_ref=5, dt=dt)
+    agent_col = h3.DHPAgent(**agent_parameters['col'], action_network_final_layer='tanh', dtype=torch.float32)
+    agent_lon = h3.DHPAgent(**agent_parameters['lon'], action_network_final_layer='tanh', dtype=torch.float32)
+    agents = [agent_col, agent_lon]
+    # the constructor consumed the global RNG like the reference's: identical initial weights
+    assert np.array_equal(agent_lon.actor.fc1.weight[:, :, 0].cpu().double().numpy(), g["snap_lon_a_w1"][0])
+    assert np.array_equal(agent_col.critic.fc2.weight[:, :, 0].cpu().double().numpy(), g["snap_col_c_w2"][0])
+    rewards = np.zeros(2)
+    for step in range(60):
+        # ---- main_3dof.py:132-161 ----
+        if step < 30:       # switch brought forward (6000 in the script) so both branches run
+            actions = [collective_pid(obs), trim_action[1] + agent_lon.get_action(obs, ref)]
+        else:
+            actions = [trim_action[0] + agent_col.get_action(obs, ref),
+                       trim_action[1] + agent_lon.get_action(obs, ref)]
+        actions = torch.stack([a.double().reshape(-1) for a in actions])
+        next_obs, _, done = env.step(actions)
+        next_ref = env.get_ref()
+        RLS.update(obs, actions, next_obs)
+        rewards_lon, dr_ds = agents[1].get_reward(next_obs, ref)
+        F, G = agents[1].get_transition_matrices(RLS)
+        agents[1].update_networks(obs, next_obs, ref, next_ref, dr_ds, F, G)
+        if step >= 30:
+            rewards_col, dr_ds = agents[0].get_reward(next_obs, ref)
+            F, G = agents[0].get_transition_matrices(RLS)
+            agents[0].update_networks(obs, next_obs, ref, next_ref, dr_ds, F, G)
+        if step < 30:       # the golden scenario switches at 6000: compare the shared prefix
+            assert abs(float(actions[1, 0]) - g["actions"][step, 1]) < 1e-7
+            assert abs(float(actions[0, 0]) - g["actions"][step, 0]) < 1e-7
+            assert abs(float(rewards_lon[0]) - g["rewards"][step, 1]) < 1e-9
+        obs = next_obs
+        ref = next_ref
+    assert not bool(done.any())
+    # cross-check the un-fused objects against the fused kernel from the same start
+    S = O.state_from_snapshots([H.snaps_from(g, "snap_")[0]], "ref32")
+    S["theta_trim"][:] = float(env.trimmed_state[4, 0])
+    cfg = O.default_config()
+    cfg["switch_step"] = 30
+    loop = H.make_loop(S, cfg, "ref32")
+    loop.run(60)
+    fused = H.loop_state(loop)
+    assert H.relerr(fused["state"][:, 0], obs[:, 0].cpu().numpy(), floor=1e-6) < 1e-6
+    assert H.relerr(fused["lon_a_w1"][..., 0], agent_lon.actor.fc1.weight[..., 0].cpu().double().numpy(), 1e-3) < 1e-4
+    assert H.relerr(fused["col_c_w2"][..., 0], agent_col.critic.fc2.weight[..., 0].cpu().double().numpy(), 1e-3) < 1e-4
+    assert H.relerr(fused["rls_W"][..., 0], RLS.W[..., 0].cpu().numpy(), 1e-3) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# random batch against the oracle (per-episode hyper-parameters, trims, all tasks)
+# ------------------------------------------------------------------------------------------------------
+def _random_problem(n, seed, task="sinusoid", per_episode=True, switch_step=40):
+    rng = np.random.default_rng(seed)
+    cfg = O.default_config()
+    cfg["task"] = task
+    cfg["switch_step"] = switch_step
+    cfg["excitation"] = H.excitation()
+    if task == "velocity":
+        cfg.update(env_kp=-1.0, env_ki=-0.05, env_kd=0.0, env_ref=30.0)
+    elif task == "stop_over_point":
+        cfg.update(env_kp=-0.3, env_ki=0.0, env_kd=2.0, env_ref=1000.0)
+    if per_episode:     # main.py:107-112-style grid mapped to 3-DOF magnitudes
+        for name in ("col", "lon"):
+            hp = cfg["agents"][name]
+            hp["tau"] = rng.choice([0.01, 0.1, 1.0], n)
+            hp["gamma"] = rng.choice([0.6, 0.7, 0.8, 0.9, 0.95, 0.99], n)
+            hp["lr_a"] = rng.choice([0.05, 0.1, 0.2, 0.4], n)
+            hp["lr_c"] = rng.choice([0.05, 0.1, 0.2, 0.4], n)
+            hp["w_r"] = rng.choice([0.01, 0.1, 1.0], n)
+            hp["scale"] = np.deg2rad(rng.choice([5.0, 10.0, 15.0], n))
+    v = rng.uniform(5, 25, n)
+    S = O.init_state(n, v_initial=v, cfg=cfg, seed=seed)
+    return S, cfg
+
+
+@pytest.mark.parametrize("task,per_episode", [("sinusoid", True), ("sinusoid", False), ("velocity", True),
+                                              ("stop_over_point", False)])
+def test_random_batch_vs_oracle(h3, task, per_episode):
+    n, n_ticks = 1024, 120
+    S, cfg = _random_problem(n, seed=5, task=task, per_episode=per_episode)
+    loop = H.make_loop({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in S.items()}, cfg,
+                       ticks_per_launch=50)
+    loop.run(n_ticks)
+    got = H.loop_state(loop)
+    O.run(S, cfg, n_ticks, "all64")
+    H.compare_states(got, S, 1e-8, what=task)      # 120 free-running ticks accumulate a few ulp per tick
+    st = loop.stats()
+    assert st["n"] == n and st["n_alive"] == int((S["flags"] == 0).sum())
+    assert abs(st["sum_r_lon"] - S["ret"][1].sum()) <= 1e-9 * max(1.0, abs(S["ret"][1].sum()))
+    assert st["sum_ticks"] == float(S["step"].sum())
+
+
+# ------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE scale (config 3: 1,048,576 episodes)
+# ------------------------------------------------------------------------------------------------------
+def _clone_state(S):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in S.items()}
+
+
+def test_full_size_replicated_episodes_agree_bitwise(h3):
+    """1,048,576 copies of the same episode must stay bit-identical whatever lane / block / SM runs them,
+    and must equal the single-episode run; the statistics epilogue must equal the torch reductions."""
+    n = 1 << 20
+    g = H.load("seed2_all64.npz")
+    snap = H.snaps_from(g, "snap_")[0]
+    cfg = O.default_config()
+    cfg["switch_step"] = 60
+    S1 = O.state_from_snapshots([snap], "all64")
+    S1["theta_trim"][:] = snap["state"][4]
+    Sn = {k: np.repeat(v, n, axis=-1) for k, v in S1.items()}
+    big = H.make_loop(Sn, cfg, ticks_per_launch=40)
+    one = H.make_loop(_clone_state(S1), cfg, ticks_per_launch=40)
+    big.run(120)
+    one.run(120)
+    for name in ("state", "corr_u", "t_ep"):
+        a = getattr(big.env, name)
+        assert bool((a == a[..., :1]).all()), name
+    for t_big, t_one in ((big.env.state, one.env.state), (big.rls._W, one.rls._W), (big.rls._cov, one.rls._cov),
+                         (big.agent_lon.net, one.agent_lon.net), (big.agent_col.net, one.agent_col.net),
+                         (big.pid.hdot_corr, one.pid.hdot_corr)):
+        assert bool((t_big == t_big[..., :1]).all())
+        assert torch.equal(t_big[..., :1], t_one)
+    st = big.stats()
+    assert st["n"] == n and st["n_alive"] == n and st["sum_ticks"] == 120.0 * n
+    assert abs(st["sum_r_lon"] - float(big.acc[1].sum())) <= 1e-9 * abs(st["sum_r_lon"])
+    # a batch is the union of its shards: launch-split and partition invariance
+    half = H.make_loop({k: v[..., :1000] for k, v in Sn.items()}, cfg, ticks_per_launch=120)
+    half.run(120)
+    assert torch.equal(half.env.state, big.env.state[:, :1000])
+    assert torch.equal(half.agent_col.net, big.agent_col.net[:, :1000])
+
+
+def test_f32_path_tolerance(h3):
+    """Full-fp32 path (model, PID, RLS and networks in fp32): trajectory RMS error against the reference's
+    mixed-precision run over the first 1000 ticks of the main_3dof.py scenario.  Stated tolerance: relative
+    RMS error <= 2e-2 on u, theta, q (RLS with cov0 = 1e4 in fp32 is the limiting factor)."""
+    g = H.load("seed2_ref32.npz")
+    snap = H.snaps_from(g, "snap_")[0]
+    S = O.state_from_snapshots([snap], "ref32")
+    S["theta_trim"][:] = snap["state"][4]
+    loop = H.make_loop(S, O.default_config(), "f32", env_dtype=torch.float32, ticks_per_launch=500)
+    traj = loop.run(1000, record=1).cpu().double().numpy()[:, :, 0]
+    assert (traj[:, 12] > 0).all()
+    for col in (2, 4, 5):
+        ref = g["state"][:1000, col]
+        rms = np.sqrt(np.mean((traj[:, col] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+        assert rms <= 2e-2, (col, rms)

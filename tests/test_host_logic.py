@@ -1,0 +1,191 @@
+"""CPU: host-side logic and the C-ABI boundary (no GPU compute): the library loads and exports every symbol
+include/heli3dof.h declares, the ctypes mirrors match the C structs, host-made tables are the reference's
+values, object plumbing / checkpoints work on CPU tensors, compute calls fail loudly without a GPU."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import msc_thesis_b200 as h3
+from msc_thesis_b200 import _lib as L
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "heli3dof.h")
+
+
+def test_library_exports_every_declared_symbol():
+    text = open(HEADER).read()
+    declared = set(re.findall(r"\b(h3_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = h3.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.h3_version() == 100
+    assert lib.h3_stats_scratch_bytes(64) == 16 + 2 * 8 * 8
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    src = tmp_path / "layout.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "heli3dof.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(H3EnvParams), sizeof(H3AgentHyper), sizeof(H3Config), sizeof(H3Batch), sizeof(H3Traj));
+  printf("%zu %zu %zu %zu %zu\\n", offsetof(H3Config, env_dtype), offsetof(H3Config, rls_gamma), offsetof(H3Config, switch_step), offsetof(H3Config, col), offsetof(H3Config, lon));
+  printf("%zu %zu %zu %zu\\n", offsetof(H3Batch, state), offsetof(H3Batch, rls_skip), offsetof(H3Batch, step), offsetof(H3Batch, acc));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    lines = subprocess.check_output([str(exe)]).decode().split("\n")
+    sizes = [int(x) for x in lines[0].split()]
+    assert sizes == [ctypes.sizeof(c) for c in (L.H3EnvParams, L.H3AgentHyper, L.H3Config, L.H3Batch, L.H3Traj)]
+    offs = [int(x) for x in lines[1].split()]
+    assert offs == [getattr(L.H3Config, k).offset for k in ("env_dtype", "rls_gamma", "switch_step", "col", "lon")]
+    offs = [int(x) for x in lines[2].split()]
+    assert offs == [getattr(L.H3Batch, k).offset for k in ("state", "rls_skip", "step", "acc")]
+
+
+def test_default_env_params_are_the_reference_constants():
+    p = L.default_env_params(0.01)
+    assert (p.g, p.cl_alpha, p.blade_solidity, p.lock_number, p.cds, p.mass) == (9.81, 5.7, 0.075, 6, 1.5, 2200)
+    assert (p.rho, p.v_tip, p.rotor_radius, p.iy, p.mast, p.tau, p.dt) == (1.225, 200, 7.32, 10615, 1, 0.1, 0.01)
+    assert p.omega == 200 / 7.32 and p.area == np.pi * 7.32 ** 2
+
+
+def test_reference_table_is_the_references_own_signal():
+    """Entry j of the host-made table is get_ref() after tick j; the golden `ref` column holds get_ref() before
+    tick k (main_3dof.py:62, :142) -> table[j] == golden[j + 1], bit for bit."""
+    g = H.load("seed2_all64.npz")
+    tab, t_end = h3.sinusoid_ref_table(0, 0.01, 3000)
+    assert np.array_equal(tab[:2999], g["ref"][1:3000, 1])
+    assert t_end == g["t"][2999]
+    # chained launches continue the same clock
+    tab2, _ = h3.sinusoid_ref_table(t_end, 0.01, 100)
+    assert np.array_equal(tab2, g["ref"][3001:3101, 1])
+
+
+def test_excitation_closed_form():
+    assert np.abs(h3.excitation_signal(1000) - H.excitation()).max() < 1e-17
+    assert h3.excitation_signal(1000).shape == (1000, 2)
+
+
+def test_shard_range_partitions_the_episode_index():
+    for n, w in ((8388608, 8), (10, 3), (5, 8), (1, 1)):
+        spans = [h3.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    with pytest.raises(ValueError):
+        h3.shard_range(10, 3, 3)
+
+
+def test_agent_constructor_reproduces_reference_weights():
+    """torch.manual_seed(2) + the constructor order of main_3dof.py:69-70 gives the reference's initial weights
+    (the golden ref32 snapshot), because init='reference' consumes the global RNG exactly like agents.py."""
+    g = H.load("seed2_ref32.npz")
+    torch.manual_seed(2)
+    kw = dict(action_network_final_layer='tanh', device="cpu", dtype=torch.float32)
+    col = h3.DHPAgent(control_channel='col', discount_factor=0.9, n_hidden_actor=10, nn_stdev_actor=0.1,
+                      learning_rate_actor=0.1, action_scaling=5, n_hidden_critic=10, nn_stdev_critic=0.1,
+                      learning_rate_critic=0.1, tau_target_critic=0.01, tracked_state=1, ac_states=[3],
+                      reward_weight=0.01, **kw)
+    lon = h3.DHPAgent(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                      learning_rate_actor=0.2, action_scaling=15, n_hidden_critic=6, nn_stdev_critic=0.2,
+                      learning_rate_critic=0.2, tau_target_critic=1, tracked_state=4, ac_states=[5], **kw)
+    for name, ag in (("col", col), ("lon", lon)):
+        nets = (ag.actor.fc1, ag.actor.fc2, ag.critic.fc1, ag.critic.fc2, ag.target_critic.fc1, ag.target_critic.fc2)
+        for key, layer in zip(("a_w1", "a_w2", "c_w1", "c_w2", "t_w1", "t_w2"), nets):
+            assert np.array_equal(layer.weight[..., 0].double().numpy(), g["snap_%s_%s" % (name, key)][0]), (name, key)
+    assert lon.actor.scale == np.deg2rad(15) and [p.shape for p in lon.networks[1].parameters()] == [(6, 2, 1), (2, 6, 1)]
+    assert lon.control_channel_str == 'lon' and lon.control_channel_num == 1
+    with pytest.raises(NotImplementedError):
+        h3.DHPAgent(control_channel='lon', discount_factor=0.9, n_hidden_actor=6, nn_stdev_actor=0.1,
+                    learning_rate_actor=0.1, action_scaling=5, action_network_final_layer='relu', n_hidden_critic=6,
+                    nn_stdev_critic=0.1, learning_rate_critic=0.1, tau_target_critic=1, tracked_state=4,
+                    ac_states=[5], device="cpu")
+
+
+def test_checkpoints_round_trip(tmp_path):
+    ag = h3.DHPAgent(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                     learning_rate_actor=0.2, action_scaling=15, action_network_final_layer='tanh',
+                     n_hidden_critic=6, nn_stdev_critic=0.2, learning_rate_critic=0.2, tau_target_critic=1,
+                     tracked_state=4, ac_states=[5], n_envs=3, device="cpu", init="batched")
+    ag.save(str(tmp_path / "lon.pt"))
+    other = h3.DHPAgent(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                        learning_rate_actor=0.2, action_scaling=15, action_network_final_layer='tanh',
+                        n_hidden_critic=6, nn_stdev_critic=0.2, learning_rate_critic=0.2, tau_target_critic=1,
+                        tracked_state=4, ac_states=[5], n_envs=3, device="cpu", init="batched")
+    assert not torch.equal(ag.net, other.net)
+    other.load(str(tmp_path / "lon.pt"))
+    assert torch.equal(ag.net, other.net)
+    # n_envs == 1 writes the reference's checkpoint format (agents.py:198-203): plain (out, in) matrices
+    one = h3.DHPAgent(control_channel='lon', discount_factor=0.99, n_hidden_actor=6, nn_stdev_actor=0.2,
+                      learning_rate_actor=0.2, action_scaling=15, action_network_final_layer='tanh',
+                      n_hidden_critic=6, nn_stdev_critic=0.2, learning_rate_critic=0.2, tau_target_critic=1,
+                      tracked_state=4, ac_states=[5], device="cpu")
+    one.save(str(tmp_path / "one.pt"))
+    ck = torch.load(str(tmp_path / "one.pt"))
+    assert ck["actor_state_dict"]["fc1.weight"].shape == (6, 2) and ck["critic_state_dict"]["fc2.weight"].shape == (2, 6)
+    other.load(str(tmp_path / "one.pt"))          # a reference-format file broadcasts over the batch
+    assert torch.equal(other.actor.fc1.weight[..., 2], one.actor.fc1.weight[..., 0])
+
+    rls = h3.RecursiveLeastSquares(state_size=7, action_size=2, gamma=1, covariance=10 ** 4, constant=False,
+                                   n_envs=2, device="cpu")
+    assert rls.W.shape == (9, 7, 2) and rls.cov.shape == (9, 9, 2) and rls.skip_update
+    assert torch.equal(rls.cov[..., 1], torch.eye(9, dtype=torch.float64) * 1e4)
+    assert rls.gradient_state().shape == (7, 7, 2) and rls.gradient_action().shape == (7, 2, 2)
+    rls.W = torch.arange(63, dtype=torch.float64).reshape(9, 7)
+    assert float(rls.gradient_state()[2, 5, 1]) == 5 * 7 + 2        # F = W[:7].T  (model.py:72)
+    assert float(rls.gradient_action()[3, 1, 0]) == 8 * 7 + 3       # G = W[7:9].T (model.py:76)
+    rls.save(str(tmp_path / "rls.pkl"))
+    back = h3.RecursiveLeastSquares.load(str(tmp_path / "rls.pkl"), device="cpu")
+    assert torch.equal(back.W, rls.W) and torch.equal(back.cov, rls.cov) and back.assume_symmetric
+    c = torch.eye(9, dtype=torch.float64)
+    c[0, 1] = 0.5
+    back.cov = c
+    assert not back.assume_symmetric                                # non-symmetric input -> general kernel
+    with pytest.raises(NotImplementedError):
+        h3.RecursiveLeastSquares(state_size=15, action_size=2, constant=False, device="cpu")
+
+
+def test_config_parsing_and_loud_failure_without_gpu(tmp_path):
+    cfg = {"dt": 0.02, "training": {"trim_speed": 10},
+           "env": {"tasks": {"velocity": {"kp": -1, "ki": -0.05, "kd": 0, "ref": 30}}}}
+    path = tmp_path / "c.json"
+    path.write_text(json.dumps(cfg))
+    env = h3.Helicopter3DOF(dt=0.01, t_max=120, n_envs=2, device="cpu")
+    env.task = "velocity"
+    env._set_pid_weights(cfg)
+    assert env.pid_weights == (-1, -0.05, 0) and env.ref == 30
+    assert env.state.shape == (7, 2) and env.episode_ticks == 12000
+    env.task = "hover"
+    with pytest.raises(NotImplementedError):
+        env._set_pid_weights(cfg)
+    # no CPU fallback: anything that computes needs the CUDA library AND a CUDA tensor
+    env.task = "velocity"
+    with pytest.raises(h3.H3Error):
+        env.setup_from_config("velocity", str(path))
+    assert env.dt == 0.02                                           # the json was read before the compute call
+    pid = h3.CollectivePID3DOF(h_ref=5, dt=0.01)
+    with pytest.raises(h3.H3Error):
+        pid(torch.zeros(7, 2, dtype=torch.float64))
+
+
+def test_launch_plan_splits_at_the_phase_switch():
+    class _E:
+        n_envs, device, dtype = 1, torch.device("cpu"), torch.float64
+    loop = h3.ClosedLoop3DOF.__new__(h3.ClosedLoop3DOF)
+    loop.k, loop.switch_step, loop.ticks_per_launch = 5500, 6000, 400
+    assert loop.plan(1000) == [(0, 400), (400, 100), (500, 400), (900, 100)]
+    loop.k = 6000
+    assert loop.plan(500) == [(0, 400), (400, 100)]
+    loop.k = None
+    assert loop.plan(300) == [(0, 300)]
