@@ -94,7 +94,7 @@ typedef struct H3Config {
     double pid_kp, pid_ki, pid_kd, pid_href;     /* PID.py:6-14, main_3dof.py:68 */
     double rls_gamma;                            /* model.py:14 */
     int32_t rls_symmetric;   /* 1: covariance known symmetric, kernel keeps the upper triangle on chip */
-    int32_t store_policy;    /* 0: library default; 1: per-thread local arrays; 2: shared-memory tile */
+    int32_t store_policy;    /* reserved (0) */
     int32_t switch_step;     /* tick at which the collective agent takes over (main_3dof.py:127-137) */
     int32_t update_lon;      /* main_3dof.py:87 (always 1 there) */
     int32_t win_lo, win_hi;  /* score window [lo, hi) on the lon reward, train.py:256 */
@@ -229,9 +229,9 @@ int h3_closed_loop(const H3Config* cfg, const H3Batch* b, int32_t step0, const d
 int64_t h3_stats_scratch_bytes(int64_t n);
 
 /* Occupancy facts of the fused kernel chosen for cfg (for bench / DESIGN.md): threads per block,
- * dynamic shared memory per block, resident blocks per SM, registers per thread. */
+ * dynamic shared memory per block, resident blocks per SM, registers per thread, episodes per warp. */
 int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int32_t* smem_bytes,
-                        int32_t* blocks_per_sm, int32_t* regs);
+                        int32_t* blocks_per_sm, int32_t* regs, int32_t* lanes_per_warp);
 
 /* Roofline denominators measured with dependent-free FMA chains: runs `iters` x 8 independent
  * FMA chains per thread on a full grid; flops = 2 * fma count is written to *flops_out (host). The caller

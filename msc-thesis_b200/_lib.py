@@ -95,7 +95,7 @@ def lib():
     L.h3_closed_loop.argtypes = [cfgp, batp, i32, vp, vp, i32, i32, C.POINTER(H3Traj), vp, vp, vp]
     L.h3_stats_scratch_bytes.argtypes = [i64]
     L.h3_stats_scratch_bytes.restype = i64
-    L.h3_closed_loop_info.argtypes = [cfgp, i32] + [C.POINTER(i32)] * 4
+    L.h3_closed_loop_info.argtypes = [cfgp, i32] + [C.POINTER(i32)] * 5
     L.h3_fma_peak.argtypes = [i32, i32, vp, dp, vp]
     for name in ("h3_trim", "h3_env_step", "h3_get_ref", "h3_pid_collective", "h3_rls_update", "h3_rls_predict",
                  "h3_agent_action", "h3_agent_reward", "h3_agent_transition", "h3_agent_update", "h3_closed_loop",

@@ -61,7 +61,7 @@ class ClosedLoop3DOF:
         self.ref2 = ref[[1, 4]].to(env.dtype).contiguous() if ref.shape[0] == 7 else ref.to(env.dtype).contiguous()
         self.acc = torch.zeros(3, n, dtype=torch.float64, device=self.device)
         self.stats_dev = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
-        nbytes = 16 + ((n + 31) // 32) * L.N_STATS * 8
+        nbytes = int(L.lib().h3_stats_scratch_bytes(n))
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
         self.k = 0                  # host copy of the lockstep tick index (None: heterogeneous batch)
         self.launches = 0
@@ -165,6 +165,6 @@ class ClosedLoop3DOF:
     def info(self, phase2=True):
         """Occupancy facts of the kernel variant run() would launch (block, smem, blocks/SM, registers)."""
         cfg = self._config(L.REF_TABLE)
-        vals = [C.c_int32() for _ in range(4)]
+        vals = [C.c_int32() for _ in range(5)]
         L.check(L.lib().h3_closed_loop_info(byref(cfg), 1 if phase2 else 0, *[C.byref(v) for v in vals]))
-        return dict(zip(("block", "smem_bytes", "blocks_per_sm", "regs"), (v.value for v in vals)))
+        return dict(zip(("block", "smem_bytes", "blocks_per_sm", "regs", "lanes_per_warp"), (v.value for v in vals)))

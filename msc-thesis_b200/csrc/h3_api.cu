@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct GlobalVec {
+    static constexpr bool kFence = false;
     T* p;
     int64_t ld;
     H3_DEV T& operator[](int i) { return p[(int64_t)i * ld]; }
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     const NT s0 = (NT)state[h.ac_state * ld + e];
     const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
     NT hh[NH], f;
-    out[e] = actor_forward<NT, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
+    out[e] = actor_forward<NT, NH, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
 }
 
 template <typename ET, typename NT, int NH>
@@ -299,9 +300,10 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
         for (int j = 0; j < 2; ++j) F[i][j] = Fm[(i * 2 + j) * ld + e];
         G[i] = Gm[i * ld + e];
     }
-    NT hh[NH], f;
-    (void)actor_forward<NT, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
-    agent_update<NT, NH, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f);
+    NT hh[NH], scr[NH], f;
+    (void)actor_forward<NT, NH, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
+    agent_update<NT, NH, NH, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f,
+                                    scr);
 }
 
 // get_reward (agents.py:123-128) and get_transition_matrices (agents.py:130-140)
@@ -692,12 +694,12 @@ int h3_closed_loop(const H3Config* cfg, const H3Batch* b, int32_t step0, const d
 }
 
 int64_t h3_stats_scratch_bytes(int64_t n) {
-    const int64_t blocks = (n + 31) / 32;
+    const int64_t blocks = (n + 7) / 8;     // upper bound on the grid of any kernel variant (>= 8 episodes per warp)
     return 16 + blocks * H3_N_STATS * (int64_t)sizeof(double);
 }
 
 int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int32_t* smem_bytes,
-                        int32_t* blocks_per_sm, int32_t* regs) {
+                        int32_t* blocks_per_sm, int32_t* regs, int32_t* lanes_per_warp) {
     if (!cfg) {
         set_error("h3_closed_loop_info: null config");
         return H3_E_ARG;
@@ -712,6 +714,7 @@ int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int
     if (smem_bytes) *smem_bytes = info.smem_bytes;
     if (blocks_per_sm) *blocks_per_sm = info.blocks_per_sm;
     if (regs) *regs = info.regs;
+    if (lanes_per_warp) *lanes_per_warp = info.lanes_per_warp;
     return H3_OK;
 }
 

@@ -2,15 +2,16 @@
 // episode, all mutable episode state resident on chip between the entry load and the exit store.
 //
 // Data movement: every per-episode field is a `[field][ld]` SoA row, so a warp's
-// load/store of one field is one fully coalesced 256 B (fp64) transaction.  HBM traffic per launch is
-// 2 * S_ep per episode regardless of n_ticks; the per-tick work never touches global memory except
-// for the optional trajectory rows.
+// load/store of one field is one fully coalesced transaction.  HBM traffic per launch is 2 * S_ep per
+// episode regardless of n_ticks; the per-tick work never touches global memory except for the
+// optional trajectory rows.
 //
-// On-chip placement (STORE policy):
-//   STORE_LOCAL : everything in per-thread arrays (registers, overflow in L1-backed local memory)
-//   STORE_SMEM  : RLS covariance + weights and the collective agent's networks in a [row][BLOCK]
-//                 shared-memory tile (conflict-free: consecutive threads hit consecutive words), the
-//                 model state / PID / previous regressors / cyclic agent's networks in registers.
+// On-chip placement: an episode's ~2.3-2.7 KB of fp64 state does not fit a thread's 255 registers, and
+// 128 threads x that state is more than the 227 KB of shared memory -- registers AND shared memory
+// together hold it.  Each warp owns a [row][LANES] shared-memory tile (conflict-free: consecutive lanes hit
+// consecutive words); the PLACE mask says which groups live in the tile, the rest stays in registers.
+// LANES <= 32 episodes per warp: trading a few idle lanes for shared-memory room per episode keeps four
+// warps (one per SM sub-partition) resident without a single local-memory spill.
 #pragma once
 #include <type_traits>
 
@@ -18,9 +19,10 @@
 
 namespace h3 {
 
-enum { STORE_LOCAL = 0, STORE_SMEM = 1 };
+// PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
+enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
-constexpr int TICK_CHUNK = 32;      // ticks of reference / excitation staged through smem at a time
+constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
 template <typename ET, typename NT>
 struct LoopParams {
@@ -83,15 +85,8 @@ struct WMatD : WMat<T, Vec> {       // + runtime-indexed read (shared memory: pl
     H3_DEV T dyn(int i, int j) { return this->v[i * 7 + j]; }
 };
 
-template <typename T>
-struct WMatLocal {                  // local-array flavour: runtime index goes through local memory
-    T v[63];
-    H3_DEV T& operator()(int i, int j) { return v[i * 7 + j]; }
-    H3_DEV T dyn(int i, int j) { return v[i * 7 + j]; }
-};
-
-template <int BLOCK>
-H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [BLOCK/32][H3_N_STATS] */) {
+template <int NWARP>
+H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [NWARP][H3_N_STATS] */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < H3_N_STATS; ++i) {
@@ -104,104 +99,165 @@ H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [BLOCK/32]
 #pragma unroll
         for (int i = 0; i < H3_N_STATS; ++i) {
             double a = 0.0;
-            for (int w2 = 0; w2 < BLOCK / 32; ++w2) a += sh[w2 * H3_N_STATS + i];
+            for (int w2 = 0; w2 < NWARP; ++w2) a += sh[w2 * H3_N_STATS + i];
             v[i] = a;
         }
     }
 }
+
+// view of a group starting at element `off`
+template <typename Vec, typename T>
+struct SubVec {
+    Vec& v;
+    int off;
+    H3_DEV T& operator[](int i) { return v[off + i]; }
+};
+
+// group storage: a strided column of the warp's tile, or registers
+template <typename T, int N, int LANES, bool IN_SMEM>
+struct Group : std::conditional<IN_SMEM, SmemVec<T, N, LANES>, LocalVec<T, N>>::type {};
+
+template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int PLACE, int LANES>
+struct LoopLayout {
+    static constexpr int NCOV = SYM ? 45 : 81;
+    static constexpr int NNL = (TAU1L ? 7 : 11) * NHL, NNC = 11 * NHC;
+    // stash: forward activations kept from get_action to the update (h[NH], f, s0, s1) + NH words of
+    // scratch for the critic's hidden layer between the two passes of agent_update
+    static constexpr int N_STASH = ((PLACE & P_STASHL) ? 2 * NHL + 3 : 0) + ((COL && (PLACE & P_STASHC)) ? 2 * NHC + 3 : 0);
+    // bytes of one episode in the tile
+    static constexpr size_t bytes_per_lane =
+        sizeof(ET) * (NCOV + 63) + (COL ? sizeof(NT) * NNC : 0) + ((PLACE & P_LON) ? sizeof(NT) * NNL : 0) +
+        ((PLACE & P_PREV) ? sizeof(ET) * 9 : 0) + ((PLACE & P_MISC) ? sizeof(double) * 4 + sizeof(ET) * 4 : 0) +
+        sizeof(NT) * N_STASH + (HYP ? sizeof(NT) * 10 + sizeof(ET) * 2 : 0);
+    static constexpr size_t tile_bytes = ((bytes_per_lane * LANES + 15) / 16) * 16;
+    __host__ __device__ static constexpr size_t head_bytes(int warps) {
+        return sizeof(double) * (3 * TICK_CHUNK + warps * H3_N_STATS);
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int warps) {
+        return head_bytes(warps) + tile_bytes * warps;
+    }
+};
 
 // Template flags
 //   COL   : the launch contains ticks >= switch_step (collective agent acts and learns); false -> its
 //           networks never leave HBM (phase 1 of main_3dof.py, PID collective)
 //   SYM   : covariance symmetric -> upper triangle on chip (45 instead of 81 words)
 //   HYP   : per-episode hyper-parameter rows present (sweeps); false -> launch-uniform values are read
-//           from the constant bank and cost no registers
+//           from the constant bank and cost neither registers nor shared memory
 //   TAU1L : tau_target_critic == 1 for the cyclic agent (main_3dof.py:44) -> its target critic is not
 //           kept on chip (see agent_update)
-template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int STORE,
-          int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopParams<ET, NT> P) {
-    constexpr int NCOV = SYM ? 45 : 81;
-    constexpr int NNL = (TAU1L ? 7 : 11) * NHL, NNC = 11 * NHC;
+//   PLACE : which optional groups live in shared memory (P_* bits); LANES episodes per warp; WARPS per block
+//   UL/UC : hidden units per chunk in the cyclic / collective agent's loops (see h3_tick.cuh); a chunked
+//           agent (U < NH) needs its networks and stash in shared memory
+template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int PLACE, int LANES,
+          int WARPS, int UL, int UC>
+__global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopParams<ET, NT> P) {
+    static_assert(UL == NHL || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
+    static_assert(UC == NHC || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");
+    typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, LANES> LY;
+    constexpr int NCOV = LY::NCOV, NNL = LY::NNL, NNC = LY::NNC;
+    constexpr int BLOCK = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // ---- shared memory carve-up: staging tables first, then the per-thread tiles ----
     double* sh_ref = reinterpret_cast<double*>(smem_raw);               // [TICK_CHUNK]
     double* sh_exc = sh_ref + TICK_CHUNK;                               // [TICK_CHUNK][2]
-    double* sh_red = sh_exc + 2 * TICK_CHUNK;                           // [BLOCK/32][H3_N_STATS]
-    unsigned char* tile = reinterpret_cast<unsigned char*>(sh_red + (BLOCK / 32) * H3_N_STATS);
+    double* sh_red = sh_exc + 2 * TICK_CHUNK;                           // [WARPS][H3_N_STATS]
 
-    const int tid = threadIdx.x;
-    const int64_t e = (int64_t)blockIdx.x * BLOCK + tid;
-    const bool valid = e < P.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t e = ((int64_t)blockIdx.x * WARPS + warp) * LANES + lane;
+    const bool valid = (lane < LANES) && (e < P.n);
     const int64_t ld = P.ld;
-    const int64_t ec = valid ? e : 0;          // clamp so that invalid lanes read in-bounds (never store)
+    const int64_t ec = valid ? e : 0;          // idle lanes read episode 0 (in bounds) and never store
+    const int lc = lane < LANES ? lane : 0;     // ... and alias lane 0's tile column (never written: flags != 0)
     const EnvK<ET>& K = P.K;
 
-    // ---- storage ----
-    typedef typename std::conditional<STORE == STORE_SMEM, SmemVec<ET, NCOV, BLOCK>, LocalVec<ET, NCOV>>::type CovVec;
-    typedef typename std::conditional<SYM, CovSym<ET, CovVec>, CovFull<ET, CovVec>>::type Cov;
-    typedef typename std::conditional<STORE == STORE_SMEM, WMatD<ET, SmemVec<ET, 63, BLOCK>>, WMatLocal<ET>>::type WM;
-    typedef typename std::conditional<STORE == STORE_SMEM, SmemVec<NT, NNC, BLOCK>, LocalVec<NT, NNC>>::type ColVec;
-    Cov cov;
-    WM Wm;
-    NetAcc<NT, NHL, LocalVec<NT, NNL>> lon;
-    NetAcc<NT, NHC, ColVec> col;
-    if constexpr (STORE == STORE_SMEM) {
-        ET* t_cov = reinterpret_cast<ET*>(tile);
-        ET* t_w = t_cov + NCOV * BLOCK;
-        NT* t_col = reinterpret_cast<NT*>(t_w + 63 * BLOCK);
-        cov.v.p = t_cov + tid;
-        Wm.v.p = t_w + tid;
-        col.v.p = t_col + tid;      // only dereferenced when COL
+    // ---- carve the warp's tile ----
+    unsigned char* tp = smem_raw + LY::head_bytes(WARPS) + LY::tile_bytes * warp;
+    typedef SmemVec<ET, NCOV, LANES> CovVec;
+    typename std::conditional<SYM, CovSym<ET, CovVec>, CovFull<ET, CovVec>>::type cov;
+    WMatD<ET, SmemVec<ET, 63, LANES>> Wm;
+    NetAcc<NT, NHC, SmemVec<NT, NNC, LANES>> col;
+    NetAcc<NT, NHL, Group<NT, NNL, LANES, (PLACE & P_LON) != 0>> lon;
+    Group<ET, 9, LANES, (PLACE & P_PREV) != 0> prev;             // x_prev[7], u_prev[2]   model.py:45-46
+    Group<double, 4, LANES, (PLACE & P_MISC) != 0> miscd;        // acc0, acc1, acc2, t
+    Group<ET, 4, LANES, (PLACE & P_MISC) != 0> misce;            // corr_u, pid_corr, trim0, trim1
+    Group<NT, 2 * NHL + 3, LANES, (PLACE & P_STASHL) != 0> stl;  // hl[NHL], fl, sl0, sl1, scratch[NHL]
+    Group<NT, 2 * NHC + 3, LANES, (PLACE & P_STASHC) != 0> stc;  // hc[NHC], fc, sc0, sc1, scratch[NHC]
+    SmemVec<NT, 10, LANES> hypn;                                 // HYP: gamma, lr_a, lr_c, tau, scale x (col, lon)
+    SmemVec<ET, 2, LANES> hype;                                  // HYP: reward weights (col, lon)
+    {
+        // widest element type first keeps every column naturally aligned
+        double* pd = reinterpret_cast<double*>(tp);
+        if constexpr ((PLACE & P_MISC) != 0) { miscd.p = pd + lc; pd += 4 * LANES; }
+        ET* pe = reinterpret_cast<ET*>(pd);
+        cov.v.p = pe + lc; pe += NCOV * LANES;
+        Wm.v.p = pe + lc; pe += 63 * LANES;
+        if constexpr ((PLACE & P_PREV) != 0) { prev.p = pe + lc; pe += 9 * LANES; }
+        if constexpr ((PLACE & P_MISC) != 0) { misce.p = pe + lc; pe += 4 * LANES; }
+        if constexpr (HYP) { hype.p = pe + lc; pe += 2 * LANES; }
+        NT* pn = reinterpret_cast<NT*>(pe);
+        col.v.p = pn + lc;                      // only dereferenced when COL
+        if constexpr (COL) pn += NNC * LANES;
+        if constexpr ((PLACE & P_LON) != 0) { lon.v.p = pn + lc; pn += NNL * LANES; }
+        if constexpr ((PLACE & P_STASHL) != 0) { stl.p = pn + lc; pn += (2 * NHL + 3) * LANES; }
+        if constexpr ((PLACE & P_STASHC) != 0) {
+            stc.p = pn + lc;                    // only dereferenced when COL
+            if constexpr (COL) pn += (2 * NHC + 3) * LANES;
+        }
+        hypn.p = pn + lc;                       // only dereferenced when HYP
     }
 
     // ---- entry load (coalesced SoA rows) ----
     // the z slot of the reference is -0 / +0 for every task (heli_models.py:236, :243, :250), so
     // `z - ref_z` is z bit for bit and the slot is not carried.
-    ET s[7], refth, corr_u, pid_corr, xprev[7], uprev[2];
+    ET s[7], refth;
 #pragma unroll
     for (int i = 0; i < 7; ++i) s[i] = P.state[i * ld + ec];
     refth = P.ref[ld + ec];
-    corr_u = P.corr_u[ec];
-    pid_corr = P.pid_corr[ec];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) xprev[i] = P.rls_x[i * ld + ec];
-    uprev[0] = P.rls_u[ec];
-    uprev[1] = P.rls_u[ld + ec];
     int skip = P.rls_skip[ec];
     int step = P.step[ec];
     int flags = valid ? P.flags[ec] : H3_FLAG_DONE;
     int term_step = P.term_step[ec];
-    double t = P.t[ec];
-    double acc0 = P.acc[ec], acc1 = P.acc[ld + ec], acc2 = P.acc[2 * ld + ec];
-    const ET trim0 = (ET)P.trim[ec], trim1 = (ET)P.trim[ld + ec];
-    AgentH<NT> Hcol_e, Hlon_e;      // only live when HYP
-    ET wr_col_e = (ET)0, wr_lon_e = (ET)0;
-    if (HYP) {
-        double wc, wl;
-        Hcol_e = load_hyper<NT>(P.col, P.col_hyper, ld, ec, wc);
-        Hlon_e = load_hyper<NT>(P.lon, P.lon_hyper, ld, ec, wl);
-        wr_col_e = (ET)wc;
-        wr_lon_e = (ET)wl;
+    // shared-memory columns are written by their owning lane only (idle lanes alias lane 0's column)
+    if (valid || (PLACE & P_PREV) == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) prev[i] = P.rls_x[i * ld + ec];
+        prev[7] = P.rls_u[ec];
+        prev[8] = P.rls_u[ld + ec];
     }
-    const AgentH<NT>& Hcol = HYP ? Hcol_e : P.col_h;
-    const AgentH<NT>& Hlon = HYP ? Hlon_e : P.lon_h;
-    const ET wr_col = HYP ? wr_col_e : P.col_wr;
-    const ET wr_lon = HYP ? wr_lon_e : P.lon_wr;
-    if (SYM) {
-        // upper triangle only
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-#pragma unroll
-            for (int j = i; j < 9; ++j) cov.v[CovSym<ET, CovVec>::idx(i, j)] = P.rls_cov[(i * 9 + j) * ld + ec];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 81; ++i) cov.v[i] = P.rls_cov[i * ld + ec];
+    if (valid || (PLACE & P_MISC) == 0) {
+        miscd[0] = P.acc[ec];
+        miscd[1] = P.acc[ld + ec];
+        miscd[2] = P.acc[2 * ld + ec];
+        miscd[3] = P.t[ec];
+        misce[0] = P.corr_u[ec];
+        misce[1] = P.pid_corr[ec];
+        misce[2] = (ET)P.trim[ec];
+        misce[3] = (ET)P.trim[ld + ec];
     }
+    if (valid) {
+        if constexpr (HYP) {
+            double wc, wl;
+            const AgentH<NT> hc_ = load_hyper<NT>(P.col, P.col_hyper, ld, ec, wc);
+            const AgentH<NT> hl_ = load_hyper<NT>(P.lon, P.lon_hyper, ld, ec, wl);
+            hypn[0] = hc_.gamma; hypn[1] = hc_.lr_a; hypn[2] = hc_.lr_c; hypn[3] = hc_.tau; hypn[4] = hc_.scale;
+            hypn[5] = hl_.gamma; hypn[6] = hl_.lr_a; hypn[7] = hl_.lr_c; hypn[8] = hl_.tau; hypn[9] = hl_.scale;
+            hype[0] = (ET)wc;
+            hype[1] = (ET)wl;
+        }
+        if (SYM) {
 #pragma unroll
-    for (int i = 0; i < 63; ++i) Wm(i / 7, i % 7) = P.rls_W[i * ld + ec];
-    lon.v.load(P.lon_net + ec, ld);         // TAU1L: rows [0, 7 nh) only (actor + critic)
-    if (COL) col.v.load(P.col_net + ec, ld);
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = i; j < 9; ++j) cov.v[CovSym<ET, CovVec>::idx(i, j)] = P.rls_cov[(i * 9 + j) * ld + ec];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 81; ++i) cov.v[i] = P.rls_cov[i * ld + ec];
+        }
+#pragma unroll
+        for (int i = 0; i < 63; ++i) Wm.v[i] = P.rls_W[i * ld + ec];
+        if (COL) col.v.load(P.col_net + ec, ld);
+    }
+    if (valid || (PLACE & P_LON) == 0) lon.v.load(P.lon_net + ec, ld);    // TAU1L: rows [0, 7 nh) only
 
     const bool lockstep = P.step0 >= 0;
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
@@ -222,26 +278,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
             __syncthreads();
         }
         for (int jj = 0; jj < cn; ++jj) {
-            if (flags != 0) continue;       // terminated (or padding) lane: frozen
+            if (flags != 0) continue;       // terminated (or idle) lane: frozen
             const int k = lockstep ? (P.step0 + c0 + jj) : step;
             const bool phase2 = COL && (k >= P.switch_step);                    // main_3dof.py:127-137
-            // -------- actions --------
+            AgentH<NT> Hcol = P.col_h, Hlon = P.lon_h;
+            ET wr_col = P.col_wr, wr_lon = P.lon_wr;
+            if constexpr (HYP) {
+                Hcol.gamma = hypn[0]; Hcol.lr_a = hypn[1]; Hcol.lr_c = hypn[2]; Hcol.tau = hypn[3]; Hcol.scale = hypn[4];
+                Hlon.gamma = hypn[5]; Hlon.lr_a = hypn[6]; Hlon.lr_c = hypn[7]; Hlon.tau = hypn[8]; Hlon.scale = hypn[9];
+                wr_col = hype[0];
+                wr_lon = hype[1];
+            }
+            // -------- actions (main_3dof.py:132-137); forward activations are kept for the update --------
             ET sth, cth;
             Math<ET>::sincos_(s[4], &sth, &cth);
-            NT hl[NHL], fl;
-            const NT sl0 = (NT)pick7(s, P.lon.ac_state);
-            const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
-            const NT a_lon = actor_forward<NT, NHL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, hl, fl);
-            ET cyc = trim1 + (ET)a_lon;
-            NT hc[NHC], fc = (NT)0, sc0 = (NT)0, sc1 = (NT)0;
-            ET colv;
+            ET cyc, colv;
+            {
+                NT fl;
+                const NT sl0 = (NT)pick7(s, P.lon.ac_state);
+                const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
+                const NT a_lon = actor_forward<NT, NHL, UL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, stl, fl);
+                cyc = misce[3] + (ET)a_lon;
+                stl[NHL] = fl;
+                stl[NHL + 1] = sl0;
+                stl[NHL + 2] = sl1;
+            }
             if (phase2) {
-                sc0 = (NT)pick7(s, P.col.ac_state);
-                sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
-                const NT a_col = actor_forward<NT, NHC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, hc, fc);
-                colv = trim0 + (ET)a_col;
+                NT fc;
+                const NT sc0 = (NT)pick7(s, P.col.ac_state);
+                const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
+                const NT a_col = actor_forward<NT, NHC, UC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, stc, fc);
+                colv = misce[2] + (ET)a_col;
+                stc[NHC] = fc;
+                stc[NHC + 1] = sc0;
+                stc[NHC + 2] = sc1;
             } else {
-                colv = pid_collective(K, s, sth, cth, pid_corr);                // PID.py:16-24
+                ET pc = misce[1];
+                colv = pid_collective(K, s, sth, cth, pc);                      // PID.py:16-24
+                misce[1] = pc;
             }
             if (lockstep) {                                                     // main_3dof.py:139-140
                 colv += (ET)sh_exc[2 * jj];
@@ -251,13 +325,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
                 cyc += (ET)P.excitation[2 * k + 1];
             }
             // -------- env.step (main_3dof.py:141) --------
-            ET obs[7];
+            ET X[9], Y[7];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) obs[i] = s[i];
-            if (P.task == H3_TASK_VELOCITY) (void)velocity_ref(K, s[2], corr_u);     // heli_models.py:155
+            for (int i = 0; i < 7; ++i) {
+                Y[i] = s[i];                        // pre-step obs
+                X[i] = s[i] - prev[i];              // model.py:41
+                prev[i] = s[i];                     // model.py:45
+            }
+            X[7] = colv - prev[7];                  // model.py:42
+            X[8] = cyc - prev[8];
+            prev[7] = colv;                         // model.py:46
+            prev[8] = cyc;
+            ET cu = misce[0];
+            if (P.task == H3_TASK_VELOCITY) (void)velocity_ref(K, s[2], cu);    // heli_models.py:155
             bool done;
             env_step(K, s, colv, cyc, sth, cth, done);
-            t += P.dt;                                                              // heli_models.py:206
+            const double t_new = miscd[3] + P.dt;                                // heli_models.py:206
+            miscd[3] = t_new;
             // -------- next_ref = env.get_ref() (main_3dof.py:142) --------
             ET nrefth;
             if (table_ref) {
@@ -268,30 +352,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
                     amp = __ldcg(P.ref_par + ec);
                     period = __ldcg(P.ref_par + ld + ec);
                 }
-                nrefth = (ET)sinusoid_ref(t + P.dt, amp, period);
+                nrefth = (ET)sinusoid_ref(t_new + P.dt, amp, period);
             } else if (P.task == H3_TASK_VELOCITY) {
-                nrefth = velocity_ref(K, s[2], corr_u);
+                nrefth = velocity_ref(K, s[2], cu);
             } else {
                 nrefth = stop_over_point_ref(K, s[0], s[2], (ET)__ldcg(P.theta_trim + ec));
             }
+            if (P.task == H3_TASK_VELOCITY) misce[0] = cu;
+            // -------- log row (main_3dof.py:164-175): pre-step obs and ref, applied actions; rewards below ----
+            const bool rec = P.traj != nullptr && e < P.n_traj;
+            ET* row = rec ? P.traj + ((int64_t)(c0 + jj) * H3_TRAJ_ROWS) * P.ld_traj + e : nullptr;
+            if (rec) {
+#pragma unroll
+                for (int i = 0; i < 7; ++i) row[i * P.ld_traj] = Y[i];
+                row[7 * P.ld_traj] = refth;
+                row[8 * P.ld_traj] = colv;
+                row[9 * P.ld_traj] = cyc;
+                row[12 * P.ld_traj] = (ET)1;
+            }
+            const bool nan_act = (colv != colv) || (cyc != cyc);                // main_3dof.py:192
             // -------- RLS.update(obs, actions, next_obs) (main_3dof.py:145, model.py:27-59) --------
             if (skip) {
                 skip = 0;
             } else {
-                ET X[9], Y[7];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    X[i] = obs[i] - xprev[i];
-                    Y[i] = s[i] - obs[i];
-                }
-                X[7] = colv - uprev[0];
-                X[8] = cyc - uprev[1];
+                for (int i = 0; i < 7; ++i) Y[i] = s[i] - Y[i];                 // model.py:43
                 rls_update(K, Wm, cov, X, Y);
             }
-#pragma unroll
-            for (int i = 0; i < 7; ++i) xprev[i] = obs[i];
-            uprev[0] = colv;
-            uprev[1] = cyc;
             // -------- cyclic agent (main_3dof.py:148-151) --------
             double r_lon = 0.0, r_col = 0.0;
             if (P.update_lon) {
@@ -302,7 +389,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
                 transition_matrices<ET, NT>(Wm, P.lon, F, G);
                 const NT n0 = (NT)pick7(s, P.lon.ac_state);
                 const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
-                agent_update<NT, NHL, TAU1L>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr, F, G, hl, fl);
+                SubVec<decltype(stl), NT> scr{stl, NHL + 3};
+                agent_update<NT, NHL, UL, TAU1L>(lon, Hlon, P.lon.final_activation, stl[NHL + 1], stl[NHL + 2], n0,
+                                                 n1, (NT)0, dr, F, G, stl, stl[NHL], scr);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -313,27 +402,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
                 transition_matrices<ET, NT>(Wm, P.col, F, G);
                 const NT n0 = (NT)pick7(s, P.col.ac_state);
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
-                agent_update<NT, NHC, false>(col, Hcol, P.col.final_activation, sc0, sc1, n0, n1, (NT)0, dr, F, G, hc, fc);
+                SubVec<decltype(stc), NT> scr{stc, NHC + 3};
+                agent_update<NT, NHC, UC, false>(col, Hcol, P.col.final_activation, stc[NHC + 1], stc[NHC + 2], n0,
+                                                 n1, (NT)0, dr, F, G, stc, stc[NHC], scr);
             }
-            // -------- log row (main_3dof.py:164-175): pre-step obs and ref, applied actions, rewards --------
-            if (P.traj != nullptr && e < P.n_traj) {
-                ET* row = P.traj + ((int64_t)(c0 + jj) * H3_TRAJ_ROWS) * P.ld_traj + e;
-#pragma unroll
-                for (int i = 0; i < 7; ++i) row[i * P.ld_traj] = obs[i];
-                row[7 * P.ld_traj] = refth;
-                row[8 * P.ld_traj] = colv;
-                row[9 * P.ld_traj] = cyc;
+            if (rec) {
                 row[10 * P.ld_traj] = (ET)r_col;
                 row[11 * P.ld_traj] = (ET)r_lon;
-                row[12 * P.ld_traj] = (ET)1;
             }
-            acc0 += r_col;
-            acc1 += r_lon;
-            if (k >= P.win_lo && k < P.win_hi) acc2 += r_lon;
+            miscd[0] += r_col;
+            miscd[1] += r_lon;
+            if (k >= P.win_lo && k < P.win_hi) miscd[2] += r_lon;
             // -------- next step / termination (main_3dof.py:189-197) --------
             refth = nrefth;
             step = k + 1;
-            const bool nan_act = (colv != colv) || (cyc != cyc);
             const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
             if (nf) {
                 flags = nf;
@@ -343,21 +425,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
     }
 
     // ---- exit store ----
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) P.state[i * ld + e] = s[i];
         P.ref[ld + e] = refth;
-        P.corr_u[e] = corr_u;
-        P.pid_corr[e] = pid_corr;
+        P.corr_u[e] = misce[0];
+        P.pid_corr[e] = misce[1];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) P.rls_x[i * ld + e] = xprev[i];
-        P.rls_u[e] = uprev[0];
-        P.rls_u[ld + e] = uprev[1];
+        for (int i = 0; i < 7; ++i) P.rls_x[i * ld + e] = prev[i];
+        P.rls_u[e] = prev[7];
+        P.rls_u[ld + e] = prev[8];
         P.rls_skip[e] = skip;
         P.step[e] = step;
         P.flags[e] = flags;
         P.term_step[e] = term_step;
-        P.t[e] = t;
+        acc0 = miscd[0];
+        acc1 = miscd[1];
+        acc2 = miscd[2];
+        P.t[e] = miscd[3];
         P.acc[e] = acc0;
         P.acc[ld + e] = acc1;
         P.acc[2 * ld + e] = acc2;
@@ -375,7 +461,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
             for (int i = 0; i < 81; ++i) P.rls_cov[i * ld + e] = cov.v[i];
         }
 #pragma unroll
-        for (int i = 0; i < 63; ++i) P.rls_W[i * ld + e] = Wm(i / 7, i % 7);
+        for (int i = 0; i < 63; ++i) P.rls_W[i * ld + e] = Wm.v[i];
         lon.v.store(P.lon_net + e, ld);
         if (TAU1L) {                // target critic == critic (agents.py:196 with tau = 1)
 #pragma unroll
@@ -391,12 +477,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
         v[1] = (valid && flags == 0) ? 1.0 : 0.0;
         v[2] = (valid && (flags & H3_FLAG_DONE)) ? 1.0 : 0.0;
         v[3] = (valid && (flags & H3_FLAG_NAN)) ? 1.0 : 0.0;
-        v[4] = valid ? acc0 : 0.0;
-        v[5] = valid ? acc1 : 0.0;
-        v[6] = valid ? acc2 : 0.0;
+        v[4] = acc0;
+        v[5] = acc1;
+        v[6] = acc2;
         v[7] = valid ? (double)step : 0.0;
         __syncthreads();
-        block_reduce_stats<BLOCK>(v, sh_red);
+        block_reduce_stats<WARPS>(v, sh_red);
         __shared__ bool is_last;
         if (tid == 0) {
 #pragma unroll
@@ -415,7 +501,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
 #pragma unroll
                 for (int i = 0; i < H3_N_STATS; ++i) a[i] += __ldcg(&P.partials[b * H3_N_STATS + i]);
             __syncthreads();
-            block_reduce_stats<BLOCK>(a, sh_red);
+            block_reduce_stats<WARPS>(a, sh_red);
             if (tid == 0) {
 #pragma unroll
                 for (int i = 0; i < H3_N_STATS; ++i) P.stats[i] = a[i];
@@ -423,16 +509,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) closed_loop_kernel(const LoopPara
             }
         }
     }
-}
-
-template <typename ET, int NCOV>
-constexpr size_t loop_smem_bytes(int block, int store, bool col, int nhc, size_t net_size) {
-    size_t b = (size_t)(3 * TICK_CHUNK + (block / 32) * H3_N_STATS) * sizeof(double);
-    if (store == STORE_SMEM) {
-        b += (size_t)block * (NCOV + 63) * sizeof(ET);
-        if (col) b += (size_t)block * 11 * nhc * net_size;
-    }
-    return b;
 }
 
 }  // namespace h3

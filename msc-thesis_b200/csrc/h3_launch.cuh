@@ -10,7 +10,7 @@ namespace h3 {
 void set_error(const char* fmt, ...);
 
 struct LoopInfo {
-    int block, smem_bytes, blocks_per_sm, regs;
+    int block, smem_bytes, blocks_per_sm, regs, lanes_per_warp;
 };
 
 template <typename ET, typename NT>
@@ -20,13 +20,10 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
 
 #ifdef H3_LOOP_IMPL
 
-constexpr int BLOCK_LOCAL = 64;
-constexpr int BLOCK_SMEM = 32;
-
 template <typename ET, typename NT>
 struct KernelSel {
     void (*fn)(const LoopParams<ET, NT>);
-    int block;
+    int block, lanes, warps;
     size_t smem;
 };
 
@@ -36,33 +33,49 @@ struct KernelSel {
 //   GENERAL : covariance not known symmetric (model.py:53-54 literally), any hyper-parameters
 enum { VAR_FAST = 0, VAR_SWEEP = 1, VAR_GENERAL = 2 };
 
-template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L>
-static KernelSel<ET, NT> sel_store(int store) {
+constexpr size_t SMEM_PER_BLOCK_MAX = 232448;   // 227 KB opt-in limit per CTA on sm_100
+
+// On-chip placement per variant.  Phase-1 launches (COL == false) keep everything
+// but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM); launches with the
+// collective agent run one 4-warp CTA per SM with as many episodes per warp as the tile allows.
+template <typename ET, typename NT, int NHL, int NHC, bool COL, int VAR>
+struct Tune {
+    static constexpr bool SYM = VAR != VAR_GENERAL, HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
+    static constexpr bool lon_smem = !TAU1L;                // the full cyclic agent (11 nh words) goes to the tile
+    static constexpr int PLACE = (COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0);
+    static constexpr int UL = lon_smem ? NHL / 2 : NHL;
+    static constexpr int UC = COL ? NHC / 2 : NHC;
+    static constexpr int WARPS = COL ? 4 : 1;
+    typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
+    static constexpr size_t room = (SMEM_PER_BLOCK_MAX - L32::head_bytes(WARPS)) / WARPS - 16;
+    static constexpr int fit = (int)(room / L32::bytes_per_lane);
+    static constexpr int LANES = fit >= 32 ? 32 : fit;
+    static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");
+};
+
+template <typename ET, typename NT, int NHL, int NHC, bool COL, int VAR>
+static KernelSel<ET, NT> sel_kernel() {
+    typedef Tune<ET, NT, NHL, NHC, COL, VAR> T;
+    typedef LoopLayout<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES> LY;
     KernelSel<ET, NT> k;
-    constexpr int NCOV = SYM ? 45 : 81;
-    if (store == STORE_SMEM) {
-        k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, STORE_SMEM, BLOCK_SMEM, 1>;
-        k.block = BLOCK_SMEM;
-        k.smem = loop_smem_bytes<ET, NCOV>(BLOCK_SMEM, STORE_SMEM, COL, NHC, sizeof(NT));
-    } else {
-        k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, STORE_LOCAL, BLOCK_LOCAL, 1>;
-        k.block = BLOCK_LOCAL;
-        k.smem = loop_smem_bytes<ET, NCOV>(BLOCK_LOCAL, STORE_LOCAL, COL, NHC, sizeof(NT));
-    }
+    k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES, T::WARPS, T::UL, T::UC>;
+    k.block = T::WARPS * 32;
+    k.lanes = T::LANES;
+    k.warps = T::WARPS;
+    k.smem = LY::smem_bytes(T::WARPS);
     return k;
 }
 
-template <typename ET, typename NT, int NHL, int NHC, bool COL>
-static KernelSel<ET, NT> sel_variant(int variant, int store) {
-    if (variant == VAR_FAST) return sel_store<ET, NT, NHL, NHC, COL, true, false, true>(store);
-    if (variant == VAR_SWEEP) return sel_store<ET, NT, NHL, NHC, COL, true, true, false>(STORE_SMEM);
-    return sel_store<ET, NT, NHL, NHC, COL, false, true, false>(store);
-}
-
 template <typename ET, typename NT, int NHL, int NHC>
-static KernelSel<ET, NT> sel_flags(bool col, int variant, int store) {
-    return col ? sel_variant<ET, NT, NHL, NHC, true>(variant, store)
-               : sel_variant<ET, NT, NHL, NHC, false>(variant, store);
+static KernelSel<ET, NT> sel_flags(bool col, int variant) {
+    if (col) {
+        if (variant == VAR_FAST) return sel_kernel<ET, NT, NHL, NHC, true, VAR_FAST>();
+        if (variant == VAR_SWEEP) return sel_kernel<ET, NT, NHL, NHC, true, VAR_SWEEP>();
+        return sel_kernel<ET, NT, NHL, NHC, true, VAR_GENERAL>();
+    }
+    if (variant == VAR_FAST) return sel_kernel<ET, NT, NHL, NHC, false, VAR_FAST>();
+    if (variant == VAR_SWEEP) return sel_kernel<ET, NT, NHL, NHC, false, VAR_SWEEP>();
+    return sel_kernel<ET, NT, NHL, NHC, false, VAR_GENERAL>();
 }
 
 template <typename ET, typename NT>
@@ -77,11 +90,10 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     const bool per_ep = b.col_hyper != nullptr || b.lon_hyper != nullptr;
     const int variant = (cfg.rls_symmetric == 0) ? VAR_GENERAL
                                                  : ((per_ep || cfg.lon.tau != 1.0) ? VAR_SWEEP : VAR_FAST);
-    const int store = (cfg.store_policy == 1) ? STORE_LOCAL : STORE_SMEM;
     KernelSel<ET, NT> k;
-    if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant, store);
+    if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant);
 #ifndef H3_FAST_BUILD
-    else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant, store);
+    else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant);
 #endif
     else {
         set_error("h3_closed_loop: hidden widths (lon %d, col %d) not compiled in (have 6/10, 8/8)", nhl, nhc);
@@ -109,6 +121,7 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
         info_only->smem_bytes = (int)k.smem;
         info_only->blocks_per_sm = nb;
         info_only->regs = fa.numRegs;
+        info_only->lanes_per_warp = k.lanes;
         return H3_OK;
     }
     if (b.n <= 0 || n_ticks <= 0) return H3_OK;
@@ -167,7 +180,8 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     P.traj = (traj != nullptr) ? (ET*)traj->out : nullptr;
     P.n_traj = (traj != nullptr) ? traj->n_traj : 0;
     P.ld_traj = (traj != nullptr) ? traj->ld_traj : 0;
-    const int64_t grid = (b.n + k.block - 1) / k.block;
+    const int64_t per_block = (int64_t)k.lanes * k.warps;
+    const int64_t grid = (b.n + per_block - 1) / per_block;
     P.stats = stats;
     P.ticket = nullptr;
     P.partials = nullptr;

@@ -139,15 +139,25 @@ H3_DEV T stop_over_point_ref(const EnvK<T>& K, T x, T u, T theta_trim) {    // :
 // RecursiveLeastSquares.update  (model.py:41-59), n = 9 regressors, m = 7 outputs.
 //   Wm(i,j): weight accessor (9x7).  Cv: covariance accessor -- full (9x9) or symmetric-packed.
 // ----------------------------------------------------------------------------------------------
+// A compiler-level fence: memory operations are not moved across it.  Placed between the rows of the
+// unrolled RLS loops it stops ptxas from hoisting all 63 + 45 shared-memory loads to the top (which would
+// need > 200 registers) while still letting one row's loads overlap the previous row's FMAs.
+template <bool ON>
+H3_DEV void row_fence() {
+    if (ON) asm volatile("" ::: "memory");
+}
+
 template <typename T, typename WAcc, typename CAcc>
 H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7]) {
     T err[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) err[j] = Y[j];
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 9; ++i) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) err[j] -= X[i] * Wm(i, j);          // :49-50
+        if (i & 1) row_fence<WAcc::kFence>();
+    }
     T covX[9], Xcov[9];
     Cv.matvec(X, covX, Xcov);                                           // :53-54
     T d = K.rls_gamma;
@@ -158,9 +168,11 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 9; ++i) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) Wm(i, j) += g[i] * err[j];          // :58
+        if (i & 1) row_fence<WAcc::kFence>();
+    }
     Cv.downdate(g, Xcov, K.rls_inv_gamma);                              // :59
 }
 
@@ -193,31 +205,41 @@ struct CovFull {            // model.py:53-54 literally: cov.X and X^T.cov compu
 template <typename T, typename Vec>
 struct CovSym {             // upper triangle only (45 elements): cov == cov^T is an invariant of
     Vec v;                  // model.py:59 when it holds initially (model.py:85: identity * c)
-    static H3_DEV constexpr int idx(int i, int j) { return i * 9 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+    __host__ __device__ static constexpr int idx(int i, int j) { return i * 9 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
     H3_DEV void matvec(const T (&X)[9], T (&covX)[9], T (&Xcov)[9]) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) covX[i] = (T)0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
+        for (int i = 0; i < 9; ++i) {
 #pragma unroll
             for (int j = i; j < 9; ++j) {
                 const T c = v[idx(i, j)];
                 covX[i] += c * X[j];
                 if (j != i) covX[j] += c * X[i];
             }
+            if (i & 1) row_fence<Vec::kFence>();
+        }
 #pragma unroll
         for (int i = 0; i < 9; ++i) Xcov[i] = covX[i];
     }
     H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
+        for (int i = 0; i < 9; ++i) {
 #pragma unroll
             for (int j = i; j < 9; ++j) v[idx(i, j)] = (v[idx(i, j)] - g[i] * Xcov[j]) * inv_gamma;
+            if (i & 1) row_fence<Vec::kFence>();
+        }
     }
 };
 
 // ----------------------------------------------------------------------------------------------
 // IDHP agent (agents.py).  Net: accessor with a1(k,i) a2(k) c1(k,i) c2(j,k) t1(k,i) t2(j,k).
+//
+// Loops over the hidden units run in chunks of U units: U == NH unrolls everything (weights may then
+// live in registers), U < NH keeps an outer `#pragma unroll 1` loop with runtime unit indices (weights,
+// activations and scratch must then be addressable, i.e. in shared or global memory).  The chunk width
+// bounds how many independent tanh chains the compiler interleaves -- enough to cover the FP64 pipe
+// latency from a single warp, few enough not to blow the register file.
 // ----------------------------------------------------------------------------------------------
 template <typename NT>
 struct AgentH {             // hyper-parameters in network precision
@@ -225,14 +247,20 @@ struct AgentH {             // hyper-parameters in network precision
 };
 
 // DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
-template <typename NT, int NH, typename Net>
-H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, NT (&h)[NH], NT& f) {
+template <typename NT, int NH, int U, typename Net, typename HVec>
+H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f) {
     typedef Math<NT> M;
+    static_assert(NH % U == 0, "chunk width must divide the hidden width");
     NT y = (NT)0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += U) {
 #pragma unroll
-    for (int k = 0; k < NH; ++k) {
-        h[k] = M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
-        y += net.a2(k) * h[k];
+        for (int u = 0; u < U; ++u) {
+            const int k = (U == NH) ? u : k0 + u;
+            const NT hk = M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
+            h[k] = hk;
+            y += net.a2(k) * hk;
+        }
     }
     f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
     return scale * f;
@@ -240,40 +268,46 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, NT (&h)[NH], 
 
 // get_reward + get_transition_matrices + update_networks (agents.py:123-196), closed form.
 //   s0,s1 = augmented state of (obs, ref); n0,n1 = augmented state of (next_obs, next_ref);
-//   dr_ds = [dr0, dr] (get_reward: dr0 = 0, dr = -2 e w_r, already in network precision); F[i][j], G[i] from the POST-update RLS weights;
-//   h_a, f = actor forward of the same (obs, ref) with the pre-update actor (== get_action's pass).
+//   dr_ds = [dr0, dr] (get_reward: dr0 = 0, dr = -2 e w_r, already in network precision);
+//   F[i][j], G[i] from the POST-update RLS weights;
+//   h_a, f = actor forward of the same (obs, ref) with the pre-update actor (== get_action's pass);
+//   scr: NH words of scratch for the critic's hidden activations between the two passes.
 //   TAU1: tau_target_critic == 1 for every episode of the launch -> the target critic IS the critic after
 //   every update (agents.py:196: 1*p + 0*t), so its rows are neither kept on chip nor updated; lambda_t2
 //   is evaluated with the critic's (pre-update) weights, which are the target's.
-template <typename NT, int NH, bool TAU1, typename Net>
+template <typename NT, int NH, int U, bool TAU1, typename Net, typename HVec, typename SVec>
 H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
-                         const NT (&F)[2][2], const NT (&G)[2], const NT (&h_a)[NH], NT f) {
+                         const NT (&F)[2][2], const NT (&G)[2], HVec& h_a, NT f, SVec& scr) {
     typedef Math<NT> M;
-    // critic(s) and target_critic(s')  (:170-171)
-    NT h_c[NH], lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0};
-#pragma unroll
-    for (int k = 0; k < NH; ++k) {
-        h_c[k] = M::tanh_(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
-        lam1[0] += net.c2(0, k) * h_c[k];
-        lam1[1] += net.c2(1, k) * h_c[k];
-        if (TAU1) {
-            const NT h_t = M::tanh_(net.c1(k, 0) * n0 + net.c1(k, 1) * n1);
-            lam2[0] += net.c2(0, k) * h_t;
-            lam2[1] += net.c2(1, k) * h_t;
-        } else {
-            const NT h_t = M::tanh_(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
-            lam2[0] += net.t2(0, k) * h_t;
-            lam2[1] += net.t2(1, k) * h_t;
-        }
-    }
-    // action.backward() (:174): delta = da/dy, p = da/d(pre-activation of hidden k)
+    static_assert(NH % U == 0, "chunk width must divide the hidden width");
+    // action.backward() (:174): delta = da/dy, p_k = da/d(pre-activation of hidden k)
     const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);
-    NT p[NH], da_ds[2] = {(NT)0, (NT)0};
+    // pass 1: critic(s), target_critic(s') (:170-171) and da/ds
+    NT lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += U) {
 #pragma unroll
-    for (int k = 0; k < NH; ++k) {
-        p[k] = delta * net.a2(k) * ((NT)1 - h_a[k] * h_a[k]);
-        da_ds[0] += net.a1(k, 0) * p[k];
-        da_ds[1] += net.a1(k, 1) * p[k];
+        for (int u = 0; u < U; ++u) {
+            const int k = (U == NH) ? u : k0 + u;
+            const NT hc = M::tanh_(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
+            scr[k] = hc;
+            lam1[0] += net.c2(0, k) * hc;
+            lam1[1] += net.c2(1, k) * hc;
+            NT ht;
+            if (TAU1) {
+                ht = M::tanh_(net.c1(k, 0) * n0 + net.c1(k, 1) * n1);
+                lam2[0] += net.c2(0, k) * ht;
+                lam2[1] += net.c2(1, k) * ht;
+            } else {
+                ht = M::tanh_(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
+                lam2[0] += net.t2(0, k) * ht;
+                lam2[1] += net.t2(1, k) * ht;
+            }
+            const NT ha = h_a[k];
+            const NT pk = delta * net.a2(k) * ((NT)1 - ha * ha);
+            da_ds[0] += net.a1(k, 0) * pk;
+            da_ds[1] += net.a1(k, 1) * pk;
+        }
     }
     // target = dr_ds + gamma * lambda_t2 ; error_critic = lambda_t1 - target (F + G da_ds)  (:178-179)
     const NT tg0 = dr0 + H.gamma * lam2[0];     // dr_ds[0] is 0 in get_reward (agents.py:124)
@@ -282,31 +316,39 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         e_c[j] = lam1[j] - (tg0 * (F[0][j] + G[0] * da_ds[j]) + tg1 * (F[1][j] + G[1] * da_ds[j]));
-    // SGD (:184-188): wa += lr_a (target.G) da/dwa ; wc -= lr_c dL/dwc, then soft target update (:195-196)
+    // pass 2: SGD (:184-188): wa += lr_a (target.G) da/dwa ; wc -= lr_c dL/dwc, then soft target update (:195-196)
     const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
     const NT one_m_tau = (NT)1 - H.tau;
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += U) {
 #pragma unroll
-    for (int k = 0; k < NH; ++k) {
-        const NT back = (net.c2(0, k) * e_c[0] + net.c2(1, k) * e_c[1]) * ((NT)1 - h_c[k] * h_c[k]);
-        // actor
-        net.a1(k, 0) += ka * (p[k] * s0);
-        net.a1(k, 1) += ka * (p[k] * s1);
-        net.a2(k) += ka * (delta * h_a[k]);
-        // critic
-        const NT c10 = net.c1(k, 0) - H.lr_c * (back * s0);
-        const NT c11 = net.c1(k, 1) - H.lr_c * (back * s1);
-        const NT c20 = net.c2(0, k) - H.lr_c * (e_c[0] * h_c[k]);
-        const NT c21 = net.c2(1, k) - H.lr_c * (e_c[1] * h_c[k]);
-        net.c1(k, 0) = c10;
-        net.c1(k, 1) = c11;
-        net.c2(0, k) = c20;
-        net.c2(1, k) = c21;
-        // target critic
-        if (!TAU1) {
-            net.t1(k, 0) = H.tau * c10 + one_m_tau * net.t1(k, 0);
-            net.t1(k, 1) = H.tau * c11 + one_m_tau * net.t1(k, 1);
-            net.t2(0, k) = H.tau * c20 + one_m_tau * net.t2(0, k);
-            net.t2(1, k) = H.tau * c21 + one_m_tau * net.t2(1, k);
+        for (int u = 0; u < U; ++u) {
+            const int k = (U == NH) ? u : k0 + u;
+            const NT hc = scr[k], ha = h_a[k];
+            const NT a2k = net.a2(k);
+            const NT pk = delta * a2k * ((NT)1 - ha * ha);
+            const NT c20o = net.c2(0, k), c21o = net.c2(1, k);
+            const NT back = (c20o * e_c[0] + c21o * e_c[1]) * ((NT)1 - hc * hc);
+            // actor
+            net.a1(k, 0) += ka * (pk * s0);
+            net.a1(k, 1) += ka * (pk * s1);
+            net.a2(k) = a2k + ka * (delta * ha);
+            // critic
+            const NT c10 = net.c1(k, 0) - H.lr_c * (back * s0);
+            const NT c11 = net.c1(k, 1) - H.lr_c * (back * s1);
+            const NT c20 = c20o - H.lr_c * (e_c[0] * hc);
+            const NT c21 = c21o - H.lr_c * (e_c[1] * hc);
+            net.c1(k, 0) = c10;
+            net.c1(k, 1) = c11;
+            net.c2(0, k) = c20;
+            net.c2(1, k) = c21;
+            // target critic
+            if (!TAU1) {
+                net.t1(k, 0) = H.tau * c10 + one_m_tau * net.t1(k, 0);
+                net.t1(k, 1) = H.tau * c11 + one_m_tau * net.t1(k, 1);
+                net.t2(0, k) = H.tau * c20 + one_m_tau * net.t2(0, k);
+                net.t2(1, k) = H.tau * c21 + one_m_tau * net.t2(1, k);
+            }
         }
     }
 }
@@ -316,6 +358,7 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
 // ----------------------------------------------------------------------------------------------
 template <typename T, int N>
 struct LocalVec {           // registers / local memory (compile-time indices after unrolling)
+    static constexpr bool kFence = false;
     T v[N];
     H3_DEV T& operator[](int i) { return v[i]; }
     H3_DEV void load(const T* g, int64_t ld) {
@@ -330,6 +373,7 @@ struct LocalVec {           // registers / local memory (compile-time indices af
 
 template <typename T, int N, int STRIDE>
 struct SmemVec {            // column of a [N][STRIDE] shared-memory tile; bank-conflict free per warp
+    static constexpr bool kFence = true;
     T* p;                   // already offset by the thread index
     H3_DEV T& operator[](int i) { return p[i * STRIDE]; }
     H3_DEV void load(const T* g, int64_t ld) {
@@ -344,6 +388,7 @@ struct SmemVec {            // column of a [N][STRIDE] shared-memory tile; bank-
 
 template <typename T, typename Vec>
 struct WMat {               // RLS weights (9,7) row-major
+    static constexpr bool kFence = Vec::kFence;
     Vec v;
     H3_DEV T& operator()(int i, int j) { return v[i * 7 + j]; }
 };

@@ -46,14 +46,22 @@ def test_open_loop_step_vs_oracle(h3):
     assert H.relerr(trim.cpu().numpy(), tr_o) < 1e-12
     exc = H.excitation()
     out = env.rollout(n_ticks, excitation=exc, record=n_rec).cpu().numpy()
-    s = st_o[:, :n_rec].copy()
-    worst = 0.0
+    # per-step parity (teacher-forced: the oracle steps from the kernel's previous state) at 1e-9, and the
+    # free-running trajectory as a looser sanity bound -- the open-loop airframe is unstable, so rounding
+    # differences of 1e-16 per tick grow along the 1200-tick rollout
+    s_free = st_o[:, :n_rec].copy()
+    prev = st_o[:, :n_rec].copy()
+    worst = worst_free = 0.0
     for k in range(n_ticks):
         a = tr_o[:, :n_rec] + (exc[k][:, None] if k < len(exc) else 0.0)
-        s, done = O.env_step(s, a, 0.01)
-        worst = max(worst, float(np.max(np.abs(out[k] - s) / np.maximum(np.abs(s), 1e-6))))
+        s_tf, done = O.env_step(prev, a, 0.01)
+        s_free, _ = O.env_step(s_free, a, 0.01)
+        worst = max(worst, float(np.max(np.abs(out[k] - s_tf) / np.maximum(np.abs(s_tf), 1e-6))))
+        worst_free = max(worst_free, float(np.max(np.abs(out[k] - s_free) / np.maximum(np.abs(s_free), 1e-6))))
         assert not done.any()
+        prev = out[k]
     assert worst < TOL64, worst
+    assert worst_free < 1e-6, worst_free
     assert int(env.step_count.min()) == n_ticks and int(env.flags.max()) == 0
     assert abs(env.t - float(env.t_ep[0])) == 0.0
 
@@ -224,6 +232,10 @@ def test_main_3dof_statements_drop_in(h3, tmp_path):
 # ------------------------------------------------------------------------------------------------------
 # random batch against the oracle (per-episode hyper-parameters, trims, all tasks)
 # ------------------------------------------------------------------------------------------------------
+def _clone_state(S):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in S.items()}
+
+
 def _random_problem(n, seed, task="sinusoid", per_episode=True, switch_step=40):
     rng = np.random.default_rng(seed)
     cfg = O.default_config()
@@ -257,9 +269,22 @@ def test_random_batch_vs_oracle(h3, task, per_episode):
                        ticks_per_launch=50)
     loop.run(n_ticks)
     got = H.loop_state(loop)
+    # free-running: rounding differences of ~1e-16 per tick are amplified by the (still untrained) closed loop
+    # -- for a few episodes by many orders of magnitude.  The bound is therefore the oracle's own sensitivity:
+    # the same run from a state perturbed by 1 ulp.  The per-tick bar is checked right below from a common state.
+    P = _clone_state(S)
+    P["state"] = P["state"] * (1 + 2.0 ** -52)
     O.run(S, cfg, n_ticks, "all64")
-    H.compare_states(got, S, 1e-8, what=task)      # 120 free-running ticks accumulate a few ulp per tick
-    st = loop.stats()
+    O.run(P, cfg, n_ticks, "all64")
+    sens = H.episode_errors(P, S)
+    assert np.median(sens) < 1e-12
+    H.compare_states(got, S, np.maximum(1e-9, 1e3 * sens), what=task)
+    one = H.make_loop(_clone_state(S), cfg, ticks_per_launch=50)
+    one.run(1)
+    O.run(S, cfg, 1, "all64")
+    H.compare_states(H.loop_state(one), S, TOL64, what=task + " (one tick from the oracle's state)")
+    n_ticks += 1
+    st = one.stats()
     assert st["n"] == n and st["n_alive"] == int((S["flags"] == 0).sum())
     assert abs(st["sum_r_lon"] - S["ret"][1].sum()) <= 1e-9 * max(1.0, abs(S["ret"][1].sum()))
     assert st["sum_ticks"] == float(S["step"].sum())
@@ -268,10 +293,6 @@ def test_random_batch_vs_oracle(h3, task, per_episode):
 # ------------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE scale (config 3: 1,048,576 episodes)
 # ------------------------------------------------------------------------------------------------------
-def _clone_state(S):
-    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in S.items()}
-
-
 def test_full_size_replicated_episodes_agree_bitwise(h3):
     """1,048,576 copies of the same episode must stay bit-identical whatever lane / block / SM runs them,
     and must equal the single-episode run; the statistics epilogue must equal the torch reductions."""

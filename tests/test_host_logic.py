@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.h3_version() == 100
-    assert lib.h3_stats_scratch_bytes(64) == 16 + 2 * 8 * 8
+    assert lib.h3_stats_scratch_bytes(64) == 16 + 8 * 8 * 8
 
 
 def test_ctypes_structs_match_the_header(tmp_path):
