@@ -389,6 +389,21 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, T* out) {
     if (s == (T)123456789) out[0] = s;      // never true; keeps the chains alive
 }
 
+// direct access to the kernel's own fp64 math (tests/test_gpu_math.py)
+__global__ void __launch_bounds__(SMALL_BLOCK) math_probe_kernel(int fn, const double* __restrict__ x, double* y,
+                                                                 double* y2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    if (fn == 0) {
+        y[i] = Math<double>::tanh_(x[i]);
+    } else {
+        double s, c;
+        Math<double>::sincos_(x[i], &s, &c);
+        y[i] = s;
+        y2[i] = c;
+    }
+}
+
 static bool dtype_ok(int d) { return d == H3_F64 || d == H3_F32; }
 
 }  // namespace h3
@@ -716,6 +731,16 @@ int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int
     if (regs) *regs = info.regs;
     if (lanes_per_warp) *lanes_per_warp = info.lanes_per_warp;
     return H3_OK;
+}
+
+int h3_math_probe(int32_t fn, const double* x, double* y, double* y2, int64_t n, void* stream) {
+    if ((fn != 0 && fn != 1) || !x || !y || (fn == 1 && !y2)) {
+        set_error("h3_math_probe: bad argument");
+        return H3_E_ARG;
+    }
+    if (n <= 0) return H3_OK;
+    math_probe_kernel<<<grid_for(n), SMALL_BLOCK, 0, (cudaStream_t)stream>>>(fn, x, y, y2, n);
+    return check_launch("math_probe_kernel");
 }
 
 int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_out, void* stream) {

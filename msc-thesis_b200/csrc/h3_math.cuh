@@ -4,26 +4,110 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "h3_coef.cuh"
+
 namespace h3 {
 
 #define H3_DEV __device__ __forceinline__
+
+// fp64 tanh / sincos written for this kernel: every polynomial coefficient is a constant-bank operand of
+// its DFMA (tools/fit_math_coef.py derives them; <= 1.6 ulp end to end), where the inlined CUDA library
+// routine spends two UMOV issue slots per coefficient.  tanh has two straight-line branches:
+//   |x| <  0.55 : x + x z P(z), z = x^2                      (hidden pre-activations of the cyclic agent)
+//   otherwise   : E / (E + 2), E = expm1(2x)                 (collective agent: inputs in m and m/s)
+// and the branch is taken once per CHUNK of hidden units (tanh_vec), so each side is straight-line code in
+// which the compiler interleaves the independent polynomial chains.
+// sin/cos use one polynomial pair on |x| <= pi/4 (flight angles) and the library, out of line, beyond.
+static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { ::sincos(x, s, c); }
+
+H3_DEV double tanh_small(double x) {
+    const double z = x * x;
+    double p = H3_TANH_C[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, z, H3_TANH_C[i]);
+    return fma(x * z, p, x);
+}
+
+// tanh(x) = E / (E + 2), E = expm1(2x) = 2^n expm1(r) + (2^n - 1), 2x = n ln2 + r: one straight-line formula
+// without cancellation for every x (2.4 ulp), used whenever a chunk holds an argument >= 0.55.
+H3_DEV double tanh_any(double x) {
+    const double xc = x > 20.0 ? 20.0 : (x < -20.0 ? -20.0 : x);    // |tanh| == 1 to the last bit beyond 19.1; NaN passes
+    const double y = xc + xc;
+    // n = rint(y / ln2) by the 1.5 * 2^52 trick: the integer lands in the low word of t
+    const double t = fma(y, H3_LN2[2], 6755399441055744.0);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -H3_LN2[0], y);
+    r = fma(nf, -H3_LN2[1], r);                             // |r| <= ln2 / 2
+    double q = H3_EXP_C[10];
+#pragma unroll
+    for (int i = 9; i >= 0; --i) q = fma(q, r, H3_EXP_C[i]);
+    const double p = fma(r * r, q, r);                      // expm1(r)
+    const int n = __double2loint(t);                        // in [-58, 58]; NaN: E is NaN whatever n is
+    const double sc = __hiloint2double((n + 1023) << 20, 0);
+    const double E = fma(sc, p, sc - 1.0);
+    const double den = E + 2.0;                             // in [1, 2^58]: no special cases in the division
+    double rc = (double)__frcp_rn((float)den);
+    rc = fma(rc, fma(-den, rc, 1.0), rc);
+    rc = fma(rc, fma(-den, rc, 1.0), rc);
+    const double q0 = E * rc;
+    return fma(fma(-q0, den, E), rc, q0);
+}
+
+H3_DEV double tanh_f64(double x) {
+    if (::fabs(x) < 0.55) return tanh_small(x);             // NaN compares false -> tanh_any -> NaN
+    return tanh_any(x);
+}
+
+H3_DEV void sincos_f64(double x, double* s, double* c) {
+    if (::fabs(x) <= 0.78539816339744828) {
+        const double z = x * x;
+        double ps = H3_SIN_C[7], pc = H3_COS_C[7];
+#pragma unroll
+        for (int i = 6; i >= 0; --i) {
+            ps = fma(ps, z, H3_SIN_C[i]);
+            pc = fma(pc, z, H3_COS_C[i]);
+        }
+        *s = fma(x * z, ps, x);
+        *c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    } else {
+        sincos_libm(x, s, c);
+    }
+}
 
 template <typename T>
 struct Math;
 
 template <>
 struct Math<double> {
-    static H3_DEV double tanh_(double x) { return ::tanh(x); }
+    static H3_DEV double tanh_(double x) { return tanh_f64(x); }
+    template <int U>
+    static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
+        bool all_small = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u) all_small = all_small && (::fabs(x[u]) < 0.55);
+        if (all_small) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) y[u] = tanh_small(x[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) y[u] = tanh_any(x[u]);
+        }
+    }
     static H3_DEV double exp_(double x) { return ::exp(x); }
     static H3_DEV double sqrt_(double x) { return ::sqrt(x); }
     static H3_DEV double abs_(double x) { return ::fabs(x); }
-    static H3_DEV void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static H3_DEV void sincos_(double x, double* s, double* c) { sincos_f64(x, s, c); }
     static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }
 };
 
 template <>
 struct Math<float> {
     static H3_DEV float tanh_(float x) { return ::tanhf(x); }
+    template <int U>
+    static H3_DEV void tanh_vec(const float (&x)[U], float (&y)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
+    }
     static H3_DEV float exp_(float x) { return ::expf(x); }
     static H3_DEV float sqrt_(float x) { return ::sqrtf(x); }
     static H3_DEV float abs_(float x) { return ::fabsf(x); }

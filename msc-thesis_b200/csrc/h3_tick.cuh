@@ -254,12 +254,18 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
     NT y = (NT)0;
 #pragma unroll 1
     for (int k0 = 0; k0 < NH; k0 += U) {
+        NT pre[U], hk[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = (U == NH) ? u : k0 + u;
-            const NT hk = M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
-            h[k] = hk;
-            y += net.a2(k) * hk;
+            pre[u] = net.a1(k, 0) * s0 + net.a1(k, 1) * s1;
+        }
+        M::template tanh_vec<U>(pre, hk);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = (U == NH) ? u : k0 + u;
+            h[k] = hk[u];
+            y += net.a2(k) * hk[u];
         }
     }
     f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
@@ -286,20 +292,25 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
     NT lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
 #pragma unroll 1
     for (int k0 = 0; k0 < NH; k0 += U) {
+        NT pre[2 * U], act[2 * U];      // critic on s and target critic on s' of the chunk: 2U independent tanh
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = (U == NH) ? u : k0 + u;
-            const NT hc = M::tanh_(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
+            pre[u] = net.c1(k, 0) * s0 + net.c1(k, 1) * s1;
+            pre[U + u] = TAU1 ? net.c1(k, 0) * n0 + net.c1(k, 1) * n1 : net.t1(k, 0) * n0 + net.t1(k, 1) * n1;
+        }
+        M::template tanh_vec<2 * U>(pre, act);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = (U == NH) ? u : k0 + u;
+            const NT hc = act[u], ht = act[U + u];
             scr[k] = hc;
             lam1[0] += net.c2(0, k) * hc;
             lam1[1] += net.c2(1, k) * hc;
-            NT ht;
             if (TAU1) {
-                ht = M::tanh_(net.c1(k, 0) * n0 + net.c1(k, 1) * n1);
                 lam2[0] += net.c2(0, k) * ht;
                 lam2[1] += net.c2(1, k) * ht;
             } else {
-                ht = M::tanh_(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
                 lam2[0] += net.t2(0, k) * ht;
                 lam2[1] += net.t2(1, k) * ht;
             }

@@ -1,0 +1,53 @@
+"""GPU: accuracy of the kernel's own fp64 tanh / sin / cos (msc-thesis_b200/csrc/h3_math.cuh) against NumPy
+(glibc, < 1 ulp) over the ranges the closed loop visits and the hand-over points of the branches."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+
+def _probe(fn, x):
+    import msc_thesis_b200 as h3
+    L = h3._lib
+    xd = torch.as_tensor(x, device="cuda")
+    y = torch.empty_like(xd)
+    y2 = torch.empty_like(xd)
+    L.check(h3.lib().h3_math_probe(fn, L.ptr(xd), L.ptr(y), L.ptr(y2), xd.numel(), L.stream_ptr(xd.device)))
+    return y.cpu().numpy(), y2.cpu().numpy()
+
+
+def _ulps(a, b):
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def test_tanh_accuracy():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-0.55, 0.55, 200000), rng.uniform(-6, 6, 200000), rng.uniform(-40, 40, 50000),
+                        rng.uniform(-1e-6, 1e-6, 10000), np.nextafter(0.55, [0, 1, 0, 1]) * [1, 1, -1, -1],
+                        [0.0, -0.0, 1e-300, 19.0, 19.1, 25.0, 25.1, 700.0, -700.0, np.inf, -np.inf]])
+    y, _ = _probe(0, x)
+    want = np.tanh(x)
+    nz = want != 0          # tanh(-0.0) comes back as +0.0: the sign of a zero is not part of the contract
+    assert np.array_equal(np.signbit(y[nz]), np.signbit(want[nz]))
+    assert float(np.nanmax(_ulps(y, want))) <= 3.0
+    yn, _ = _probe(0, np.array([np.nan]))
+    assert np.isnan(yn[0])
+
+
+def test_sincos_accuracy():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-np.pi / 4, np.pi / 4, 200000), rng.uniform(-1e-6, 1e-6, 10000),
+                        rng.uniform(-10, 10, 100000), rng.uniform(-1e6, 1e6, 10000),
+                        [0.0, np.pi / 4, -np.pi / 4, np.nextafter(np.pi / 4, 1), 1e22]])
+    s, c = _probe(1, x)
+    assert float(np.nanmax(_ulps(s, np.sin(x)))) <= 3.0
+    assert float(np.nanmax(_ulps(c, np.cos(x)))) <= 3.0
+    s, c = _probe(1, np.array([np.nan, np.inf]))
+    assert np.isnan(s).all() and np.isnan(c).all()
