@@ -9,7 +9,7 @@ import os
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libheli3dof.so")
+LIB_PATH = os.environ.get("H3_LIB_PATH") or os.path.join(PKG_DIR, "libheli3dof.so")   # override: tuning builds
 
 H3_F64, H3_F32 = 0, 1
 TASKS = {"sinusoid": 0, "velocity": 1, "stop_over_point": 2}

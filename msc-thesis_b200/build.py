@@ -42,8 +42,14 @@ def up_to_date():
     return all(os.path.getmtime(f) <= t for f in _deps())
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile every .cu for sm_100a and link the shared library; returns its path."""
+def build(force=False, verbose=False, extra_flags=(), out=None, sources=SOURCES):
+    """Compile every .cu for sm_100a and link the shared library; returns its path.  `out` / `extra_flags`
+    build a tuning variant next to the default library (selected at run time with H3_LIB_PATH)."""
+    global LIB_PATH, BUILD_DIR
+    if out is not None:
+        LIB_PATH = os.path.join(PKG_DIR, out)
+        BUILD_DIR = os.path.join(PKG_DIR, "build", os.path.splitext(out)[0])
+        force = True
     if not force and up_to_date():
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
@@ -56,8 +62,8 @@ def build(force=False, verbose=False, extra_flags=()):
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        results = list(ex.map(compile_one, sources))
     objs = []
     for src, obj, r in results:
         if verbose or r.returncode != 0:
@@ -75,6 +81,12 @@ def build(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
-                 extra_flags=["-DH3_FAST_BUILD"] if "--fast" in sys.argv else ())
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    if "--fast" in sys.argv:
+        flags.append("-DH3_FAST_BUILD")
+    out = None
+    for a in sys.argv[1:]:
+        if a.startswith("--out="):
+            out = a.split("=", 1)[1]
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, extra_flags=flags, out=out)
     print(path)

@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
             col += (ET)excitation[2 * k];
             cyc += (ET)excitation[2 * k + 1];
         }
-        ET sth, cth;
-        Math<ET>::sincos_(s[4], &sth, &cth);
+        ET sth, cth, scy, ccy;
+        Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
         bool done;
-        env_step(K, s, col, cyc, sth, cth, done);
+        env_step(K, s, col, cyc, sth, cth, scy, ccy, done);
         tt += dt;
         if (states_out != nullptr && e < n_out) {
 #pragma unroll
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
         C.v.p = cov + e;
         C.v.ld = ld;
         (void)sym;
-        rls_update(K, Wm, C, X, Y);
+        rls_update<ET, 1>(K, Wm, C, X, Y);
     }
 #pragma unroll
     for (int i = 0; i < 7; ++i) xp[i * ld + e] = st[i];

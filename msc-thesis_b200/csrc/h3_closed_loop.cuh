@@ -149,8 +149,9 @@ struct LoopLayout {
 //   PLACE : which optional groups live in shared memory (P_* bits); LANES episodes per warp; WARPS per block
 //   UL/UC : hidden units per chunk in the cyclic / collective agent's loops (see h3_tick.cuh); a chunked
 //           agent (U < NH) needs its networks and stash in shared memory
+//   RD    : look-ahead depth (groups) of the RLS shared-memory streams
 template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int PLACE, int LANES,
-          int WARPS, int UL, int UC>
+          int WARPS, int UL, int UC, int RD>
 __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopParams<ET, NT> P) {
     static_assert(UL == NHL || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
     static_assert(UC == NHC || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");
@@ -291,7 +292,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopPa
             }
             // -------- actions (main_3dof.py:132-137); forward activations are kept for the update --------
             ET sth, cth;
-            Math<ET>::sincos_(s[4], &sth, &cth);
             ET cyc, colv;
             {
                 NT fl;
@@ -312,18 +312,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopPa
                 stc[NHC] = fc;
                 stc[NHC + 1] = sc0;
                 stc[NHC + 2] = sc1;
-            } else {
+            }
+            ET exc0 = (ET)0, exc1 = (ET)0;                                      // main_3dof.py:139-140
+            if (lockstep) {
+                exc0 = (ET)sh_exc[2 * jj];
+                exc1 = (ET)sh_exc[2 * jj + 1];
+            } else if (P.excitation != nullptr && k < P.exc_len) {
+                exc0 = (ET)P.excitation[2 * k];
+                exc1 = (ET)P.excitation[2 * k + 1];
+            }
+            cyc += exc1;
+            // sin/cos of theta (model + PID) and of the cyclic pitch (model) in one interleaved evaluation
+            ET scy, ccy;
+            Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
+            if (!phase2) {
                 ET pc = misce[1];
                 colv = pid_collective(K, s, sth, cth, pc);                      // PID.py:16-24
                 misce[1] = pc;
             }
-            if (lockstep) {                                                     // main_3dof.py:139-140
-                colv += (ET)sh_exc[2 * jj];
-                cyc += (ET)sh_exc[2 * jj + 1];
-            } else if (P.excitation != nullptr && k < P.exc_len) {
-                colv += (ET)P.excitation[2 * k];
-                cyc += (ET)P.excitation[2 * k + 1];
-            }
+            colv += exc0;
             // -------- env.step (main_3dof.py:141) --------
             ET X[9], Y[7];
 #pragma unroll
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopPa
             ET cu = misce[0];
             if (P.task == H3_TASK_VELOCITY) (void)velocity_ref(K, s[2], cu);    // heli_models.py:155
             bool done;
-            env_step(K, s, colv, cyc, sth, cth, done);
+            env_step(K, s, colv, cyc, sth, cth, scy, ccy, done);
             const double t_new = miscd[3] + P.dt;                                // heli_models.py:206
             miscd[3] = t_new;
             // -------- next_ref = env.get_ref() (main_3dof.py:142) --------
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopPa
             } else {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) Y[i] = s[i] - Y[i];                 // model.py:43
-                rls_update(K, Wm, cov, X, Y);
+                rls_update<ET, RD>(K, Wm, cov, X, Y);
             }
             // -------- cyclic agent (main_3dof.py:148-151) --------
             double r_lon = 0.0, r_col = 0.0;

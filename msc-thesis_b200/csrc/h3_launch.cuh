@@ -46,6 +46,13 @@ struct Tune {
     static constexpr int UL = lon_smem ? NHL / 2 : NHL;
     static constexpr int UC = COL ? NHC / 2 : NHC;
     static constexpr int WARPS = COL ? 4 : 1;
+#ifndef H3_RD_P1
+#define H3_RD_P1 1
+#endif
+#ifndef H3_RD_P2
+#define H3_RD_P2 2
+#endif
+    static constexpr int RD = COL ? H3_RD_P2 : H3_RD_P1;    // RLS stream look-ahead (groups)
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
     static constexpr size_t room = (SMEM_PER_BLOCK_MAX - L32::head_bytes(WARPS)) / WARPS - 16;
     static constexpr int fit = (int)(room / L32::bytes_per_lane);
@@ -58,7 +65,7 @@ static KernelSel<ET, NT> sel_kernel() {
     typedef Tune<ET, NT, NHL, NHC, COL, VAR> T;
     typedef LoopLayout<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES> LY;
     KernelSel<ET, NT> k;
-    k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES, T::WARPS, T::UL, T::UC>;
+    k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES, T::WARPS, T::UL, T::UC, T::RD>;
     k.block = T::WARPS * 32;
     k.lanes = T::LANES;
     k.warps = T::WARPS;

@@ -80,17 +80,80 @@ struct Math;
 template <>
 struct Math<double> {
     static H3_DEV double tanh_(double x) { return tanh_f64(x); }
+    // U independent arguments at once; the polynomial loops run coefficient-major so that consecutive DFMAs
+    // belong to different elements (a single warp per scheduler then covers the DFMA latency by itself).
     template <int U>
     static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
         bool all_small = true;
 #pragma unroll
         for (int u = 0; u < U; ++u) all_small = all_small && (::fabs(x[u]) < 0.55);
         if (all_small) {
+            double z[U], p[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) y[u] = tanh_small(x[u]);
+            for (int u = 0; u < U; ++u) {
+                z[u] = x[u] * x[u];
+                p[u] = H3_TANH_C[11];
+            }
+#pragma unroll
+            for (int i = 10; i >= 0; --i)
+#pragma unroll
+                for (int u = 0; u < U; ++u) p[u] = fma(p[u], z[u], H3_TANH_C[i]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) y[u] = fma(x[u] * z[u], p[u], x[u]);
         } else {
+            double r[U], q[U], t[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) y[u] = tanh_any(x[u]);
+            for (int u = 0; u < U; ++u) {
+                const double xc = x[u] > 20.0 ? 20.0 : (x[u] < -20.0 ? -20.0 : x[u]);
+                const double yy = xc + xc;
+                t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
+                const double nf = t[u] - 6755399441055744.0;
+                r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
+                q[u] = H3_EXP_C[10];
+            }
+#pragma unroll
+            for (int i = 9; i >= 0; --i)
+#pragma unroll
+                for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
+            double E[U], den[U], rc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double p = fma(r[u] * r[u], q[u], r[u]);
+                const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
+                E[u] = fma(sc, p, sc - 1.0);
+                den[u] = E[u] + 2.0;
+                rc[u] = (double)__frcp_rn((float)den[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double q0 = E[u] * rc[u];
+                y[u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
+            }
+        }
+    }
+    // sin/cos of two independent angles (theta and the cyclic pitch): four interleaved polynomial chains
+    static H3_DEV void sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
+        if (::fabs(a) <= 0.78539816339744828 && ::fabs(b) <= 0.78539816339744828) {
+            const double za = a * a, zb = b * b;
+            double psa = H3_SIN_C[7], pca = H3_COS_C[7], psb = H3_SIN_C[7], pcb = H3_COS_C[7];
+#pragma unroll
+            for (int i = 6; i >= 0; --i) {
+                psa = fma(psa, za, H3_SIN_C[i]);
+                pca = fma(pca, za, H3_COS_C[i]);
+                psb = fma(psb, zb, H3_SIN_C[i]);
+                pcb = fma(pcb, zb, H3_COS_C[i]);
+            }
+            *sa = fma(a * za, psa, a);
+            *ca = fma(za * za, pca, fma(-0.5, za, 1.0));
+            *sb = fma(b * zb, psb, b);
+            *cb = fma(zb * zb, pcb, fma(-0.5, zb, 1.0));
+        } else {
+            sincos_f64(a, sa, ca);
+            sincos_f64(b, sb, cb);
         }
     }
     static H3_DEV double exp_(double x) { return ::exp(x); }
@@ -107,6 +170,10 @@ struct Math<float> {
     static H3_DEV void tanh_vec(const float (&x)[U], float (&y)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
+    }
+    static H3_DEV void sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
+        ::sincosf(a, sa, ca);
+        ::sincosf(b, sb, cb);
     }
     static H3_DEV float exp_(float x) { return ::expf(x); }
     static H3_DEV float sqrt_(float x) { return ::sqrtf(x); }

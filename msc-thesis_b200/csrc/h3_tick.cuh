@@ -57,14 +57,13 @@ __host__ inline EnvK<T> make_envk(const H3Config& c) {
 //   atan2 is eliminated: cos/sin(alpha_c) with alpha_c = cyc - atan2(w,u) are expanded with
 //   cos(atan2(w,u)) = u/V, sin(atan2(w,u)) = w/V, so v_diml*cos(alpha_c) = (u cos cyc + w sin cyc)/v_tip.
 // ----------------------------------------------------------------------------------------------
+//   sc/cc = sin/cos(cyc) (evaluated together with theta's by the caller, four interleaved chains).
 template <typename T>
-H3_DEV void env_step(const EnvK<T>& K, T (&s)[7], T col, T cyc, T sth, T cth, bool& done) {
+H3_DEV void env_step(const EnvK<T>& K, T (&s)[7], T col, T cyc, T sth, T cth, T sc, T cc, bool& done) {
     typedef Math<T> M;
     const T u = s[2], w = s[3], q = s[5], li = s[6];
     const T q_diml = q * K.inv_omega;                       // :159
     const T V = M::sqrt_(u * u + w * w);                    // :160  (vv, :175)
-    T sc, cc;
-    M::sincos_(cyc, &sc, &cc);
     const T mu = (u * cc + w * sc) * K.inv_vtip;            // :163
     const T lc = (u * sc - w * cc) * K.inv_vtip;            // :164
     const T lsum = lc + li;
@@ -139,41 +138,62 @@ H3_DEV T stop_over_point_ref(const EnvK<T>& K, T x, T u, T theta_trim) {    // :
 // RecursiveLeastSquares.update  (model.py:41-59), n = 9 regressors, m = 7 outputs.
 //   Wm(i,j): weight accessor (9x7).  Cv: covariance accessor -- full (9x9) or symmetric-packed.
 // ----------------------------------------------------------------------------------------------
-// A compiler-level fence: memory operations are not moved across it.  Placed between the rows of the
-// unrolled RLS loops it stops ptxas from hoisting all 63 + 45 shared-memory loads to the top (which would
-// need > 200 registers) while still letting one row's loads overlap the previous row's FMAs.
+// A compiler-level fence: memory operations are not moved across it.  The unrolled RLS loops stream the
+// 63 + 45 shared-memory words in groups with an explicit look-ahead of DEPTH groups: the loads of group
+// g + DEPTH are issued before the FMAs of group g, and the fence stops ptxas from hoisting ALL loads to the
+// top (> 200 registers) or sinking them next to their use (latency exposed with one warp per scheduler).
 template <bool ON>
 H3_DEV void row_fence() {
     if (ON) asm volatile("" ::: "memory");
 }
 
-template <typename T, typename WAcc, typename CAcc>
+template <typename T, int NG, int GS, int DEPTH, bool FENCE, typename Load, typename Body>
+H3_DEV void stream_groups(Load load, Body body) {
+    T buf[DEPTH + 1][GS];
+#pragma unroll
+    for (int g = 0; g < DEPTH && g < NG; ++g) load(g, buf[g]);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g + DEPTH < NG) load(g + DEPTH, buf[(g + DEPTH) % (DEPTH + 1)]);
+        row_fence<FENCE>();
+        body(g, buf[g % (DEPTH + 1)]);
+    }
+}
+
+template <typename T, int DEPTH, typename WAcc, typename CAcc>
 H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7]) {
+    constexpr bool F = WAcc::kFence;
     T err[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) err[j] = Y[j];
+    stream_groups<T, 9, 7, DEPTH, F>(                                   // :49-50  err = Y - W^T X
+        [&](int i, T (&w)[7]) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
+            for (int j = 0; j < 7; ++j) w[j] = Wm(i, j);
+        },
+        [&](int i, T (&w)[7]) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) err[j] -= X[i] * Wm(i, j);          // :49-50
-        if (i & 1) row_fence<WAcc::kFence>();
-    }
+            for (int j = 0; j < 7; ++j) err[j] -= X[i] * w[j];
+        });
     T covX[9], Xcov[9];
-    Cv.matvec(X, covX, Xcov);                                           // :53-54
-    T d = K.rls_gamma;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) d += Xcov[j] * X[j];                    // :55
-    const T inv_d = (T)1 / d;
+    Cv.template matvec<DEPTH>(X, covX, Xcov);                           // :53-54
+    const T d0 = (K.rls_gamma + Xcov[0] * X[0]) + Xcov[1] * X[1] + Xcov[2] * X[2];      // :55 (three partial sums)
+    const T d1 = Xcov[3] * X[3] + Xcov[4] * X[4] + Xcov[5] * X[5];
+    const T d2 = Xcov[6] * X[6] + Xcov[7] * X[7] + Xcov[8] * X[8];
+    const T inv_d = (T)1 / (d0 + (d1 + d2));
     T g[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
+    stream_groups<T, 9, 7, DEPTH, F>(                                   // :58  W += (cov X) err / d
+        [&](int i, T (&w)[7]) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
+            for (int j = 0; j < 7; ++j) w[j] = Wm(i, j);
+        },
+        [&](int i, T (&w)[7]) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) Wm(i, j) += g[i] * err[j];          // :58
-        if (i & 1) row_fence<WAcc::kFence>();
-    }
-    Cv.downdate(g, Xcov, K.rls_inv_gamma);                              // :59
+            for (int j = 0; j < 7; ++j) Wm(i, j) = w[j] + g[i] * err[j];
+        });
+    Cv.template downdate<DEPTH>(g, Xcov, K.rls_inv_gamma);              // :59
 }
 
 // covariance policies ------------------------------------------------------------------------
@@ -182,23 +202,34 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
 template <typename T, typename Vec>
 struct CovFull {            // model.py:53-54 literally: cov.X and X^T.cov computed separately
     Vec v;                  // 81 elements, row-major
+    template <int DEPTH>
     H3_DEV void matvec(const T (&X)[9], T (&covX)[9], T (&Xcov)[9]) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) { covX[i] = (T)0; Xcov[i] = (T)0; }
+        stream_groups<T, 9, 9, DEPTH, Vec::kFence>(
+            [&](int i, T (&c)[9]) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
+                for (int j = 0; j < 9; ++j) c[j] = v[i * 9 + j];
+            },
+            [&](int i, T (&c)[9]) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const T c = v[i * 9 + j];
-                covX[i] += c * X[j];
-                Xcov[j] += X[i] * c;
-            }
+                for (int j = 0; j < 9; ++j) {
+                    covX[i] += c[j] * X[j];
+                    Xcov[j] += X[i] * c[j];
+                }
+            });
     }
+    template <int DEPTH>
     H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
+        stream_groups<T, 9, 9, DEPTH, Vec::kFence>(
+            [&](int i, T (&c)[9]) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
+                for (int j = 0; j < 9; ++j) c[j] = v[i * 9 + j];
+            },
+            [&](int i, T (&c)[9]) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) v[i * 9 + j] = (v[i * 9 + j] - g[i] * Xcov[j]) * inv_gamma;
+                for (int j = 0; j < 9; ++j) v[i * 9 + j] = (c[j] - g[i] * Xcov[j]) * inv_gamma;
+            });
     }
 };
 
@@ -206,29 +237,47 @@ template <typename T, typename Vec>
 struct CovSym {             // upper triangle only (45 elements): cov == cov^T is an invariant of
     Vec v;                  // model.py:59 when it holds initially (model.py:85: identity * c)
     __host__ __device__ static constexpr int idx(int i, int j) { return i * 9 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+    // The 45 elements are visited in 5 groups of 9, diagonal by diagonal (group 0: the main diagonal; group
+    // g: the 9-g elements of diagonal g and the g elements of diagonal 9-g), so that consecutive FMAs of the
+    // matrix-vector product hit different accumulators instead of one 9-long dependent chain per row.
+    __host__ __device__ static constexpr int gi(int g, int e) { return g == 0 ? e : (e < 9 - g ? e : e - (9 - g)); }
+    __host__ __device__ static constexpr int gj(int g, int e) {
+        return g == 0 ? e : (e < 9 - g ? e + g : e - (9 - g) + (9 - g));
+    }
+    template <int DEPTH>
     H3_DEV void matvec(const T (&X)[9], T (&covX)[9], T (&Xcov)[9]) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) covX[i] = (T)0;
+        stream_groups<T, 5, 9, DEPTH, Vec::kFence>(
+            [&](int g, T (&c)[9]) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+                for (int e = 0; e < 9; ++e) c[e] = v[idx(gi(g, e), gj(g, e))];
+            },
+            [&](int g, T (&c)[9]) {
 #pragma unroll
-            for (int j = i; j < 9; ++j) {
-                const T c = v[idx(i, j)];
-                covX[i] += c * X[j];
-                if (j != i) covX[j] += c * X[i];
-            }
-            if (i & 1) row_fence<Vec::kFence>();
-        }
+                for (int e = 0; e < 9; ++e) {
+                    const int i = gi(g, e), j = gj(g, e);
+                    covX[i] += c[e] * X[j];
+                    if (j != i) covX[j] += c[e] * X[i];
+                }
+            });
 #pragma unroll
         for (int i = 0; i < 9; ++i) Xcov[i] = covX[i];
     }
+    template <int DEPTH>
     H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
+        stream_groups<T, 5, 9, DEPTH, Vec::kFence>(
+            [&](int gr, T (&c)[9]) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+                for (int e = 0; e < 9; ++e) c[e] = v[idx(gi(gr, e), gj(gr, e))];
+            },
+            [&](int gr, T (&c)[9]) {
 #pragma unroll
-            for (int j = i; j < 9; ++j) v[idx(i, j)] = (v[idx(i, j)] - g[i] * Xcov[j]) * inv_gamma;
-            if (i & 1) row_fence<Vec::kFence>();
-        }
+                for (int e = 0; e < 9; ++e) {
+                    const int i = gi(gr, e), j = gj(gr, e);
+                    v[idx(i, j)] = (c[e] - g[i] * Xcov[j]) * inv_gamma;
+                }
+            });
     }
 };
 
@@ -330,35 +379,56 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
     // pass 2: SGD (:184-188): wa += lr_a (target.G) da/dwa ; wc -= lr_c dL/dwc, then soft target update (:195-196)
     const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
     const NT one_m_tau = (NT)1 - H.tau;
+    // (narrower chunks than pass 1: 13 values per unit are live here)
+    constexpr int V = (U == NH) ? NH : ((NH % 2 == 0) ? 2 : 1);
 #pragma unroll 1
-    for (int k0 = 0; k0 < NH; k0 += U) {
+    for (int k0 = 0; k0 < NH; k0 += V) {
+        // all loads of the chunk first (one shared-memory latency per chunk, not per element) ...
+        NT hc[V], ha[V], a10[V], a11[V], a2k[V], c10[V], c11[V], c20[V], c21[V], t10[V], t11[V], t20[V], t21[V];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int k = (U == NH) ? u : k0 + u;
-            const NT hc = scr[k], ha = h_a[k];
-            const NT a2k = net.a2(k);
-            const NT pk = delta * a2k * ((NT)1 - ha * ha);
-            const NT c20o = net.c2(0, k), c21o = net.c2(1, k);
-            const NT back = (c20o * e_c[0] + c21o * e_c[1]) * ((NT)1 - hc * hc);
+        for (int u = 0; u < V; ++u) {
+            const int k = (V == NH) ? u : k0 + u;
+            hc[u] = scr[k];
+            ha[u] = h_a[k];
+            a10[u] = net.a1(k, 0);
+            a11[u] = net.a1(k, 1);
+            a2k[u] = net.a2(k);
+            c10[u] = net.c1(k, 0);
+            c11[u] = net.c1(k, 1);
+            c20[u] = net.c2(0, k);
+            c21[u] = net.c2(1, k);
+            if (!TAU1) {
+                t10[u] = net.t1(k, 0);
+                t11[u] = net.t1(k, 1);
+                t20[u] = net.t2(0, k);
+                t21[u] = net.t2(1, k);
+            }
+        }
+        // ... then the arithmetic and the stores
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int k = (V == NH) ? u : k0 + u;
+            const NT pk = delta * a2k[u] * ((NT)1 - ha[u] * ha[u]);
+            const NT back = (c20[u] * e_c[0] + c21[u] * e_c[1]) * ((NT)1 - hc[u] * hc[u]);
             // actor
-            net.a1(k, 0) += ka * (pk * s0);
-            net.a1(k, 1) += ka * (pk * s1);
-            net.a2(k) = a2k + ka * (delta * ha);
+            net.a1(k, 0) = a10[u] + ka * (pk * s0);
+            net.a1(k, 1) = a11[u] + ka * (pk * s1);
+            net.a2(k) = a2k[u] + ka * (delta * ha[u]);
             // critic
-            const NT c10 = net.c1(k, 0) - H.lr_c * (back * s0);
-            const NT c11 = net.c1(k, 1) - H.lr_c * (back * s1);
-            const NT c20 = c20o - H.lr_c * (e_c[0] * hc);
-            const NT c21 = c21o - H.lr_c * (e_c[1] * hc);
-            net.c1(k, 0) = c10;
-            net.c1(k, 1) = c11;
-            net.c2(0, k) = c20;
-            net.c2(1, k) = c21;
+            const NT n10 = c10[u] - H.lr_c * (back * s0);
+            const NT n11 = c11[u] - H.lr_c * (back * s1);
+            const NT n20 = c20[u] - H.lr_c * (e_c[0] * hc[u]);
+            const NT n21 = c21[u] - H.lr_c * (e_c[1] * hc[u]);
+            net.c1(k, 0) = n10;
+            net.c1(k, 1) = n11;
+            net.c2(0, k) = n20;
+            net.c2(1, k) = n21;
             // target critic
             if (!TAU1) {
-                net.t1(k, 0) = H.tau * c10 + one_m_tau * net.t1(k, 0);
-                net.t1(k, 1) = H.tau * c11 + one_m_tau * net.t1(k, 1);
-                net.t2(0, k) = H.tau * c20 + one_m_tau * net.t2(0, k);
-                net.t2(1, k) = H.tau * c21 + one_m_tau * net.t2(1, k);
+                net.t1(k, 0) = H.tau * n10 + one_m_tau * t10[u];
+                net.t1(k, 1) = H.tau * n11 + one_m_tau * t11[u];
+                net.t2(0, k) = H.tau * n20 + one_m_tau * t20[u];
+                net.t2(1, k) = H.tau * n21 + one_m_tau * t21[u];
             }
         }
     }
