@@ -300,8 +300,20 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback"
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
+        # DRAM traffic and pipe utilisation of the same kernels from the committed ncu capture (per episode)
+        traffic, ncu_note = None, None
+        tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tfile) and a.precision == "f64":
+            tj = json.load(open(tfile))
+            per_ep = (tj["phase1"]["dram_bytes_per_episode"] * half + tj["phase2"]["dram_bytes_per_episode"] * (K - half)) / K
+            traffic = per_ep * n
+            ncu_note = {"source": tj.get("source"), "fp64_pipe_active_pct": {"phase1": tj["phase1"]["fp64_pipe_active_pct"],
+                                                                             "phase2": tj["phase2"]["fp64_pipe_active_pct"]},
+                        "dram_throughput_pct": {"phase1": tj["phase1"]["dram_throughput_pct"],
+                                                "phase2": tj["phase2"]["dram_throughput_pct"]}}
         roofline = {"bound": "fp64" if a.precision != "f32" else "fp32", "achieved": achieved / 1e12,
-                    "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "ncu": ncu_note,
                     "peak_source": "FMA-chain microbenchmark in this run (h3_fma_peak, 2 flop/FMA)",
                     "flops_per_env_step": {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2,
                                            "note": "literal reference operator count; transcendental calls "

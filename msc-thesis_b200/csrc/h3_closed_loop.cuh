@@ -22,6 +22,10 @@ namespace h3 {
 // PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
+#ifndef H3_PAIR_SPLIT_W
+#define H3_PAIR_SPLIT_W 0     // PAIR mode: split the columns of the RLS weight matrix between the two lanes
+#endif
+
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
 template <typename ET, typename NT>
@@ -81,9 +85,7 @@ H3_DEV void transition_matrices(WAcc& Wm, const H3AgentHyper& h, NT (&F)[2][2], 
 }
 
 template <typename T, typename Vec>
-struct WMatD : WMat<T, Vec> {       // + runtime-indexed read (shared memory: plain address arithmetic)
-    H3_DEV T dyn(int i, int j) { return this->v[i * 7 + j]; }
-};
+struct WMatD : WMat<T, Vec> {};     // shared-memory flavour (runtime-indexed reads are plain address arithmetic)
 
 template <int NWARP>
 H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [NWARP][H3_N_STATS] */) {
@@ -413,7 +415,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopPa
             } else {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) Y[i] = s[i] - Y[i];                 // model.py:43
-                rls_update<ET, RD>(K, Wm, cov, X, Y);
+                rls_update<ET, RD, PAIR && H3_PAIR_SPLIT_W>(K, Wm, cov, X, Y, half);
+                if (PAIR) __syncwarp(amask);            // F, G below read columns owned by the partner lane
             }
             // -------- cyclic agent (main_3dof.py:148-151) --------
             double r_lon = 0.0, r_col = 0.0;

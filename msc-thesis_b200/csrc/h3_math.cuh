@@ -109,8 +109,9 @@ struct Math<double> {
                 t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
                 const double nf = t[u] - 6755399441055744.0;
                 r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
-                q[u] = H3_EXP_C[10];
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = H3_EXP_C[10];
 #pragma unroll
             for (int i = 9; i >= 0; --i)
 #pragma unroll

@@ -160,20 +160,25 @@ H3_DEV void stream_groups(Load load, Body body) {
     }
 }
 
-template <typename T, int DEPTH, typename WAcc, typename CAcc>
-H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7]) {
+//   PAIR: the two lanes of an episode split the 7 output columns of W (lane half h owns columns
+//   [4h, 4h + NC), NC = 4 or 3): the prediction error and the weight update of a column need nothing from
+//   the other columns, so no exchange is required; the covariance part is computed by both lanes.
+template <typename T, int DEPTH, bool PAIR = false, typename WAcc, typename CAcc>
+H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7], int half = 0) {
     constexpr bool F = WAcc::kFence;
-    T err[7];
+    constexpr int NC = PAIR ? 4 : 7;            // columns handled by this lane (the 4th is masked for half 1)
+    const int j0 = PAIR ? 4 * half : 0;
+    T err[NC];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) err[j] = Y[j];
-    stream_groups<T, 9, 7, DEPTH, F>(                                   // :49-50  err = Y - W^T X
-        [&](int i, T (&w)[7]) {
+    for (int j = 0; j < NC; ++j) err[j] = PAIR ? (half ? Y[j < 3 ? 4 + j : 6] : Y[j]) : Y[j];
+    stream_groups<T, 9, NC, DEPTH, F>(                                  // :49-50  err = Y - W^T X
+        [&](int i, T (&w)[NC]) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) w[j] = Wm(i, j);
+            for (int j = 0; j < NC; ++j) w[j] = (PAIR && j == 3) ? Wm.dyn(i, half ? 6 : 3) : Wm.dyn(i, j0 + j);
         },
-        [&](int i, T (&w)[7]) {
+        [&](int i, T (&w)[NC]) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) err[j] -= X[i] * w[j];
+            for (int j = 0; j < NC; ++j) err[j] -= X[i] * w[j];
         });
     T covX[9], Xcov[9];
     Cv.template matvec<DEPTH>(X, covX, Xcov);                           // :53-54
@@ -184,14 +189,21 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
     T g[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
-    stream_groups<T, 9, 7, DEPTH, F>(                                   // :58  W += (cov X) err / d
-        [&](int i, T (&w)[7]) {
+    stream_groups<T, 9, NC, DEPTH, F>(                                  // :58  W += (cov X) err / d
+        [&](int i, T (&w)[NC]) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) w[j] = Wm(i, j);
+            for (int j = 0; j < NC; ++j) w[j] = (PAIR && j == 3) ? Wm.dyn(i, half ? 6 : 3) : Wm.dyn(i, j0 + j);
         },
-        [&](int i, T (&w)[7]) {
+        [&](int i, T (&w)[NC]) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) Wm(i, j) = w[j] + g[i] * err[j];
+            for (int j = 0; j < NC; ++j) {
+                const T nw = w[j] + g[i] * err[j];
+                if (PAIR && j == 3) {
+                    if (!half) Wm.ref(i, 3) = nw;       // half 1 owns columns 4..6 only: its 4th slot re-did column 6
+                } else {
+                    Wm.ref(i, j0 + j) = nw;
+                }
+            }
         });
     Cv.template downdate<DEPTH>(g, Xcov, K.rls_inv_gamma);              // :59
 }
@@ -490,6 +502,8 @@ struct WMat {               // RLS weights (9,7) row-major
     static constexpr bool kFence = Vec::kFence;
     Vec v;
     H3_DEV T& operator()(int i, int j) { return v[i * 7 + j]; }
+    H3_DEV T dyn(int i, int j) { return v[i * 7 + j]; }
+    H3_DEV T& ref(int i, int j) { return v[i * 7 + j]; }
 };
 
 template <typename NT, int NH, typename Vec, bool OFFS = false>
