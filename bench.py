@@ -44,51 +44,54 @@ def parse():
     ap.add_argument("--store", type=int, default=0, help="0 default, 1 local arrays, 2 shared-memory tile")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-episodes", type=int, default=4096)
-    ap.add_argument("--cpu-ticks", type=int, default=300)
+    ap.add_argument("--cpu-episodes", type=int, default=16384, help="CPU sample: episodes (per host thread for "
+                                                                     "--impl reference)")
+    ap.add_argument("--cpu-ticks", type=int, default=400)
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------
 # CPU legs (the oracle; the only place besides tests/ and smoke() that may execute oracle/)
 # ---------------------------------------------------------------------------------------------------------
-def _oracle_chunk(args):
-    n, n_ticks, seed, switch = args
-    import numpy as _np
+def _cpu_workload(n, n_ticks, seed=0):
+    """Same workload shape as the GPU arm on a bounded sample: main_3dof.py scenario, excitation on, phase
+    switch at the midpoint of the sample."""
     from oracle import heli3dof_np as O
     from tests import helpers as H
     cfg = O.default_config()
-    cfg["switch_step"] = switch
+    cfg["switch_step"] = n_ticks // 2
     cfg["excitation"] = H.excitation_closed_form()
     S = O.init_state(n, v_initial=10.0, cfg=cfg, seed=seed)
+    return S, cfg
+
+
+def cpu_c_oracle_rate(n, n_ticks, threads=1):
+    """env-steps/s of the compiled C restatement (oracle/heli3dof_ref.c) on `threads` host threads (OpenMP
+    over episodes).  Conversion to the C array-of-structs is outside the timed region."""
+    from oracle import c_oracle as CO
+    S, cfg = _cpu_workload(n, n_ticks)
+    E = CO.pack(S)
+    CO.run_packed(E[:64].copy(), cfg, 4, threads=threads)        # load the library, spin up the thread pool
+    t0 = time.perf_counter()
+    steps = CO.run_packed(E, cfg, n_ticks, threads=threads)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def cpu_numpy_oracle_rate(n, n_ticks):
+    from oracle import heli3dof_np as O
+    S, cfg = _cpu_workload(n, n_ticks)
     t0 = time.perf_counter()
     O.run(S, cfg, n_ticks, "all64")
     dt = time.perf_counter() - t0
-    return float(S["step"].sum()), dt
-
-
-def cpu_oracle_rate(n, n_ticks, procs=1):
-    """env-steps/s of the NumPy oracle on `procs` host processes, same workload shape (half the ticks in
-    each phase)."""
-    switch = n_ticks // 2
-    if procs <= 1:
-        steps, dt = _oracle_chunk((n, n_ticks, 0, switch))
-        return steps / dt, dt
-    import multiprocessing as mp
-    per = max(1, n // procs)
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        pool.map(_oracle_chunk, [(8, 2, 0, 1)] * procs)         # warm the workers (imports)
-        t0 = time.perf_counter()
-        res = pool.map(_oracle_chunk, [(per, n_ticks, i, switch) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    return sum(r[0] for r in res) / wall, wall
+    return float(S["step"].sum()) / dt, dt
 
 
 def run_reference_arm(a):
     """--impl reference: the reference's algorithm for this path on the host cores.  The reference is
-    pure Python (NumPy + torch-CPU) and cannot travel to the GPU box, so this leg runs its pinned CPU
-    restatement (oracle/heli3dof_np.py, `kind: port`) on every host core."""
+    pure Python (NumPy + torch-CPU autograd, 400-485 ticks/s per core in the build container)
+    and cannot travel to the GPU box, so this leg runs its pinned, compiled CPU restatement
+    (oracle/heli3dof_ref.c, `kind: port`) on every host core -- a far stronger baseline than the reference."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -96,18 +99,20 @@ def run_reference_arm(a):
     n, n_ticks = a.cpu_episodes * cores, a.cpu_ticks
     vals = []
     for i in range(a.warmup + a.steps):
-        v, wall = cpu_oracle_rate(n, n_ticks, procs=cores)
+        v, wall = cpu_c_oracle_rate(n, n_ticks, threads=cores)
         if i >= a.warmup:
             vals.append((v, wall))
     v = float(np.mean([x[0] for x in vals]))
     wall = float(np.mean([x[1] for x in vals]))
-    sample = "%d episodes x %d ticks per step over %d processes (NumPy oracle, fp64)" % (n, n_ticks, cores)
+    sample = "%d episodes x %d ticks per step on %d OpenMP threads (C oracle oracle/heli3dof_ref.c, fp64)" % (
+        n, n_ticks, cores)
     print(json.dumps({
         "impl": "reference", "metric": "closed-loop env-steps/sec (model+RLS+actor-critic)", "value": v,
         "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config3: 3-DOF closed-loop (RLS + IDHP actor-critic), CPU sample", "sample": sample},
+        "config": {"workload": "config3: 3-DOF closed-loop training (RLS incremental model + IDHP actor-critic "
+                               "online update), bounded CPU sample", "sample": sample},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -235,6 +240,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if "H3_KEEP_NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     h3.lib()
 
@@ -391,11 +398,15 @@ def main():
     # ---- CPU baseline: the oracle on one host core, bounded sample ----
     if rank == 0:
         if not a.no_cpu and world == 1:
-            v, wall = cpu_oracle_rate(a.cpu_episodes, a.cpu_ticks, procs=1)
+            v, wall = cpu_c_oracle_rate(a.cpu_episodes, a.cpu_ticks, threads=1)
+            v_np, wall_np = cpu_numpy_oracle_rate(max(256, a.cpu_episodes // 8), max(50, a.cpu_ticks // 6))
             out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                   "sample": "%d episodes x %d ticks, NumPy oracle (oracle/heli3dof_np.py), "
-                                             "1 process, %.1f s" % (a.cpu_episodes, a.cpu_ticks, wall),
-                                   "host_cores": os.cpu_count()}
+                                   "sample": "%d episodes x %d ticks, compiled C oracle (oracle/heli3dof_ref.c), "
+                                             "1 thread, %.1f s" % (a.cpu_episodes, a.cpu_ticks, wall),
+                                   "host_cores": os.cpu_count(),
+                                   "numpy_oracle_env_steps_per_s": v_np,
+                                   "reference_python_loop_ticks_per_s": "400-485 per core (measured in the build "
+                                                                        "container, BASELINE.md section 2)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -2,7 +2,7 @@
 import json
 import sys
 
-d = json.load(open(sys.argv[1]))
+d = json.loads([ln for ln in open(sys.argv[1]).read().splitlines() if ln.startswith('{')][-1])
 for k in ("value", "ms_per_step", "phase1_env_steps_per_s_rank0", "phase1_ms_per_launch_rank0",
           "phase2_ms_per_launch_rank0", "alive_fraction_end"):
     print(k, d.get(k))
