@@ -1,0 +1,7 @@
+"""Drop-in module name of the reference (`from model import ...` as in main_3dof.py:8-12): put this directory
+on sys.path instead of the reference checkout and the batched B200 classes are picked up."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from msc_thesis_b200 import RecursiveLeastSquares  # noqa: E402,F401

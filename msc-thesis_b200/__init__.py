@@ -20,6 +20,7 @@ from .distributed import allreduce_stats, shard_range
 from .excitation import excitation_signal, load_excitation
 from .heli_models import Helicopter3DOF
 from .model import RecursiveLeastSquares
+from . import sweep
 
 __all__ = ["Helicopter3DOF", "CollectivePID3DOF", "RecursiveLeastSquares", "DHPAgent", "DHPActor", "DHPCritic",
            "ClosedLoop3DOF", "TRAJ_COLUMNS", "sinusoid_ref_table", "excitation_signal", "load_excitation",

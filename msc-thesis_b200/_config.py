@@ -75,7 +75,8 @@ def build_config(env=None, pid=None, rls=None, col=None, lon=None, env_dtype=tor
         kp, ki, kd = env.pid_weights if len(env.pid_weights) == 3 else (0.0, 0.0, 0.0)
         cfg.env_kp, cfg.env_ki, cfg.env_kd = float(kp), float(ki), float(kd)
         cfg.env_ref = float(env.ref) if env.ref is not None and not torch.is_tensor(env.ref) else 0.0
-        cfg.ref_amp, cfg.ref_period = float(env.ref_amplitude), float(env.ref_period)
+        cfg.ref_amp = 10.0 if is_per_episode(env.ref_amplitude) else scalar(env.ref_amplitude)
+        cfg.ref_period = 10.0 if is_per_episode(env.ref_period) else scalar(env.ref_period)
         env_dtype = env.dtype
     else:
         cfg.env = L.default_env_params(dt)

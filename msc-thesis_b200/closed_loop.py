@@ -116,6 +116,7 @@ class ClosedLoop3DOF:
         col_hyper, lon_hyper = self.agent_col._hyper_rows(), self.agent_lon._hyper_rows()
         b = self._batch(col_hyper, lon_hyper)
         traj = None
+        self._t_at_record_start = env.t
         if record:
             traj = torch.zeros(n_ticks, L.TRAJ_ROWS, record, dtype=env.dtype, device=self.device)
         stream = L.stream_ptr(self.device)
@@ -161,6 +162,23 @@ class ClosedLoop3DOF:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.stats_dev, op=dist.ReduceOp.SUM, group=group)
         return self.stats_dev
+
+    def to_dataframe(self, traj, episode=0, t0=None):
+        """The per-tick log of main_3dof.py:164-175 for one recorded episode as a pandas DataFrame with the
+        reference's column names (t, x, z, u, w, theta, q, reference, collective, cyclic, r1, r2): what
+        plotting.plot_stats_3dof consumes.  `t` is env.t AFTER the step, accumulated like heli_models.py:206."""
+        import pandas as pd
+        rows = traj[:, :, episode].detach().cpu().double().numpy()
+        rows = rows[rows[:, 12] > 0]                     # ticks this episode actually executed
+        t = np.empty(len(rows))
+        acc = float(self._t_at_record_start if t0 is None else t0)
+        for i in range(len(rows)):
+            acc = acc + self.env.dt
+            t[i] = acc
+        names = ("x", "z", "u", "w", "theta", "q", "lambda_i", "reference", "collective", "cyclic", "r1", "r2")
+        df = pd.DataFrame({n: rows[:, i] for i, n in enumerate(names) if n != "lambda_i"})
+        df.insert(0, "t", t)
+        return df
 
     def info(self, phase2=True):
         """Occupancy facts of the kernel variant run() would launch (block, smem, blocks/SM, registers)."""

@@ -100,6 +100,18 @@ class Helicopter3DOF:
         self.pid_weights = (params["kp"], params["ki"], params["kd"])
         self.ref = params["ref"]
 
+    def set_reference_signal(self, amplitude=10.0, period=10.0):
+        """Generalised sinusoid task (heli_models.py:220-235 hard-codes 10 deg / 10 s):
+        theta_ref = deg2rad(A / 1.76 (sin(pi t / T) + sin(2 pi t / T))) with scalar or per-episode (N,) A, T."""
+        from ._config import is_per_episode
+        self.ref_amplitude, self.ref_period = amplitude, period
+        if is_per_episode(amplitude) or is_per_episode(period):
+            a = as_vec(amplitude, self.n_envs, torch.float64, self.device)
+            p = as_vec(period, self.n_envs, torch.float64, self.device)
+            self.ref_params = torch.stack([a, p]).contiguous()
+        else:
+            self.ref_params = None
+
     def reset(self, v_initial=0.5):
         """heli_models.py:285-291; v_initial may be a scalar or one speed per episode."""
         trimmed_controls, trimmed_state = self._trim(v_initial)

@@ -87,7 +87,7 @@ def make_loop(S, cfg, mode="all64", device="cuda", heterogeneous=False, env_dtyp
     env.task = cfg["task"]
     env.pid_weights = (cfg["env_kp"], cfg["env_ki"], cfg["env_kd"])
     env.ref = cfg["env_ref"]
-    env.ref_amplitude, env.ref_period = cfg["ref_amp"], cfg["ref_period"]
+    env.set_reference_signal(cfg["ref_amp"], cfg["ref_period"])
     env.state = torch.as_tensor(S["state"]).to(device, edt).contiguous()
     env.trimmed_controls = torch.as_tensor(S["trim"]).to(device, torch.float64).contiguous()
     env.trimmed_state = torch.zeros(7, n, dtype=torch.float64, device=device)

@@ -341,3 +341,70 @@ def test_f32_path_tolerance(h3):
         ref = g["state"][:1000, col]
         rms = np.sqrt(np.mean((traj[:, col] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
         assert rms <= 2e-2, (col, rms)
+
+
+# ------------------------------------------------------------------------------------------------------
+# per-episode reference signals (config 5), log export, sweep driver (config 4)
+# ------------------------------------------------------------------------------------------------------
+def test_per_episode_reference_signals_vs_oracle(h3):
+    """Randomised trims and reference signals (amplitude, period per episode; BASELINE config 5): the kernel
+    evaluates the sinusoid per episode; compared with the oracle per tick from a common state."""
+    n = 512
+    rng = np.random.default_rng(9)
+    cfg = O.default_config()
+    cfg["switch_step"] = 20
+    cfg["ref_amp"] = rng.uniform(5, 15, n)
+    cfg["ref_period"] = rng.uniform(5, 15, n)
+    S = O.init_state(n, v_initial=rng.uniform(5, 25, n), cfg=cfg, seed=2)
+    loop = H.make_loop(_clone_state(S), cfg, ticks_per_launch=25)
+    P = _clone_state(S)
+    P["state"] = P["state"] * (1 + 2.0 ** -52)
+    loop.run(60)
+    O.run(S, cfg, 60, "all64")
+    O.run(P, cfg, 60, "all64")
+    sens = H.episode_errors(P, S)
+    H.compare_states(H.loop_state(loop), S, np.maximum(1e-9, 1e3 * sens), what="per-episode sinusoid")
+    one = H.make_loop(_clone_state(S), cfg)
+    one.run(1)
+    O.run(S, cfg, 1, "all64")
+    H.compare_states(H.loop_state(one), S, TOL64, what="per-episode sinusoid, one tick")
+
+
+def test_log_export_matches_reference_columns(h3):
+    g = H.load("seed2_all64.npz")
+    snap = H.snaps_from(g, "snap_")[0]
+    S = O.state_from_snapshots([snap], "all64")
+    S["theta_trim"][:] = snap["state"][4]
+    loop = H.make_loop(S, O.default_config())
+    traj = loop.run(300, record=1)
+    df = loop.to_dataframe(traj, 0)
+    assert list(df.columns) == ["t", "x", "z", "u", "w", "theta", "q", "reference", "collective", "cyclic", "r1", "r2"]
+    assert np.array_equal(df["t"].to_numpy(), g["t"][:300])                # env.t after the step, bit for bit
+    assert np.array_equal(df["reference"].to_numpy(), g["ref"][:300, 1])   # host-made table == reference's values
+    assert np.max(np.abs(df["theta"].to_numpy() - g["state"][:300, 4])) < 1e-12
+    assert np.max(np.abs(df["cyclic"].to_numpy() - g["actions"][:300, 1])) < 1e-12
+
+
+def test_sweep_is_shard_independent(h3):
+    """main.py-style sweep: per-setting success counts / scores must not depend on how the expanded
+    (setting, seed) list is sharded over ranks."""
+    grid = {"tau_target_critic": [0.01, 1.0], "learning_rate_actor": [0.1, 0.4], "nn_stdev": [0.1, 0.2]}
+    keys, settings, setting_of, seed_of = h3.sweep.expand_grid(grid, n_seeds=6)
+    n = len(setting_of)
+    kw = dict(switch_step=60, score_window=(20, 120), ticks_per_launch=40)
+    whole = h3.sweep.build_sweep_loop(keys, settings, setting_of, seed_of, 0, n, **kw)
+    whole.run(120)
+    res = h3.sweep.sweep_results(whole, setting_of, len(settings), 100)
+    parts = []
+    for r in range(3):
+        lo, hi = h3.shard_range(n, r, 3)
+        lp = h3.sweep.build_sweep_loop(keys, settings, setting_of, seed_of, lo, hi, **kw)
+        lp.run(120)
+        assert torch.equal(lp.env.state, whole.env.state[:, lo:hi])
+        assert torch.equal(lp.acc, whole.acc[:, lo:hi])
+        parts.append(h3.sweep.sweep_results(lp, setting_of[lo:hi], len(settings), 100))
+    assert np.array_equal(sum(p["n"] for p in parts), res["n"]) and res["n"].sum() == n
+    assert np.array_equal(sum(p["success"] for p in parts), res["success"])
+    assert np.all(res["success"] <= res["n"]) and np.isfinite(res["mean_score_of_successes"][res["success"] > 0]).all()
+    st = whole.stats()
+    assert st["n"] == n and st["n_alive"] == res["success"].sum()

@@ -189,3 +189,26 @@ def test_launch_plan_splits_at_the_phase_switch():
     assert loop.plan(500) == [(0, 400), (400, 100)]
     loop.k = None
     assert loop.plan(300) == [(0, 300)]
+
+
+def test_sweep_grid_and_compat_modules():
+    keys, settings, setting_of, seed_of = h3.sweep.expand_grid({"a": [1, 2, 3], "b": [10, 20]}, n_seeds=4)
+    assert keys == ["a", "b"] and settings.shape == (6, 2) and len(setting_of) == 24
+    assert list(settings[1]) == [1, 20] and list(setting_of[:5]) == [0, 0, 0, 0, 1] and list(seed_of[:5]) == [0, 1, 2, 3, 0]
+    # per-episode draws depend on (seed, salt) only, not on the shard they are generated in
+    a = h3.sweep._normal((3, 2), np.arange(10), 5)
+    b = h3.sweep._normal((3, 2), np.arange(4, 10), 5)
+    assert torch.equal(a[..., 4:], b)
+    # the reference's module names resolve to the batched classes when compat/ is on sys.path
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        for mod, name in (("agents", "DHPAgent"), ("model", "RecursiveLeastSquares"), ("heli_models", "Helicopter3DOF"),
+                          ("PID", "CollectivePID3DOF")):
+            sys.modules.pop(mod, None)
+            assert getattr(importlib.import_module(mod), name) is getattr(h3, name)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for mod in ("agents", "model", "heli_models", "PID"):
+            sys.modules.pop(mod, None)
