@@ -23,7 +23,7 @@ namespace h3 {
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
 #ifndef H3_PAIR_SPLIT_W
-#define H3_PAIR_SPLIT_W 0     // PAIR mode: split the columns of the RLS weight matrix between the two lanes
+#define H3_PAIR_SPLIT_W 1     // PAIR mode: split the columns of the RLS weight matrix between the two lanes
 #endif
 
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
@@ -159,9 +159,10 @@ struct LoopLayout {
 //           could keep only one warp per scheduler, every latency exposed; PAIR gives two, each with half
 //           the agent work on its critical path.  Both halves of a 64-bit shared-memory access are separate
 //           wavefronts anyway, so the 16-lane rows cost no extra bank conflicts.
+//   MINB  : minimum resident CTAs per SM the register allocation has to allow
 template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int PLACE, int LANES,
-          int WARPS, int UL, int UC, int RD, bool PAIR>
-__global__ void __launch_bounds__(WARPS * 32, 1) closed_loop_kernel(const LoopParams<ET, NT> P) {
+          int WARPS, int UL, int UC, int RD, bool PAIR, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const LoopParams<ET, NT> P) {
     constexpr int NHLh = PAIR ? NHL / 2 : NHL, NHCh = PAIR ? NHC / 2 : NHC;     // hidden units of this lane
     static_assert(UL == NHLh || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
     static_assert(UC == NHCh || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");

@@ -42,16 +42,26 @@ template <typename ET, typename NT, int NHL, int NHC, bool COL, int VAR>
 struct Tune {
     static constexpr bool SYM = VAR != VAR_GENERAL, HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
     static constexpr bool lon_smem = !TAU1L;                // the full cyclic agent (11 nh words) goes to the tile
+#ifndef H3_P1_PAIR
+#define H3_P1_PAIR 0        // tuning: two lanes per episode in phase-1 launches as well
+#endif
+#ifndef H3_P1_MINB
+#define H3_P1_MINB 1
+#endif
+#ifndef H3_P1_WARPS
+#define H3_P1_WARPS 8
+#endif
 #ifndef H3_NO_PAIR
     // collective-agent launches of the fast variant: two lanes per episode (see closed_loop_kernel, PAIR)
-    static constexpr bool PAIR = COL && VAR == VAR_FAST && NHL % 2 == 0 && NHC % 2 == 0;
+    static constexpr bool PAIR = (COL || H3_P1_PAIR) && VAR == VAR_FAST && NHL % 2 == 0 && NHC % 2 == 0;
 #else
     static constexpr bool PAIR = false;
 #endif
+    static constexpr int MINB = (!COL && PAIR) ? H3_P1_MINB : 1;
     static constexpr int PLACE = PAIR ? 0 : ((COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0));
     static constexpr int UL = PAIR ? NHL / 2 : (lon_smem ? NHL / 2 : NHL);
     static constexpr int UC = PAIR ? NHC / 2 : (COL ? NHC / 2 : NHC);
-    static constexpr int WARPS = PAIR ? 8 : (COL ? 4 : 1);
+    static constexpr int WARPS = PAIR ? (COL ? 8 : H3_P1_WARPS) : (COL ? 4 : 1);
 #ifndef H3_RD_P1
 #define H3_RD_P1 1
 #endif
@@ -60,7 +70,7 @@ struct Tune {
 #endif
     static constexpr int RD = COL ? H3_RD_P2 : H3_RD_P1;    // RLS stream look-ahead (groups)
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
-    static constexpr size_t room = (SMEM_PER_BLOCK_MAX - L32::head_bytes(WARPS)) / WARPS - 16;
+    static constexpr size_t room = (SMEM_PER_BLOCK_MAX / MINB - 1024 * (MINB - 1) - L32::head_bytes(WARPS)) / WARPS - 16;
     static constexpr int fit = (int)(room / L32::bytes_per_lane);
     static constexpr int cap = PAIR ? 16 : 32;
     static constexpr int LANES = fit >= cap ? cap : fit;
@@ -73,7 +83,7 @@ static KernelSel<ET, NT> sel_kernel() {
     typedef LoopLayout<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES> LY;
     KernelSel<ET, NT> k;
     k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES, T::WARPS, T::UL,
-                              T::UC, T::RD, T::PAIR>;
+                              T::UC, T::RD, T::PAIR, T::MINB>;
     k.block = T::WARPS * 32;
     k.lanes = T::LANES;
     k.warps = T::WARPS;
