@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--precision", default="f64", choices=["f64", "mixed", "f32"])
     ap.add_argument("--store", type=int, default=0, help="0 default, 1 local arrays, 2 shared-memory tile")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=16384, help="CPU sample: episodes (per host thread for "
                                                                      "--impl reference)")
@@ -198,13 +199,6 @@ def make_workload(h3, torch, n, precision, device, seed, store, ticks):
     return loop
 
 
-def state_tensors(loop):
-    """Every mutable per-episode tensor of the loop (what a host-resident batch consists of)."""
-    env, rls = loop.env, loop.rls
-    return [env.state, env.t_ep, loop.ref2, env.corr_u, loop.pid.hdot_corr, rls._W, rls._cov, rls.x, rls.u,
-            rls._skip, loop.agent_col.net, loop.agent_lon.net, env.step_count, env.flags, env.term_step, loop.acc]
-
-
 def fma_peak(h3, torch, dtype_code, device):
     import ctypes as C
     lib = h3.lib()
@@ -348,40 +342,42 @@ def main():
         }
 
     # ---- e2e: same metric through the public API from HOST buffers (H2D + launch + D2H every step) ----
+    # The batch lives in pinned host memory as `n_chunks` chunks; h3.HostBatchPipeline streams them through two
+    # device slots on two CUDA streams, so uploads, launches and downloads overlap.
     if not a.no_e2e:
-        tensors = state_tensors(loop)
-        loop2 = make_workload(h3, torch, n, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
-        loop2.switch_step = T // 2
-        dev_t = state_tensors(loop2)
-        del loop, tensors
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in dev_t]
-        res_dev = [loop2.acc, loop2.env.flags, loop2.env.term_step, loop2.env.step_count, loop2.stats_dev]
-        res_host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res_dev]
-        h2d = sum(t.numel() * t.element_size() for t in host)
-        d2h = sum(t.numel() * t.element_size() for t in res_host)
-        t0_host = loop2.env.t
+        del loop
+        torch.cuda.empty_cache()
+        n_chunks = a.e2e_chunks
+        chunk = n // n_chunks
 
-        def e2e_step():
-            for h, d in zip(host, dev_t):
-                d.copy_(h, non_blocking=True)
-            loop2.k = 0
-            loop2.env.t = t0_host
-            loop2.run(T)
-            for h, d in zip(res_host, res_dev):
-                h.copy_(d, non_blocking=True)
+        k_e2e = W * T                       # the host batch is the state after the same untimed warm-up ticks
 
+        def make(nc):
+            lp = make_workload(h3, torch, nc, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
+            lp.switch_step = k_e2e + T // 2
+            return lp
+
+        pipe = h3.HostBatchPipeline(make, chunk, n_slots=2)
+        for _ in range(W):
+            pipe.slots[0].run(T)
+        pipe.k0, pipe.t0 = pipe.slots[0].k, pipe.slots[0].env.t
+        ticks_at_start = float(pipe.slots[0].stats()["sum_ticks"])
+        host_chunks = pipe.host_chunks_from(pipe.slots[0], n_chunks)
+        host_results = pipe.result_buffers(n_chunks)
+        h2d = sum(t.numel() * t.element_size() for ch in host_chunks for t in ch)
+        d2h = sum(t.numel() * t.element_size() for ch in host_results for t in ch)
         for _ in range(max(1, min(W, 2))):
-            e2e_step()
+            pipe.run(host_chunks, host_results, T)
         barrier()
         ke = max(2, min(K, 4))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        steps_e2e = 0.0
         for _ in range(ke):
-            e2e_step()
+            pipe.run(host_chunks, host_results, T)
         e1.record()
         barrier()
-        steps_e2e = float(res_host[4][7].item()) * ke            # sum_ticks of one step (identical steps)
+        # sum_ticks of every chunk minus the ticks the host batch had already run, ke passes
+        steps_e2e = sum(float(r[4][7].item()) - ticks_at_start for r in host_results) * ke
         ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
         se = torch.tensor([steps_e2e], dtype=torch.float64, device=device)
         if world > 1:
@@ -391,9 +387,12 @@ def main():
             out["e2e"] = {"value": float(se.item()) / (float(ems.item()) * 1e-3), "unit": "env-steps/s",
                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
                           "ms_per_step": float(ems.item()) / ke,
-                          "what": "pinned host batch -> device, one %d-tick launch (switch at tick %d), "
-                                  "per-episode returns/flags/term_step/step + statistics -> host" % (T, T // 2)}
-        del loop2
+                          "what": "pinned host batch (%d chunks of %d episodes, state after %d warm-up ticks) -> "
+                                  "device, one %d-tick launch per chunk (ticks %d-%d, switch at %d), per-episode "
+                                  "returns/flags/term_step/step + statistics -> host; 2 device slots on 2 streams "
+                                  "(copies overlap launches)"
+                                  % (n_chunks, chunk, k_e2e, T, k_e2e, k_e2e + T, k_e2e + T // 2)}
+        del pipe
 
     # ---- CPU baseline: the oracle on one host core, bounded sample ----
     if rank == 0:

@@ -19,6 +19,7 @@ from .closed_loop import TRAJ_COLUMNS, ClosedLoop3DOF, sinusoid_ref_table
 from .distributed import allreduce_stats, shard_range
 from .excitation import excitation_signal, load_excitation
 from .heli_models import Helicopter3DOF
+from .host_batch import HostBatchPipeline, loop_result_tensors, loop_state_tensors
 from .model import RecursiveLeastSquares
 from . import sweep
 

@@ -31,6 +31,9 @@ def sinusoid_ref_table(t0, dt, n_ticks, amp=10.0, period=10.0):
     return out, t
 
 
+_TABLE_CACHE = {}
+
+
 class ClosedLoop3DOF:
     def __init__(self, env, pid, rls, agent_col, agent_lon, excitation=None, switch_step=6000,
                  score_window=(0, 0), ticks_per_launch=1000, store_policy=0, ref=None):
@@ -125,8 +128,16 @@ class ClosedLoop3DOF:
         for j0, m in plan:
             table = None
             if table_mode:
-                tab, t_end = sinusoid_ref_table(env.t, env.dt, m, env.ref_amplitude, env.ref_period)
-                table = torch.as_tensor(tab).to(self.device, non_blocking=False)
+                # the table only depends on the clock: reuse the device copy across launches / chunks / slots
+                key = (float(env.t), float(env.dt), m, float(env.ref_amplitude), float(env.ref_period), str(self.device))
+                hit = _TABLE_CACHE.get(key)
+                if hit is None:
+                    tab, t_end = sinusoid_ref_table(env.t, env.dt, m, env.ref_amplitude, env.ref_period)
+                    hit = (torch.as_tensor(tab).to(self.device, non_blocking=False), t_end)
+                    if len(_TABLE_CACHE) > 256:
+                        _TABLE_CACHE.clear()
+                    _TABLE_CACHE[key] = hit
+                table, t_end = hit
             else:
                 t_end = env.t
                 for _ in range(m):

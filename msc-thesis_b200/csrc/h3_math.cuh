@@ -20,6 +20,14 @@ namespace h3 {
 // sin/cos use one polynomial pair on |x| <= pi/4 (flight angles) and the library, out of line, beyond.
 static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { ::sincos(x, s, c); }
 
+// ~20-bit reciprocal seed from the high word: one MUFU.RCP64H.  (__frcp_rn on the float-converted value is
+// IEEE-rounded and drags a slow-path branch into every element, which also stops the interleaving.)
+H3_DEV double rcp_seed(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+
 H3_DEV double tanh_small(double x) {
     const double z = x * x;
     double p = H3_TANH_C[11];
@@ -46,7 +54,7 @@ H3_DEV double tanh_any(double x) {
     const double sc = __hiloint2double((n + 1023) << 20, 0);
     const double E = fma(sc, p, sc - 1.0);
     const double den = E + 2.0;                             // in [1, 2^58]: no special cases in the division
-    double rc = (double)__frcp_rn((float)den);
+    double rc = rcp_seed(den);
     rc = fma(rc, fma(-den, rc, 1.0), rc);
     rc = fma(rc, fma(-den, rc, 1.0), rc);
     const double q0 = E * rc;
@@ -101,38 +109,43 @@ struct Math<double> {
 #pragma unroll
             for (int u = 0; u < U; ++u) y[u] = fma(x[u] * z[u], p[u], x[u]);
         } else {
-            double r[U], q[U], t[U];
+            // at most G elements in flight: each carries ~6 live doubles through the pipeline below
+            constexpr int G = U <= 5 ? U : (U % 5 == 0 ? 5 : (U % 4 == 0 ? 4 : (U % 3 == 0 ? 3 : U)));
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double xc = x[u] > 20.0 ? 20.0 : (x[u] < -20.0 ? -20.0 : x[u]);
-                const double yy = xc + xc;
-                t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
-                const double nf = t[u] - 6755399441055744.0;
-                r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
-            }
+            for (int g0 = 0; g0 < U; g0 += G) {
+                double r[G], q[G], t[G];
 #pragma unroll
-            for (int u = 0; u < U; ++u) q[u] = H3_EXP_C[10];
+                for (int u = 0; u < G; ++u) {
+                    const double xu = x[g0 + u];
+                    const double xc = xu > 20.0 ? 20.0 : (xu < -20.0 ? -20.0 : xu);
+                    const double yy = xc + xc;
+                    t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
+                    const double nf = t[u] - 6755399441055744.0;
+                    r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
+                    q[u] = H3_EXP_C[10];
+                }
 #pragma unroll
-            for (int i = 9; i >= 0; --i)
+                for (int i = 9; i >= 0; --i)
 #pragma unroll
-                for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
-            double E[U], den[U], rc[U];
+                    for (int u = 0; u < G; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
+                double E[G], den[G], rc[G];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double p = fma(r[u] * r[u], q[u], r[u]);
-                const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
-                E[u] = fma(sc, p, sc - 1.0);
-                den[u] = E[u] + 2.0;
-                rc[u] = (double)__frcp_rn((float)den[u]);
-            }
+                for (int u = 0; u < G; ++u) {
+                    const double p = fma(r[u] * r[u], q[u], r[u]);
+                    const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
+                    E[u] = fma(sc, p, sc - 1.0);
+                    den[u] = E[u] + 2.0;
+                    rc[u] = rcp_seed(den[u]);
+                }
 #pragma unroll
-            for (int u = 0; u < U; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+                for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+                for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double q0 = E[u] * rc[u];
-                y[u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
+                for (int u = 0; u < G; ++u) {
+                    const double q0 = E[u] * rc[u];
+                    y[g0 + u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
+                }
             }
         }
     }

@@ -7,6 +7,10 @@
 #include "../../include/heli3dof.h"
 #include "h3_math.cuh"
 
+#ifndef H3_SPLIT_UPDATE_TANH
+#define H3_SPLIT_UPDATE_TANH 0
+#endif
+
 namespace h3 {
 
 // ----------------------------------------------------------------------------------------------
@@ -372,7 +376,19 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
             pre[u] = net.c1(k, 0) * s0 + net.c1(k, 1) * s1;
             pre[U + u] = TAU1 ? net.c1(k, 0) * n0 + net.c1(k, 1) * n1 : net.t1(k, 0) * n0 + net.t1(k, 1) * n1;
         }
+#if H3_SPLIT_UPDATE_TANH
+        {
+            NT pa[U], aa[U], pb[U], ab[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { pa[u] = pre[u]; pb[u] = pre[U + u]; }
+            M::template tanh_vec<U>(pa, aa);
+            M::template tanh_vec<U>(pb, ab);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { act[u] = aa[u]; act[U + u] = ab[u]; }
+        }
+#else
         M::template tanh_vec<2 * U>(pre, act);
+#endif
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = (U == NH) ? u : k0 + u;
