@@ -408,3 +408,40 @@ def test_sweep_is_shard_independent(h3):
     assert np.all(res["success"] <= res["n"]) and np.isfinite(res["mean_score_of_successes"][res["success"] > 0]).all()
     st = whole.stats()
     assert st["n"] == n and st["n_alive"] == res["success"].sum()
+
+
+@pytest.mark.parametrize("n", [1, 15, 17, 31, 33, 250])
+def test_ragged_batch_sizes_and_canaries(h3, n):
+    """Batch sizes that do not fill a warp / a CTA (16 episodes per warp in collective-agent launches, 32 in
+    phase-1 launches): results equal the oracle, and guard words placed directly before and after every state
+    buffer are untouched (compute-sanitizer is closed on this pool, so out-of-bounds stores are caught this way)."""
+    cfg = O.default_config()
+    cfg["switch_step"] = 12
+    cfg["excitation"] = H.excitation()
+    S = O.init_state(n, v_initial=np.linspace(6.0, 24.0, n), cfg=cfg, seed=n)
+    loop = H.make_loop(_clone_state(S), cfg, ticks_per_launch=10)
+    pad, canary = 64, 1234.5
+    guarded = []
+
+    def guard(owner, attr):
+        t = getattr(owner, attr)
+        flat = torch.full((t.numel() + 2 * pad,), canary, dtype=t.dtype, device=t.device)
+        flat[pad:pad + t.numel()] = t.reshape(-1)
+        setattr(owner, attr, flat[pad:pad + t.numel()].view(t.shape))
+        guarded.append(flat)
+
+    for owner, attr in ((loop.env, "state"), (loop.env, "t_ep"), (loop.env, "corr_u"), (loop.rls, "_W"),
+                        (loop.rls, "_cov"), (loop.rls, "x"), (loop.rls, "u"), (loop.agent_col, "net"),
+                        (loop.agent_lon, "net"), (loop, "acc"), (loop, "ref2"), (loop.pid, "hdot_corr")):
+        guard(owner, attr)
+    loop.run(30)
+    O.run(S, cfg, 30, "all64")
+    P = O.init_state(n, v_initial=np.linspace(6.0, 24.0, n), cfg=cfg, seed=n)
+    P["state"] = P["state"] * (1 + 2.0 ** -52)
+    O.run(P, cfg, 30, "all64")
+    sens = H.episode_errors(P, S)
+    H.compare_states(H.loop_state(loop), S, np.maximum(1e-9, 1e3 * sens), what="n=%d" % n)
+    for flat in guarded:
+        assert bool((flat[:pad] == canary).all()) and bool((flat[-pad:] == canary).all())
+    st = loop.stats()
+    assert st["n"] == n and st["sum_ticks"] == float(S["step"].sum())
