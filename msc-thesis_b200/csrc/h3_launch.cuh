@@ -51,17 +51,20 @@ struct Tune {
 #ifndef H3_P1_WARPS
 #define H3_P1_WARPS 8
 #endif
+#ifndef H3_P2_WARPS
+#define H3_P2_WARPS 8    // PAIR launches: warps per CTA (8 / H3_P2_WARPS CTAs per SM)
+#endif
 #ifndef H3_NO_PAIR
     // collective-agent launches of the fast variant: two lanes per episode (see closed_loop_kernel, PAIR)
     static constexpr bool PAIR = (COL || H3_P1_PAIR) && VAR == VAR_FAST && NHL % 2 == 0 && NHC % 2 == 0;
 #else
     static constexpr bool PAIR = false;
 #endif
-    static constexpr int MINB = (!COL && PAIR) ? H3_P1_MINB : 1;
+    static constexpr int MINB = (!COL && PAIR) ? H3_P1_MINB : ((COL && PAIR) ? 8 / H3_P2_WARPS : 1);
     static constexpr int PLACE = PAIR ? 0 : ((COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0));
     static constexpr int UL = PAIR ? NHL / 2 : (lon_smem ? NHL / 2 : NHL);
     static constexpr int UC = PAIR ? NHC / 2 : (COL ? NHC / 2 : NHC);
-    static constexpr int WARPS = PAIR ? (COL ? 8 : H3_P1_WARPS) : (COL ? 4 : 1);
+    static constexpr int WARPS = PAIR ? (COL ? H3_P2_WARPS : H3_P1_WARPS) : (COL ? 4 : 1);
 #ifndef H3_RD_P1
 #define H3_RD_P1 1
 #endif
