@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=16384, help="CPU sample: episodes (per host thread for "
                                                                      "--impl reference)")
     ap.add_argument("--cpu-ticks", type=int, default=400)
@@ -402,6 +403,25 @@ def main():
                                   "(copies overlap launches)"
                                   % (n_chunks, chunk, k_e2e, T, k_e2e, k_e2e + T, k_e2e + T // 2)}
         del pipe
+
+    # ---- extras (rank 0, N == 1): BASELINE config 2, open-loop model step only, 65,536 episodes ----
+    if rank == 0 and world == 1 and not a.no_extras:
+        env2 = h3.Helicopter3DOF(dt=0.01, t_max=120, n_envs=65536, device=device)
+        gen = torch.Generator().manual_seed(0)
+        env2.reset(v_initial=5 + 20 * torch.rand(65536, generator=gen, dtype=torch.float64))
+        exc = h3.excitation_signal(1000)
+        env2.rollout(1000, excitation=exc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            env2.rollout(1000)
+        e1.record()
+        torch.cuda.synchronize(device)
+        alive2 = float((env2.flags == 0).double().mean().item())
+        out["extras"] = {"config2_open_loop": {"episodes": 65536, "ticks_per_launch": 1000,
+                                               "env_steps_per_s": 5 * 65536 * 1000 / (e0.elapsed_time(e1) * 1e-3),
+                                               "alive_fraction": alive2}}
+        del env2
 
     # ---- CPU baseline: the oracle on one host core, bounded sample ----
     if rank == 0:
