@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     constexpr int NHLh = PAIR ? NHL / 2 : NHL, NHCh = PAIR ? NHC / 2 : NHC;     // hidden units of this lane
     static_assert(UL == NHLh || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
     static_assert(UC == NHCh || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");
-    static_assert(!PAIR || ((PLACE & (P_STASHL | P_STASHC | P_LON | P_PREV | P_MISC)) == 0 && UL == NHLh &&
+    static_assert(!PAIR || ((PLACE & (P_STASHL | P_STASHC | P_LON)) == 0 && UL == NHLh &&
                             UC == NHCh && NHL % 2 == 0 && NHC % 2 == 0 && LANES <= 16),
                   "PAIR mode: per-lane groups live in registers, hidden widths even, <= 16 episodes per warp");
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, LANES> LY;

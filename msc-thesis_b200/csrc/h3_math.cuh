@@ -82,6 +82,52 @@ H3_DEV void sincos_f64(double x, double* s, double* c) {
     }
 }
 
+#ifndef H3_TANH_G
+#define H3_TANH_G 5
+#endif
+
+// tanh_any on elements [G0, min(G0 + H3_TANH_G, U)) of x, interleaved, then the next group
+template <int G0, int U>
+H3_DEV void tanh_any_group(const double (&x)[U], double (&y)[U]) {
+    constexpr int G = (U - G0) < H3_TANH_G ? (U - G0) : H3_TANH_G;
+    if constexpr (G > 0) {
+        double r[G], q[G], t[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const double xu = x[G0 + u];
+            const double xc = xu > 20.0 ? 20.0 : (xu < -20.0 ? -20.0 : xu);
+            const double yy = xc + xc;
+            t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
+            const double nf = t[u] - 6755399441055744.0;
+            r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
+            q[u] = H3_EXP_C[10];
+        }
+#pragma unroll
+        for (int i = 9; i >= 0; --i)
+#pragma unroll
+            for (int u = 0; u < G; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
+        double E[G], den[G], rc[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const double p = fma(r[u] * r[u], q[u], r[u]);
+            const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
+            E[u] = fma(sc, p, sc - 1.0);
+            den[u] = E[u] + 2.0;
+            rc[u] = rcp_seed(den[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+#pragma unroll
+        for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const double q0 = E[u] * rc[u];
+            y[G0 + u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
+        }
+        tanh_any_group<G0 + G, U>(x, y);
+    }
+}
+
 template <typename T>
 struct Math;
 
@@ -109,44 +155,8 @@ struct Math<double> {
 #pragma unroll
             for (int u = 0; u < U; ++u) y[u] = fma(x[u] * z[u], p[u], x[u]);
         } else {
-            // at most G elements in flight: each carries ~6 live doubles through the pipeline below
-            constexpr int G = U <= 5 ? U : (U % 5 == 0 ? 5 : (U % 4 == 0 ? 4 : (U % 3 == 0 ? 3 : U)));
-#pragma unroll
-            for (int g0 = 0; g0 < U; g0 += G) {
-                double r[G], q[G], t[G];
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    const double xu = x[g0 + u];
-                    const double xc = xu > 20.0 ? 20.0 : (xu < -20.0 ? -20.0 : xu);
-                    const double yy = xc + xc;
-                    t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
-                    const double nf = t[u] - 6755399441055744.0;
-                    r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
-                    q[u] = H3_EXP_C[10];
-                }
-#pragma unroll
-                for (int i = 9; i >= 0; --i)
-#pragma unroll
-                    for (int u = 0; u < G; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
-                double E[G], den[G], rc[G];
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    const double p = fma(r[u] * r[u], q[u], r[u]);
-                    const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
-                    E[u] = fma(sc, p, sc - 1.0);
-                    den[u] = E[u] + 2.0;
-                    rc[u] = rcp_seed(den[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
-#pragma unroll
-                for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    const double q0 = E[u] * rc[u];
-                    y[g0 + u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
-                }
-            }
+            // at most H3_TANH_G elements in flight: each carries ~6 live doubles through the pipeline below
+            tanh_any_group<0, U>(x, y);
         }
     }
     // sin/cos of two independent angles (theta and the cyclic pitch): four interleaved polynomial chains
