@@ -35,7 +35,9 @@ class CollectivePID3DOF:
         obs = as_rows(obs, 7, n, obs.dtype, obs.device, "obs")
         corr = self._ensure(n, obs.dtype, obs.device)
         out = torch.empty(n, dtype=obs.dtype, device=obs.device)
+        before = corr.clone()
         cfg = build_config(pid=self, env_dtype=obs.dtype, dt=self.dt)
         b = build_batch(n, state=obs, pid_corr=corr)
         L.check(L.lib().h3_pid_collective(byref(cfg), byref(b), L.ptr(out), L.stream_ptr(obs.device)))
+        self.hdot_err = (corr - before) / self.dt        # PID.py:20 keeps the last error as an attribute
         return out

@@ -217,15 +217,44 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
         }
         X[7] = ac[0] - up[e];
         X[8] = ac[1] - up[ld + e];
-        WMat<ET, GlobalVec<ET>> Wm;
-        Wm.v.p = W + e;
-        Wm.v.ld = ld;
-        // the un-fused path always uses the literal (non-symmetric) update of model.py:53-59
-        CovFull<ET, GlobalVec<ET>> C;
-        C.v.p = cov + e;
-        C.v.ld = ld;
+        // literal model.py:49-59 on the HBM-resident matrices (rolled loops: this path is bandwidth-bound)
         (void)sym;
-        rls_update<ET, 1>(K, Wm, C, X, Y);
+        ET err[7], covX[9], Xcov[9];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) err[j] = Y[j];
+#pragma unroll 1
+        for (int i = 0; i < 9; ++i) {
+            const ET xi = X[i];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) err[j] -= xi * W[(i * 7 + j) * ld + e];           // :49-50
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Xcov[i] = (ET)0;
+#pragma unroll 1
+        for (int i = 0; i < 9; ++i) {
+            ET a = (ET)0;
+            const ET xi = X[i];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const ET c = cov[(i * 9 + j) * ld + e];
+                a += c * X[j];                                                          // :53  cov X
+                Xcov[j] += xi * c;                                                      // :54  X^T cov
+            }
+            covX[i] = a;
+        }
+        ET d = K.rls_gamma;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) d += Xcov[j] * X[j];                                // :55
+        const ET inv_d = (ET)1 / d;
+#pragma unroll 1
+        for (int i = 0; i < 9; ++i) {
+            const ET gi = covX[i] * inv_d;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) W[(i * 7 + j) * ld + e] += gi * err[j];           // :58
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                cov[(i * 9 + j) * ld + e] = (cov[(i * 9 + j) * ld + e] - gi * Xcov[j]) * K.rls_inv_gamma;   // :59
+        }
     }
 #pragma unroll
     for (int i = 0; i < 7; ++i) xp[i * ld + e] = st[i];
@@ -271,7 +300,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     const NT s0 = (NT)state[h.ac_state * ld + e];
     const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
     NT hh[NH], f;
-    out[e] = actor_forward<NT, NH, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
+    out[e] = actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f);
 }
 
 template <typename ET, typename NT, int NH>
@@ -301,9 +330,10 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
         G[i] = Gm[i * ld + e];
     }
     NT hh[NH], scr[NH], f;
-    (void)actor_forward<NT, NH, NH>(N, s0, s1, H.scale, h.final_activation, hh, f);
-    agent_update<NT, NH, NH, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f,
-                                    scr);
+    // chunks of 2 hidden units: weights are addressed in global memory, activations in local arrays
+    (void)actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f);
+    agent_update<NT, NH, 2, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f,
+                                   scr);
 }
 
 // get_reward (agents.py:123-128) and get_transition_matrices (agents.py:130-140)

@@ -196,6 +196,20 @@ class Helicopter3DOF:
             self.t += self.dt
         return out
 
+    def _get_reward(self, goal_state, actual_state, clip_reward=True, clip_value=-5.0):
+        """heli_models.py:330-344 (not on the tick path: the call at :205 is commented out in the reference).
+        Quadratic penalty diag(0, .05, 0, 0, 100, 0, 0) on the goal entries that are not NaN."""
+        if self.task is None:
+            return 0
+        q = torch.tensor([0, 0.05, 0, 0, 100, 0, 0], dtype=actual_state.dtype, device=actual_state.device)
+        goal = torch.as_tensor(goal_state).to(actual_state)
+        if goal.dim() == 1:
+            goal = goal.reshape(7, 1)
+        mask = ~torch.isnan(goal)
+        err = torch.where(mask, actual_state - torch.nan_to_num(goal), torch.zeros_like(actual_state))
+        reward = -(q.reshape(7, 1) * err * err).sum(dim=0)
+        return torch.clamp(reward, clip_value, 0.0) if clip_reward else reward
+
     def get_environment_transition_function(self, h=0.001):
         """heli_models.py:257-270: finite-difference ds/da around (0.1, 0.1), shape (8, 2, 1, N)."""
         base = self.step(actions=[0.1, 0.1], virtual=True)[0]

@@ -97,6 +97,9 @@ class RecursiveLeastSquares:
         s = as_rows(state, 7, n, dt, dev, "state")
         a = as_rows(action, 2, n, dt, dev, "action")
         s2 = as_rows(next_state, 7, n, dt, dev, "next_state")
+        first = self._skip.bool()
+        self.X[:7] = torch.where(first, self.X[:7], s - self.x)         # model.py:41-42 (kept as an attribute)
+        self.X[7:9] = torch.where(first, self.X[7:9], a - self.u)
         cfg = build_config(rls=self, env_dtype=dt)
         b = self._batch()
         L.check(L.lib().h3_rls_update(byref(cfg), byref(b), L.ptr(s), L.ptr(a), L.ptr(s2), L.stream_ptr(dev)))
