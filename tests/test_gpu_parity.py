@@ -445,3 +445,40 @@ def test_ragged_batch_sizes_and_canaries(h3, n):
         assert bool((flat[:pad] == canary).all()) and bool((flat[-pad:] == canary).all())
     st = loop.stats()
     assert st["n"] == n and st["sum_ticks"] == float(S["step"].sum())
+
+
+def test_long_horizon_masked_lockstep(h3):
+    """BASELINE config 5 in miniature: 4096 episodes with randomised trims and reference signals, 6000 ticks in
+    launches of 1000 with the collective agent taking over at tick 2000, fp64.  Episodes that terminate (pitch
+    > 90 deg / NaN) must freeze exactly: their state, clock and counters never change again, `term_step + 1`
+    ticks were executed, and the statistics vector accounts for every episode."""
+    n = 4096
+    rng = np.random.default_rng(21)
+    cfg = O.default_config()
+    cfg["switch_step"] = 2000
+    cfg["excitation"] = H.excitation()
+    cfg["ref_amp"] = rng.uniform(5, 15, n)
+    cfg["ref_period"] = rng.uniform(5, 15, n)
+    S = O.init_state(n, v_initial=rng.uniform(5, 25, n), cfg=cfg, seed=8)
+    loop = H.make_loop(S, cfg, ticks_per_launch=1000)
+    dead_ids, dead_vals = np.zeros(0, dtype=np.int64), {}
+    for launch in range(6):
+        loop.run(1000)
+        flags = loop.env.flags.cpu().numpy()
+        step = loop.env.step_count.cpu().numpy()
+        term = loop.env.term_step.cpu().numpy()
+        dead = flags != 0
+        assert np.array_equal(step[~dead], np.full((~dead).sum(), (launch + 1) * 1000))
+        assert np.array_equal(step[dead], term[dead] + 1) and (term[~dead] == -1).all()
+        snap = {"state": loop.env.state.cpu().numpy(), "t": loop.env.t_ep.cpu().numpy(),
+                "W": loop.rls._W.cpu().numpy(), "cov": loop.rls._cov.cpu().numpy(),
+                "col": loop.agent_col.net.cpu().numpy(), "lon": loop.agent_lon.net.cpu().numpy(),
+                "acc": loop.acc.cpu().numpy(), "flags": flags, "term": term}
+        for k, v in dead_vals.items():          # everything that was dead before is bit-identical now
+            assert np.array_equal(v, snap[k][..., dead_ids], equal_nan=True), (launch, k)
+        dead_ids = np.nonzero(dead)[0]
+        dead_vals = {k: v[..., dead_ids].copy() for k, v in snap.items()}
+        st = loop.stats()
+        assert st["n"] == n and st["n_alive"] == int((~dead).sum()) and st["sum_ticks"] == float(step.sum())
+        assert st["n_done"] + st["n_nan"] >= int(dead.sum())
+    assert dead.any() and (~dead).any()         # the scenario exercises both outcomes
