@@ -422,6 +422,27 @@ def main():
                                                "env_steps_per_s": 5 * 65536 * 1000 / (e0.elapsed_time(e1) * 1e-3),
                                                "alive_fraction": alive2}}
         del env2
+        # the other two precision paths of the same kernel template, same workload and phase mix (device-resident)
+        if a.precision == "f64":
+            other = {}
+            for prec in ("mixed", "f32"):
+                lp = make_workload(h3, torch, n, prec, device, seed=1, store=a.store, ticks=T)
+                lp.switch_step = (W + 2) * T
+                for _ in range(W):
+                    lp.run(T)
+                torch.cuda.synchronize(device)
+                t_before = lp.stats()["sum_ticks"]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    lp.run(T)
+                e1.record()
+                torch.cuda.synchronize(device)
+                other[prec] = {"env_steps_per_s": (lp.stats()["sum_ticks"] - t_before) / (e0.elapsed_time(e1) * 1e-3),
+                               "what": {"mixed": "fp64 model/PID/RLS + fp32 networks (the reference's torch-1.4 precision)",
+                                        "f32": "everything fp32"}[prec], "steps": 4}
+                del lp
+            out["extras"]["other_precisions"] = other
 
     # ---- CPU baseline: the oracle on one host core, bounded sample ----
     if rank == 0:
