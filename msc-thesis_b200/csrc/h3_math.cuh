@@ -66,19 +66,44 @@ H3_DEV double tanh_f64(double x) {
     return tanh_any(x);
 }
 
-H3_DEV void sincos_f64(double x, double* s, double* c) {
-    if (::fabs(x) <= 0.78539816339744828) {
-        const double z = x * x;
-        double ps = H3_SIN_C[7], pc = H3_COS_C[7];
+// sin / cos polynomials on the reduced argument |r| <= pi/4
+H3_DEV void sincos_poly(double r, double* s, double* c) {
+    const double z = r * r;
+    double ps = H3_SIN_C[7], pc = H3_COS_C[7];
 #pragma unroll
-        for (int i = 6; i >= 0; --i) {
-            ps = fma(ps, z, H3_SIN_C[i]);
-            pc = fma(pc, z, H3_COS_C[i]);
-        }
-        *s = fma(x * z, ps, x);
-        *c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    for (int i = 6; i >= 0; --i) {
+        ps = fma(ps, z, H3_SIN_C[i]);
+        pc = fma(pc, z, H3_COS_C[i]);
+    }
+    *s = fma(r * z, ps, r);
+    *c = fma(z * z, pc, fma(-0.5, z, 1.0));
+}
+
+// |x| <= 1e5: Cody-Waite reduction by multiples of pi/2 (three FMA pieces), polynomial pair, quadrant swap --
+// straight-line code.  Pitch angles between 45 and 90 degrees (episodes on their way to termination) stay on
+// this path instead of dragging their whole warp through the library's out-of-line routine.
+H3_DEV void sincos_reduced(double x, double* s, double* c) {
+    const double t = fma(x, H3_PIO2[3], 6755399441055744.0);      // q = rint(x * 2/pi) in the low word of t
+    const double q = t - 6755399441055744.0;
+    double r = fma(-q, H3_PIO2[0], x);
+    r = fma(-q, H3_PIO2[1], r);
+    r = fma(-q, H3_PIO2[2], r);
+    double sr, cr;
+    sincos_poly(r, &sr, &cr);
+    const int n = __double2loint(t);
+    const double a = (n & 1) ? cr : sr, b = (n & 1) ? sr : cr;    // sin x, cos x up to sign
+    *s = (n & 2) ? -a : a;
+    *c = ((n + 1) & 2) ? -b : b;
+}
+
+H3_DEV void sincos_f64(double x, double* s, double* c) {
+    const double ax = ::fabs(x);
+    if (ax <= 0.78539816339744828) {
+        sincos_poly(x, s, c);
+    } else if (ax <= 1.0e5) {
+        sincos_reduced(x, s, c);
     } else {
-        sincos_libm(x, s, c);
+        sincos_libm(x, s, c);                                     // huge, inf, NaN
     }
 }
 
@@ -175,6 +200,9 @@ struct Math<double> {
             *ca = fma(za * za, pca, fma(-0.5, za, 1.0));
             *sb = fma(b * zb, psb, b);
             *cb = fma(zb * zb, pcb, fma(-0.5, zb, 1.0));
+        } else if (::fabs(a) <= 1.0e5 && ::fabs(b) <= 1.0e5) {
+            sincos_reduced(a, sa, ca);
+            sincos_reduced(b, sb, cb);
         } else {
             sincos_f64(a, sa, ca);
             sincos_f64(b, sb, cb);
