@@ -104,10 +104,11 @@ def build_config(env=None, pid=None, rls=None, col=None, lon=None, env_dtype=tor
     return cfg
 
 
-def build_batch(n, **tensors):
-    """H3Batch with the given tensors (all (rows, n) or (n,) contiguous on one CUDA device)."""
+def build_batch(n, n_active=None, **tensors):
+    """H3Batch with the given tensors (all (rows, n) or (n,) contiguous on one CUDA device); `n_active` <= n
+    launches only the first n_active columns (ld stays n)."""
     b = L.H3Batch()
-    b.n = n
+    b.n = n if n_active is None else n_active
     b.ld = n
     for k, v in tensors.items():
         setattr(b, k, L.ptr(v).value if v is not None else None)

@@ -68,6 +68,12 @@ class ClosedLoop3DOF:
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
         self.k = 0                  # host copy of the lockstep tick index (None: heterogeneous batch)
         self.launches = 0
+        # compaction (long horizons): live episodes are kept in the first n_active columns; `order[i]` is the
+        # original index of the episode now stored in column i; retired episodes keep their frozen state in
+        # the columns behind n_active and their share of the statistics in _retired
+        self.n_active = n
+        self.order = torch.arange(n, device=self.device)
+        self._retired = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
 
     # -- state ------------------------------------------------------------------------------------------
     def set_heterogeneous(self):
@@ -78,7 +84,7 @@ class ClosedLoop3DOF:
 
     def _batch(self, col_hyper, lon_hyper):
         env, rls = self.env, self.rls
-        return build_batch(self.n, state=env.state, t=env.t_ep, ref=self.ref2, corr_u=env.corr_u,
+        return build_batch(self.n, n_active=self.n_active, state=env.state, t=env.t_ep, ref=self.ref2, corr_u=env.corr_u,
                            trim=env.trimmed_controls, theta_trim=env._theta_trim(), ref_par=env.ref_params,
                            pid_corr=self.pid.hdot_corr, rls_W=rls._W, rls_cov=rls._cov, rls_x=rls.x, rls_u=rls.u,
                            rls_skip=rls._skip, col_net=self.agent_col.net, lon_net=self.agent_lon.net,
@@ -157,9 +163,64 @@ class ClosedLoop3DOF:
                                        L.ptr(self._scratch) if stats is not None else None, stream))
             env.t = t_end
             self.launches += 1
+        if want_stats and self.n_active < self.n:
+            self.stats_dev += self._retired         # episodes retired by compact() are not launched any more
         if self.k is not None:
             self.k += n_ticks
         return traj
+
+    def _episode_tensors(self):
+        env, rls = self.env, self.rls
+        ts = [env.state, env.t_ep, self.ref2, env.corr_u, env.trimmed_controls, env.trimmed_state, self.pid.hdot_corr,
+              rls._W, rls._cov, rls.x, rls.u, rls._skip, rls.X, self.agent_col.net, self.agent_lon.net,
+              env.step_count, env.flags, env.term_step, self.acc, self.order]
+        if env.ref_params is not None:
+            ts.append(env.ref_params)
+        return ts
+
+    def compact(self):
+        """Move the live episodes to the front (stable order) so that launches only cover them: terminated
+        episodes otherwise keep occupying lanes of their warp.  Returns the number of live episodes.  Per-episode
+        tensors of all five objects are permuted IN PLACE; `self.order` maps columns to original episode indices
+        (`self.original_order(t)` undoes the permutation for reporting).  Per-episode hyper-parameter tensors held
+        by the agents are permuted as well."""
+        na = self.n_active
+        alive = self.env.flags[:na] == 0
+        n_alive = int(alive.sum().item())
+        if n_alive == na:
+            return na
+        perm = torch.cat([torch.nonzero(alive).reshape(-1), torch.nonzero(~alive).reshape(-1)])
+        for t in self._episode_tensors():
+            head = t[..., :na]
+            head.copy_(head.index_select(-1, perm))
+        for ag in (self.agent_col, self.agent_lon):
+            for name in ("gamma", "learning_rate_actor", "learning_rate_critic", "tau_target_critic", "reward_weight"):
+                v = getattr(ag, name)
+                if torch.is_tensor(v) and v.numel() == self.n:
+                    v = v.clone()
+                    v[:na] = v[:na].index_select(0, perm.to(v.device))
+                    setattr(ag, name, v)
+            if torch.is_tensor(ag.actor.scale) and ag.actor.scale.numel() == self.n:
+                v = ag.actor.scale.clone()
+                v[:na] = v[:na].index_select(0, perm.to(v.device))
+                ag.actor.scale = v
+        # statistics share of the episodes retired now (same field order as the kernel epilogue)
+        f = self.env.flags[n_alive:na]
+        r = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
+        r[0] = na - n_alive
+        r[2] = ((f & L.FLAG_DONE) != 0).sum()
+        r[3] = ((f & L.FLAG_NAN) != 0).sum()
+        r[4:7] = self.acc[:, n_alive:na].sum(dim=1)
+        r[7] = self.env.step_count[n_alive:na].sum()
+        self._retired += r
+        self.n_active = n_alive
+        return n_alive
+
+    def original_order(self, t):
+        """Per-episode tensor `t` (episode axis last) re-ordered to the original episode indices."""
+        out = torch.empty_like(t)
+        out.index_copy_(-1, self.order.to(t.device), t)
+        return out
 
     # -- results ----------------------------------------------------------------------------------------------
     def stats(self):

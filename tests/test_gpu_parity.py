@@ -482,3 +482,35 @@ def test_long_horizon_masked_lockstep(h3):
         assert st["n"] == n and st["n_alive"] == int((~dead).sum()) and st["sum_ticks"] == float(step.sum())
         assert st["n_done"] + st["n_nan"] >= int(dead.sum())
     assert dead.any() and (~dead).any()         # the scenario exercises both outcomes
+
+
+def test_compaction_changes_nothing_but_the_order(h3):
+    """Long horizon with periodic compaction (live episodes moved to the front, launches cover only them) against
+    the same run without: per-episode results, re-ordered to the original indices, and statistics are bit-identical."""
+    n = 2048
+    rng = np.random.default_rng(33)
+    cfg = O.default_config()
+    cfg["switch_step"] = 1500
+    cfg["excitation"] = H.excitation()
+    cfg["ref_amp"] = rng.uniform(5, 15, n)
+    cfg["ref_period"] = rng.uniform(5, 15, n)
+    S = O.init_state(n, v_initial=rng.uniform(5, 25, n), cfg=cfg, seed=12)
+    plain = H.make_loop(_clone_state(S), cfg, ticks_per_launch=500)
+    comp = H.make_loop(_clone_state(S), cfg, ticks_per_launch=500)
+    live = n
+    for _ in range(10):
+        plain.run(500)
+        comp.run(500)
+        live = comp.compact()
+    assert 0 < live < n and comp.n_active == live
+    assert sorted(comp.order.cpu().tolist()) == list(range(n))
+    for a, b in ((plain.env.state, comp.env.state), (plain.env.t_ep, comp.env.t_ep), (plain.rls._W, comp.rls._W),
+                 (plain.rls._cov, comp.rls._cov), (plain.agent_col.net, comp.agent_col.net),
+                 (plain.agent_lon.net, comp.agent_lon.net), (plain.acc, comp.acc), (plain.env.flags, comp.env.flags),
+                 (plain.env.term_step, comp.env.term_step), (plain.env.step_count, comp.env.step_count)):
+        assert torch.equal(a, comp.original_order(b))
+    sp, sc = plain.stats(), comp.stats()
+    for k in ("n", "n_alive", "n_done", "n_nan", "sum_ticks"):
+        assert sp[k] == sc[k], k
+    for k in ("sum_r_col", "sum_r_lon"):
+        assert abs(sp[k] - sc[k]) <= 1e-9 * abs(sp[k])
