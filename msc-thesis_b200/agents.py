@@ -133,12 +133,20 @@ class DHPAgent:
         vals = self._hyper_values()
         if not any(is_per_episode(v) for v in vals.values()):
             return None
+        # the rows are rebuilt only when one of the attributes was re-bound or modified in place
+        key = tuple((id(v), v._version if torch.is_tensor(v) else None) for v in vals.values())
+        cacheable = not any(isinstance(v, np.ndarray) for v in vals.values())   # in-place numpy edits are invisible
+        cached = getattr(self, "_hyper_cache", None)
+        if cacheable and cached is not None and cached[0] == key:
+            return cached[1]
         rows = []
         for k in L.HYPER_NAMES:
             v = vals[k]
             v = v.detach().to("cpu", torch.float64) if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, np.float64))
             rows.append(v.reshape(-1).expand(self.n_envs))
-        return torch.stack(rows).to(self.device).contiguous()
+        out = torch.stack(rows).to(self.device).contiguous()
+        self._hyper_cache = (key, out, list(vals.values()))      # keep the keyed objects alive (ids stay unique)
+        return out
 
     def _which(self):
         return self.control_channel_num

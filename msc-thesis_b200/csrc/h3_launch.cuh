@@ -38,10 +38,13 @@ constexpr size_t SMEM_PER_BLOCK_MAX = 232448;   // 227 KB opt-in limit per CTA o
 // On-chip placement per variant.  Phase-1 launches (COL == false) keep everything
 // but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM); launches with the
 // collective agent run one 4-warp CTA per SM with as many episodes per warp as the tile allows.
-template <typename ET, typename NT, int NHL, int NHC, bool COL, int VAR>
-struct Tune {
-    static constexpr bool SYM = VAR != VAR_GENERAL, HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
-    static constexpr bool lon_smem = !TAU1L;                // the full cyclic agent (11 nh words) goes to the tile
+// ---- tuning knobs (compile-time; defaults are the measured best) ----
+#ifndef H3_SWEEP_P1_REGS
+#define H3_SWEEP_P1_REGS 1
+#endif
+#ifndef H3_PAIR_ALL
+#define H3_PAIR_ALL 0       // tuning: PAIR also for the SWEEP / GENERAL variants
+#endif
 #ifndef H3_P1_PAIR
 #define H3_P1_PAIR 0        // tuning: two lanes per episode in phase-1 launches as well
 #endif
@@ -54,9 +57,22 @@ struct Tune {
 #ifndef H3_P2_WARPS
 #define H3_P2_WARPS 8    // PAIR launches: warps per CTA (8 / H3_P2_WARPS CTAs per SM)
 #endif
+#ifndef H3_RD_P1
+#define H3_RD_P1 1
+#endif
+#ifndef H3_RD_P2
+#define H3_RD_P2 2
+#endif
+
+template <typename ET, typename NT, int NHL, int NHC, bool COL, int VAR>
+struct Tune {
+    static constexpr bool SYM = VAR != VAR_GENERAL, HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
+    // the full cyclic agent (11 nh words) goes to the tile in collective-agent launches of the SWEEP / GENERAL
+    // variants; phase-1 launches keep it in registers (7 instead of 4 warps per SM)
+    static constexpr bool lon_smem = !TAU1L && !(H3_PAIR_ALL && COL) && (COL || !H3_SWEEP_P1_REGS);
 #ifndef H3_NO_PAIR
     // collective-agent launches of the fast variant: two lanes per episode (see closed_loop_kernel, PAIR)
-    static constexpr bool PAIR = (COL || H3_P1_PAIR) && VAR == VAR_FAST && NHL % 2 == 0 && NHC % 2 == 0;
+    static constexpr bool PAIR = (COL || H3_P1_PAIR) && (VAR == VAR_FAST || H3_PAIR_ALL) && NHL % 2 == 0 && NHC % 2 == 0;
 #else
     static constexpr bool PAIR = false;
 #endif
@@ -65,12 +81,6 @@ struct Tune {
     static constexpr int UL = PAIR ? NHL / 2 : (lon_smem ? NHL / 2 : NHL);
     static constexpr int UC = PAIR ? NHC / 2 : (COL ? NHC / 2 : NHC);
     static constexpr int WARPS = PAIR ? (COL ? H3_P2_WARPS : H3_P1_WARPS) : (COL ? 4 : 1);
-#ifndef H3_RD_P1
-#define H3_RD_P1 1
-#endif
-#ifndef H3_RD_P2
-#define H3_RD_P2 2
-#endif
     static constexpr int RD = COL ? H3_RD_P2 : H3_RD_P1;    // RLS stream look-ahead (groups)
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
     static constexpr size_t room = (SMEM_PER_BLOCK_MAX / MINB - 1024 * (MINB - 1) - L32::head_bytes(WARPS)) / WARPS - 16;

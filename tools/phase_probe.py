@@ -13,6 +13,11 @@ nl = int(sys.argv[4]) if len(sys.argv) > 4 else 14
 dev = torch.device("cuda", 0)
 loop = make_workload(h3, torch, n, "f64", dev, seed=1, store=0, ticks=T)
 loop.switch_step = switch
+if len(sys.argv) > 5 and sys.argv[5] == 'hyp':      # per-episode hyper-parameters (SWEEP kernel variant)
+    g = torch.Generator().manual_seed(3)
+    for ag in (loop.agent_col, loop.agent_lon):
+        ag.gamma = 0.6 + 0.39 * torch.rand(n, generator=g, dtype=torch.float64)
+        ag.tau_target_critic = torch.tensor([0.01, 0.1, 1.0], dtype=torch.float64)[torch.randint(0, 3, (n,), generator=g)]
 for i in range(nl):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
