@@ -170,20 +170,7 @@ H3_DEV void stream_groups(Load load, Body body) {
 template <typename T, int DEPTH, bool PAIR = false, typename WAcc, typename CAcc>
 H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7], int half = 0) {
     constexpr bool F = WAcc::kFence;
-    constexpr int NC = PAIR ? 4 : 7;            // columns handled by this lane (the 4th is masked for half 1)
-    const int j0 = PAIR ? 4 * half : 0;
-    T err[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) err[j] = PAIR ? (half ? Y[j < 3 ? 4 + j : 6] : Y[j]) : Y[j];
-    stream_groups<T, 9, NC, DEPTH, F>(                                  // :49-50  err = Y - W^T X
-        [&](int i, T (&w)[NC]) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) w[j] = (PAIR && j == 3) ? Wm.dyn(i, half ? 6 : 3) : Wm.dyn(i, j0 + j);
-        },
-        [&](int i, T (&w)[NC]) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) err[j] -= X[i] * w[j];
-        });
+    // gain first: it needs the covariance only (model.py:53-55)
     T covX[9], Xcov[9];
     Cv.template matvec<DEPTH>(X, covX, Xcov);                           // :53-54
     const T d0 = (K.rls_gamma + Xcov[0] * X[0]) + Xcov[1] * X[1] + Xcov[2] * X[2];      // :55 (three partial sums)
@@ -193,20 +180,26 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
     T g[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
-    stream_groups<T, 9, NC, DEPTH, F>(                                  // :58  W += (cov X) err / d
-        [&](int i, T (&w)[NC]) {
+    // then ONE pass over W, column by column: the prediction error of output j (model.py:49-50) and the update of
+    // column j (:58) need nothing from the other columns, so each weight is loaded once, not twice.
+    //   PAIR: lane half h owns columns [4h, 4h + 4) (the 4th slot of half 1 re-does column 6 and is not stored).
+    constexpr int NC = PAIR ? 4 : 7;
+    stream_groups<T, NC, 9, DEPTH, F>(
+        [&](int jl, T (&w)[9]) {
+            const int j = PAIR ? ((jl == 3) ? (half ? 6 : 3) : 4 * half + jl) : jl;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) w[j] = (PAIR && j == 3) ? Wm.dyn(i, half ? 6 : 3) : Wm.dyn(i, j0 + j);
+            for (int i = 0; i < 9; ++i) w[i] = Wm.dyn(i, j);
         },
-        [&](int i, T (&w)[NC]) {
+        [&](int jl, T (&w)[9]) {
+            const int j = PAIR ? ((jl == 3) ? (half ? 6 : 3) : 4 * half + jl) : jl;
+            const T yj = PAIR ? (half ? Y[jl < 3 ? 4 + jl : 6] : Y[jl]) : Y[jl];
+            // two partial sums keep the 9-long dependent chain short
+            const T ea = ((yj - X[0] * w[0]) - X[2] * w[2]) - X[4] * w[4] - X[6] * w[6] - X[8] * w[8];
+            const T eb = ((X[1] * w[1] + X[3] * w[3]) + X[5] * w[5]) + X[7] * w[7];
+            const T err = ea - eb;
+            if (!PAIR || jl < 3 || !half) {
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const T nw = w[j] + g[i] * err[j];
-                if (PAIR && j == 3) {
-                    if (!half) Wm.ref(i, 3) = nw;       // half 1 owns columns 4..6 only: its 4th slot re-did column 6
-                } else {
-                    Wm.ref(i, j0 + j) = nw;
-                }
+                for (int i = 0; i < 9; ++i) Wm.ref(i, j) = w[i] + g[i] * err;
             }
         });
     Cv.template downdate<DEPTH>(g, Xcov, K.rls_inv_gamma);              // :59
