@@ -18,5 +18,20 @@ def build(force=False):
     return LIB
 
 
+SRC6 = os.path.join(HERE, "heli6dof_ref.c")
+LIB6 = os.path.join(OUT_DIR, "libheli6dof_ref.so")
+
+
+def build6(force=False):
+    """The 6-DOF restatement (oracle/heli6dof_ref.c)."""
+    if not force and os.path.exists(LIB6) and os.path.getmtime(LIB6) >= os.path.getmtime(SRC6):
+        return LIB6
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", LIB6, SRC6, "-lm"]
+    subprocess.check_call(cmd)
+    return LIB6
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build6(force=True))
