@@ -16,7 +16,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libheli3dof.so")
 
-SOURCES = ("h3_api.cu", "h3_loop_f64.cu", "h3_loop_mixed.cu", "h3_loop_f32.cu")
+SOURCES = ("h3_api.cu", "h3_loop_f64.cu", "h3_loop_mixed.cu", "h3_loop_f32.cu", "h6_api.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 

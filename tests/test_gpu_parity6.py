@@ -1,0 +1,190 @@
+"""GPU parity of the 6-DOF path through the C ABI (include/heli6dof.h): the CUDA
+kernels against the reference-generated fixtures tests/golden/h6_*.npz and against the C oracle
+(oracle/heli6dof_ref.c) on seeded random batches.  fp64: 1e-9 relative per tick; integer bookkeeping bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle6 as C6
+from tests import helpers6 as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def pkg():
+    return importlib.import_module("msc-thesis_b200.heli6dof")
+
+
+def test_trim_matches_reference():
+    g = H.load("h6_trim.npz")
+    H6 = pkg()
+    env = H6.Helicopter6DOF(dt=0.01, t_max=120, n_envs=len(g["cases"]), device=DEV)
+    st, ct = env.trim(g["cases"][:, 0], g["cases"][:, 1], g["cases"][:, 2])
+    assert (env.trim_iterations > 0).all() and (env.trim_iterations < 30).all()
+    assert H.rel_err(st.cpu().numpy().T, g["state"]) < 1e-8
+    assert H.rel_err(ct.cpu().numpy().T, g["controls"]) < 1e-8
+    assert H.rel_err(env.P_out.cpu().numpy(), g["P_out"]) < 1e-8
+
+
+def test_derivatives_and_step_match_reference():
+    g = H.load("h6_model.npz")
+    H6 = pkg()
+    n = len(g["state"])
+    env = H6.Helicopter6DOF(dt=float(g["dt"]), t_max=120, n_envs=n, device=DEV)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a).T), device=DEV)
+    env.P_available.copy_(T(g["P_avail"]))
+    env.P_out.copy_(T(g["P_in"]))
+    d = env.calculate_state_derivatives(T(g["actions"]), T(g["state"]))
+    for i in range(n):
+        assert H.rel_err(d[:, i].cpu().numpy(), g["dots"][i]) < 1e-9, i
+    assert H.rel_err(env.P_out.cpu().numpy(), g["P_after_dots"]) < 1e-12
+    env.P_out.copy_(T(g["P_in"]))
+    env.state.copy_(T(g["state"]))
+    nxt, _, done = env.step(T(g["actions"]))
+    for i in range(n):
+        assert H.rel_err(nxt[:, i].cpu().numpy(), g["next"][i]) < 1e-11, i
+    assert H.rel_err(env.P_out.cpu().numpy(), g["P_after_step"]) < 1e-12
+    assert not done.any() and abs(env.t - float(g["dt"])) < 1e-15
+
+
+@pytest.mark.parametrize("mode_id,mode", [(0, "train"), (1, "test_1"), (2, "test_2")])
+def test_teacher_forced_ticks(mode_id, mode):
+    g = H.load("h6_ticks.npz")
+    info = g["info"]
+    sel = np.nonzero(info[:, 7] == mode_id)[0]
+    pre = {k[4:]: v[sel] for k, v in g.items() if k.startswith("pre_")}
+    loop = H.build_loop(pre, mode, excitation_=H.excitation())
+    log = loop.run(1, record=len(sel))
+    got = H.loop_state(loop)
+    worst = 0.0
+    for j, i in enumerate(sel):
+        worst = max(worst, H.compare(got, g, j, i, 1e-9, "post_"))
+        assert int(got["flags"][j]) == int(info[i, 6]), (i, got["flags"][j], info[i, 6])
+        assert int(got["term_step"][j]) == (int(pre["step"][j]) if info[i, 6] else -1)
+        assert H.rel_err(log[0, 18:22, j].cpu().numpy(), info[i, :4]) < 1e-12          # actions
+        assert H.rel_err(log[0, 22:24, j].cpu().numpy(), info[i, 4:6], floor=1e-12) < 1e-9   # rewards
+    st = loop.stats()
+    assert st["n"] == len(sel) and st["n_alive"] == int((info[sel, 6] == 0).sum())
+    print("worst", mode, worst)
+
+
+def test_free_running_short_episode_and_log():
+    g = H.load("h6_train_short.npz")
+    ticks = [int(k) for k in g["snap_ticks"]]
+    snap = {k[5:]: v for k, v in g.items() if k.startswith("snap_")}
+    loop = H.build_loop({k: v[:1] for k, v in snap.items()}, "train", step_switch=int(g["step_switch"]),
+                        excitation_=H.excitation(), ticks_per_launch=97)
+    done, logs = ticks[0], []
+    for i, k in enumerate(ticks[1:], start=1):
+        logs.append(loop.run(k - done, record=1))
+        done = k
+        H.compare(H.loop_state(loop), g, 0, i, 1e-7, "snap_")
+    log = torch.cat(logs)[:, :, 0].cpu().numpy()
+    n = len(log)
+    assert H.rel_err(log[:, :15], g["traj_state"][:n]) < 1e-7
+    assert H.rel_err(log[:, 18:22], g["traj_actions"][:n]) < 1e-7
+    assert H.rel_err(log[:, 15:18], g["traj_ref"][:n]) < 1e-7
+    assert (log[:, 25] == 1).all()
+
+
+def test_reference_scenario_segments():
+    """Every snapshot of the seed-101 reference run (train.py __main__) advanced to the next one if it is at
+    most two ticks away (events at 0, 1000, 6000), and 300 free-running ticks from tick 6001."""
+    g = H.load("h6_train.npz")
+    ticks = [int(k) for k in g["snap_ticks"]]
+    snap = {k[5:]: v for k, v in g.items() if k.startswith("snap_")}
+    for i in range(len(ticks) - 1):
+        gap = ticks[i + 1] - ticks[i]
+        if gap > 2:
+            continue
+        loop = H.build_loop({k: v[i:i + 1] for k, v in snap.items()}, "train", excitation_=H.excitation())
+        loop.run(gap)
+        H.compare(H.loop_state(loop), g, 0, i + 1, 1e-9, "snap_")
+    i = ticks.index(6001)
+    loop = H.build_loop({k: v[i:i + 1] for k, v in snap.items()}, "train", excitation_=H.excitation())
+    E = C6.pack_snapshots({k: v[i:i + 1] for k, v in snap.items()})
+    C6.run(E, C6.default_config(excitation=H.excitation()), 300)
+    loop.run(300)
+    got = H.loop_state(loop)
+    assert H.rel_err(got["state"][0], E[0]["s"]) < 1e-7 and int(got["step"][0]) == int(E[0]["step"])
+
+
+def test_random_batch_against_c_oracle():
+    """1000 fresh episodes with random networks, 40 + 1 ticks through the switch (switch at 30), every tick
+    teacher-forced from the CUDA state: per-tick agreement with the C oracle to 1e-9, symmetric and literal
+    covariance paths, a ragged batch size."""
+    exc = H.excitation()
+    n = 1000
+    cfg = C6.default_config(excitation=exc, step_switch=30)
+    E = C6.fresh_episodes(n, cfg, seed=5)
+    snaps = {k: np.stack([C6.unpack_episode(e)[k] for e in E]) for k in H.REAL_KEYS + H.INT_KEYS if k != "P_available"}
+    snaps["P_available"] = E["P_avail"].copy()
+    snaps["trim_actions"] = E["trim_act"].copy()
+    snaps["trim_state"] = np.tile(C6.trim(15)[0], (n, 1))
+    for sym in (True, False):
+        loop = H.build_loop(snaps, "train", step_switch=30, excitation_=exc)
+        loop.rls.assume_symmetric = sym
+        Eo = E.copy()
+        worst = 0.0
+        for k in range(41):
+            loop.run(1)
+            C6.run(Eo, cfg, 1)
+            got = H.loop_state(loop)
+            for key, field in (("state", "s"), ("rls_W", "W"), ("rls_cov", "cov"), ("pid", "pid"), ("gen", "gen"),
+                               ("ref", "ref"), ("P_out", "P_out"), ("lr", "lr")):
+                for j in (0, 1, n // 2, n - 1):
+                    e = H.rel_err(got[key][j], Eo[j][field])
+                    assert e < 1e-9, (sym, k, key, j, e)
+                    worst = max(worst, e)
+            assert np.array_equal(got["step"], Eo["step"]) and np.array_equal(got["flags"], Eo["flags"])
+            # teacher forcing: continue the oracle from the CUDA state
+            for key, field in (("state", "s"), ("rls_W", "W"), ("rls_cov", "cov"), ("pid", "pid"), ("gen", "gen"),
+                               ("ref", "ref"), ("P_out", "P_out"), ("rls_x", "xprev"), ("rls_u", "uprev")):
+                Eo[field] = got[key]
+            for name in ("col", "lon"):
+                Eo[name] = np.concatenate([got[name + "_" + kk].reshape(n, -1) for kk in H.NET_KEYS], axis=1)
+        print("sym", sym, "worst", worst)
+
+
+def test_object_api_tick_matches_fused_tick():
+    """The statements of train.py:109-224 executed through the per-object methods (LatPedPID, CollectivePID6DOF,
+    DHPAgent6DOF, Helicopter6DOF.step, RefGenerator, RecursiveLeastSquares6) against the fused kernel."""
+    H6 = pkg()
+    exc = H.excitation()
+    n, ticks = 64, 12
+    gen = torch.Generator().manual_seed(3)
+    fused = H6.make_closed_loop(n, "train", excitation=exc, device=DEV, init="batched", generator=gen)
+    obj = H6.make_closed_loop(n, "train", excitation=exc, device=DEV, init="batched")
+    obj.agent_col.net.copy_(fused.agent_col.net); obj.agent_lon.net.copy_(fused.agent_lon.net)
+    fused.run(ticks)
+    env, lat_pid, col_pid, rg, rls = obj.env, obj.lat_pid, obj.col_pid, obj.gen, obj.rls
+    a_col, a_lon = obj.agent_col, obj.agent_lon
+    trim = env.trim_controls.clone()
+    observation, ref = env.state.clone(), env.state.clone()
+    e4 = torch.as_tensor(exc, device=DEV)
+    for step in range(ticks):
+        lateral_cyclic, pedal = lat_pid(observation)
+        if step == 0:
+            rg.set_task(task="train_lon", t=0, obs=observation, velocity_filter_target=0)
+            ref = rg.get_ref(observation, env.t)
+        actions = torch.stack([col_pid(observation), trim[1] - 0.5 + a_lon.get_action(observation, ref), lateral_cyclic, pedal])
+        actions = actions + e4[step].reshape(4, 1)
+        actions = torch.clip(actions, 0, 1)
+        next_observation, _, done = env.step(actions)
+        rg.A = 10 if env.t < 20 else (15 if env.t < 40 else 20)
+        next_ref = rg.get_ref(observation, env.t)
+        rls.update(observation, actions[:2], next_observation)
+        reward, dr_ds = a_lon.get_reward(next_observation, ref)
+        F, G = a_lon.get_transition_matrices(rls)
+        a_lon.update_networks(observation, next_observation, ref, next_ref, dr_ds, F, G)
+        assert not H6.envelope_limits_reached(observation)[0].any() and not done.any()
+        observation, ref = next_observation, next_ref
+    assert H.rel_err(env.state.cpu().numpy(), fused.env.state.cpu().numpy()) < 1e-9
+    assert H.rel_err(rls.W.cpu().numpy(), fused.rls.W.cpu().numpy()) < 1e-9
+    assert H.rel_err(rls.cov.cpu().numpy(), fused.rls.cov.cpu().numpy()) < 1e-9
+    assert H.rel_err(a_lon.net.cpu().numpy(), fused.agent_lon.net.cpu().numpy()) < 1e-9
+    assert H.rel_err(col_pid.hdot_corr.cpu().numpy(), fused.pid[0].cpu().numpy()) < 1e-9
+    assert H.rel_err(next_ref[[0, 7, 11]].cpu().numpy(), fused.ref3.cpu().numpy()) < 1e-9

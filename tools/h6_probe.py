@@ -1,0 +1,36 @@
+"""Timing probe of the fused 6-DOF kernel: N episodes, phase 1 (PID collective) and phase 2 (both agents)."""
+import importlib
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+H6 = importlib.import_module("msc-thesis_b200.heli6dof")
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+    ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    exc = np.load("tests/golden/h6_excitation.npz")["excitation"]
+    for switch in (10 ** 6, 0):
+        ep = dict(H6.env_params_train, step_switch=switch)
+        loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device="cuda", init="batched",
+                                   ticks_per_launch=ticks)
+        print("info", loop.info())
+        loop.run(ticks)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        loop.run(ticks)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        st = loop.stats()
+        print("phase %d: n=%d ticks=%d  %.3f ms  -> %.3e env-steps/s  alive %.4f" %
+              (1 if switch else 2, n, ticks, ms, n * ticks / ms * 1e3, st["n_alive"] / st["n"]))
+
+
+if __name__ == "__main__":
+    main()
