@@ -53,6 +53,67 @@ int main(void) {
     assert offs == [getattr(L.H3Batch, k).offset for k in ("state", "rls_skip", "step", "acc")]
 
 
+def test_6dof_exports_and_struct_layout(tmp_path):
+    """include/heli6dof.h: every declared h6_* symbol is exported, and the ctypes mirrors match the C structs."""
+    text = open(os.path.join(ROOT, "include", "heli6dof.h")).read()
+    declared = set(re.findall(r"\b(h6_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(L.H6_EXPORTS), declared ^ set(L.H6_EXPORTS)
+    lib = h3.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    out = (ctypes.c_double * 3)()
+    lib.h6_engine_power(out)
+    assert list(out) == [2 * 313000 * 0.95 * 0.8643, 0.95 * 313000 * 0.95, 1.10 * 313000 * 0.95]    # heli_models.py:397-401
+    assert lib.h6_stats_scratch_bytes(1000) == 4 * 10 * 8
+    src = tmp_path / "layout6.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "heli6dof.h"
+int main(void) {
+  printf("%zu %zu %zu\\n", sizeof(H6Config), sizeof(H6Batch), sizeof(H6Traj));
+  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(H6Config, lat_gains), offsetof(H6Config, amp), offsetof(H6Config, run_mode), offsetof(H6Config, win_hi), offsetof(H6Config, col), offsetof(H6Config, lon));
+  printf("%zu %zu %zu %zu\\n", offsetof(H6Batch, state), offsetof(H6Batch, trim_act), offsetof(H6Batch, rls_skip), offsetof(H6Batch, acc));
+  return 0;
+}''')
+    exe = tmp_path / "layout6"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    lines = subprocess.check_output([str(exe)]).decode().split("\n")
+    assert [int(x) for x in lines[0].split()] == [ctypes.sizeof(c) for c in (L.H6Config, L.H6Batch, L.H6Traj)]
+    assert [int(x) for x in lines[1].split()] == [getattr(L.H6Config, k).offset for k in
+                                                  ("lat_gains", "amp", "run_mode", "win_hi", "col", "lon")]
+    assert [int(x) for x in lines[2].split()] == [getattr(L.H6Batch, k).offset for k in
+                                                  ("state", "trim_act", "rls_skip", "acc")]
+    assert len(L.H6_BATCH_FIELDS) == 24
+
+
+def test_6dof_host_objects_fail_loudly_without_gpu():
+    """The 6-DOF classes can be constructed on the CPU (plumbing), every compute call raises: no fallback."""
+    import importlib
+    H6 = importlib.import_module("msc-thesis_b200.heli6dof")
+    env = H6.Helicopter6DOF(dt=0.01, t_max=120, n_envs=4, device="cpu")
+    assert env.state.shape == (15, 4) and env.Paeo == 2 * 313000 * 0.95 * 0.8643
+    env.set_engine_status(1, transient=True)
+    assert float(env.P_available[0]) == env.Poeitr
+    with pytest.raises(ValueError):
+        env.set_engine_status(3)
+    with pytest.raises(L.H3Error):
+        env.trim(15, 0, 0)
+    pid = H6.LatPedPID(0.0, 0.5, 0.5, 0.01, H6.pid_params)
+    assert pid.gains[4] == pid.gains[3] == np.rad2deg(5)              # PID.py:51 uses Kphi twice
+    gen = H6.RefGenerator(T=10, dt=0.01, A=10, u_ref=0, t_switch=60, filter_tau=2.5, n_envs=4, device="cpu")
+    with pytest.raises(NotImplementedError):
+        gen.get_ref(env.state, 0.0)                                   # util.py:163: no task set
+    with pytest.raises(NotImplementedError):
+        H6.RecursiveLeastSquares6(state_size=15, action_size=2, constant=True, device="cpu")
+    rls = H6.RecursiveLeastSquares6(**H6.rls_params, n_envs=4, device="cpu")
+    assert rls.W.shape == (17, 15, 4) and float(rls.cov[3, 3, 0]) == 1e8 and rls.skip_update
+    assert H6.env_params_train["step_switch"] == 6000 and H6.env_params_test2["n_steps"] == 3000
+    lim, which = H6.envelope_limits_reached(torch.tensor([[0.0] * 6 + [0.0, 1.6] + [0.0] * 7, [0.0] * 6 + [-1.56, 0.0] + [0.0] * 7,
+                                                          [0.0] * 15]).T.contiguous())
+    assert lim.tolist() == [True, True, False] and which.tolist() == [1, 2, 0]
+
+
 def test_default_env_params_are_the_reference_constants():
     p = L.default_env_params(0.01)
     assert (p.g, p.cl_alpha, p.blade_solidity, p.lock_number, p.cds, p.mass) == (9.81, 5.7, 0.075, 6, 1.5, 2200)
