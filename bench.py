@@ -14,6 +14,7 @@ reported next to the whole-region value.  env-steps are COUNTED (sum of per-epis
 kernel's statistics epilogue), so terminated episodes stop counting.
 """
 import argparse
+import importlib
 import json
 import os
 import subprocess
@@ -207,6 +208,59 @@ def make_workload(h3, torch, n, precision, device, seed, store, ticks):
     loop = h3.ClosedLoop3DOF(env, pid, rls, col, lon, excitation=h3.excitation_signal(1000), switch_step=6000,
                              ticks_per_launch=ticks, store_policy=store)
     return loop
+
+
+def bench_6dof(torch, device, n=262144, ticks=50, reps=3, no_cpu=False):
+    """Device-resident throughput of the fused 6-DOF loop (include/heli6dof.h: h6_closed_loop), the HBM bytes it
+    moves per env-step against the measured HBM peak, and the C oracle (oracle/heli6dof_ref.c) on one host core."""
+    H6 = importlib.import_module("msc-thesis_b200.heli6dof")
+    exc = np.load(os.path.join(ROOT, "tests", "golden", "h6_excitation.npz"))["excitation"]
+    res = {"episodes": n, "ticks_per_launch": ticks, "dtype": "f64"}
+    for name, switch in (("phase1", 10 ** 6), ("phase2", 0)):
+        ep = dict(H6.env_params_train, step_switch=switch)
+        loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device=device, init="batched",
+                                   generator=torch.Generator().manual_seed(2), ticks_per_launch=ticks)
+        loop.run(ticks)
+        torch.cuda.synchronize(device)
+        before = loop.stats()["sum_ticks"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            loop.run(ticks)
+        e1.record()
+        torch.cuda.synchronize(device)
+        st = loop.stats()
+        sec = e0.elapsed_time(e1) * 1e-3
+        res[name] = {"env_steps_per_s": (st["sum_ticks"] - before) / sec, "ms_per_launch": sec / reps * 1e3,
+                     "alive_fraction": st["n_alive"] / st["n"]}
+        if name == "phase2":
+            res["kernel"] = loop.info()
+        del loop
+    # algorithmic HBM words per env-step (DESIGN.md section 9): W 255 r+w, symmetric covariance 153 r+w, the
+    # networks (tau = 1: actor 30 + critic 40 per agent, r+w), model input / regressor rows 17 r+w
+    words = {"phase1": 2 * (255 + 153 + 70 + 17), "phase2": 2 * (255 + 153 + 140 + 17)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6548.0)) if isinstance(peaks, dict) else 6548.0
+    for name in ("phase1", "phase2"):
+        gbs = res[name]["env_steps_per_s"] * words[name] * 8 / 1e9
+        res[name]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                 "bytes_per_env_step": words[name] * 8}
+    if not no_cpu:
+        from oracle import c_oracle6 as C6
+        cfg = C6.default_config(excitation=exc, step_switch=100)
+        E = C6.fresh_episodes(256, cfg, seed=1)
+        C6.run(E, cfg, 20)
+        t0 = time.perf_counter()
+        total = C6.run(E, cfg, 180)
+        wall = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": total / wall, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                               "sample": "256 episodes x 180 ticks (100 phase 1 + 100 phase 2 incl. warm-up), C oracle "
+                                         "oracle/heli6dof_ref.c, 1 thread, %.1f s" % wall}
+    return res
 
 
 def fma_peak(h3, torch, dtype_code, device):
@@ -443,6 +497,12 @@ def main():
                                         "f32": "everything fp32"}[prec], "steps": 4}
                 del lp
             out["extras"]["other_precisions"] = other
+
+        # the 6-DOF widening: train.py's loop, 262,144 episodes, phase 1 and phase 2
+        try:
+            out["extras"]["six_dof_closed_loop"] = bench_6dof(torch, device, no_cpu=a.no_cpu)
+        except Exception as exc:                    # an extra must never take the headline line down with it
+            out["extras"]["six_dof_closed_loop"] = {"error": repr(exc)}
 
     # ---- CPU baseline: the oracle on one host core, bounded sample ----
     if rank == 0:

@@ -10,7 +10,8 @@
 #include <cstdio>
 #include <cstring>
 
-#include "h6_loop.cuh"
+#include "h3_tick.cuh"
+#include "h6_model.cuh"
 
 namespace h3 {
 void set_error(const char* fmt, ...);
@@ -18,9 +19,18 @@ void set_error(const char* fmt, ...);
 
 namespace h6 {
 
+using h3::AgentH;
+using h3::NetAcc;
 using h3::set_error;
 
+constexpr int NS = H6_N_STATE, NR = H6_N_REG, NH = H6_N_HIDDEN;
 constexpr int BLOCK = 128;
+#ifndef H6_MINB
+#define H6_MINB 4
+#endif
+#ifndef H6_U
+#define H6_U 5
+#endif
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
 
 static int check_launch(const char* what) {
@@ -31,6 +41,14 @@ static int check_launch(const char* what) {
     }
     return H3_OK;
 }
+
+struct GVec {               // one episode's column of a `[rows][ld]` global array
+    static constexpr bool kFence = false;
+    double* p;
+    int64_t ld;
+    H3_DEV double& operator[](int i) { return p[(int64_t)i * ld]; }
+};
+typedef NetAcc<double, NH, GVec> Net;
 
 // ----------------------------------------------------------------------------------------------
 // RecursiveLeastSquares.update (model.py:41-59), n = 17, m = 15, on global-memory W / cov.
@@ -100,6 +118,235 @@ H3_DEV void rls_update(double* __restrict__ W, double* __restrict__ cov, int64_t
             }
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// fused closed loop
+// ----------------------------------------------------------------------------------------------
+struct LoopParams {
+    H6Config C;
+    ModelK K;
+    H6Batch b;
+    const double* excitation;
+    int exc_len, n_ticks;
+    H6Traj traj;
+};
+
+struct AgentIO {            // one agent's per-tick inputs, kept between get_action and update_networks
+    double s0, s1, f;
+    bool fwd;
+};
+
+H3_DEV void agent_step_update(const H3AgentHyper& h, Net& net, double lr_a, double lr_c, const double* __restrict__ W,
+                              int64_t ld, const double (&obs)[NS], const double (&nxt)[NS], const double (&ref)[3],
+                              const double (&nref)[3], AgentIO& io, double (&hh)[NH], double& reward, bool tau1_fast) {
+    const int ac = h.ac_state, tr = h.tracked_state;
+    if (!io.fwd) {          // the actor forward pass of this (obs, ref) was not needed for the action
+        io.s0 = obs[ac];
+        io.s1 = obs[tr] - ref_slot(ref, tr);
+        (void)h3::actor_forward<double, NH, H6_U>(net, io.s0, io.s1, h.scale, h.final_activation, hh, io.f);
+    }
+    const double n0 = nxt[ac], n1 = nxt[tr] - ref_slot(nref, tr);
+    const double et = nxt[tr] - ref_slot(ref, tr);                      // agents.py:125
+    reward = -(et * et) * h.reward_weight;
+    const double dr = -2 * et * h.reward_weight;
+    double F[2][2], G[2];                                               // agents.py:130-140, post-update W
+    const int idx[2] = {ac, tr};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) F[i][j] = W[(int64_t)(idx[j] * NS + idx[i]) * ld];
+        G[i] = W[(int64_t)((NS + h.channel) * NS + idx[i]) * ld];
+    }
+    AgentH<double> H;
+    H.gamma = h.gamma; H.lr_a = lr_a; H.lr_c = lr_c; H.tau = h.tau; H.scale = h.scale;
+    double scr[NH];
+    // tau == 1: after one update the target critic IS the critic (agents.py:196), so later ticks of the launch
+    // neither read nor write its rows; they are refreshed from the critic at launch exit
+    if (tau1_fast)
+        h3::agent_update<double, NH, H6_U, true>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
+    else
+        h3::agent_update<double, NH, H6_U, false>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __grid_constant__ LoopParams P) {
+    const H6Config& C = P.C;
+    const H6Batch& b = P.b;
+    const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x, ld = b.ld;
+    if (e >= b.n) return;
+    int flags = b.flags[e];
+    if (flags != 0) return;                                             // frozen: the episode has ended
+    double obs[NS], ref[3], pid[4], gen[H6_GEN_ROWS], trim[4], lr[4], acc[3];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) obs[i] = b.state[i * ld + e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ref[i] = b.ref[i * ld + e]; acc[i] = b.acc[i * ld + e]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pid[i] = b.pid[i * ld + e]; trim[i] = b.trim_act[i * ld + e]; lr[i] = b.lr[i * ld + e]; }
+#pragma unroll
+    for (int i = 0; i < H6_GEN_ROWS; ++i) gen[i] = b.gen[i * ld + e];
+    double t = b.t[e], P_out = b.P_out[e], P_avail = b.P_avail[e];
+    const double phi_trim = b.phi_trim[e];
+    int task = b.task[e], step = b.step[e], update_col = b.update_col[e], exc_phase = b.excitation_phase[e];
+    int skip = b.rls_skip[e], term = -1;
+    double* __restrict__ W = b.rls_W + e;
+    double* __restrict__ cov = b.rls_cov + e;
+    Net ncol, nlon;
+    ncol.v.p = b.col_net + e; ncol.v.ld = ld;
+    nlon.v.p = b.lon_net + e; nlon.v.ld = ld;
+    const double inv_gamma = 1.0 / C.rls_gamma;
+    int ticks_done = 0, col_updates = 0;
+
+#pragma unroll 1
+    for (int it = 0; it < P.n_ticks; ++it) {
+        const int k = step;
+        const ObsTrig g = obs_trig(obs);
+        double act[4];
+        pid_latped(C, obs, g, phi_trim, trim[2], trim[3], pid[1], pid[2], pid[3], act[2], act[3]);     // train.py:110
+        bool both = true;
+        if (C.run_mode == H6_MODE_TRAIN) {                                                                // :113-137
+            if (k == 0) {
+                gen_set_task(task, gen, H6_TASK_TRAIN_LON, 0.0, obs, 0.0, 0.0, 0.0);
+                gen_get_ref(C, task, gen, obs, t, ref);
+            } else if (k == C.exc_off_step) {
+                exc_phase = 0;
+            } else if (k == C.step_switch) {
+                lr[2] *= C.lr_decay; lr[3] *= C.lr_decay;
+                update_col = 1;
+                gen_set_task(task, gen, H6_TASK_TRAIN_COL, t, obs, obs[11], 0.0, 0.0);
+            }
+            both = !(k < C.step_switch);
+        } else if (C.run_mode == H6_MODE_TEST1) {                                                         // :138-160
+            if (k == 0) { gen_set_task(task, gen, H6_TASK_HOVER, 0.0, obs, 0.0, 0.0, 0.0); gen_get_ref(C, task, gen, obs, t, ref); }
+            else if (k == 500) gen_set_task(task, gen, H6_TASK_VELOCITY, t, obs, 0.0, 25 - obs[0], 0.0);
+            else if (k == 2000) gen_set_task(task, gen, H6_TASK_VELOCITY, t, obs, 0.0, 0 - obs[0], 0.0);
+        } else if (C.run_mode == H6_MODE_TEST2) {                                                         // :161-170
+            if (k == 0) { gen_set_task(task, gen, H6_TASK_DESCENT, 0.0, obs, 0.0, 0.0, 0.0); gen_get_ref(C, task, gen, obs, t, ref); }
+            else if (k == 1000) P_avail = C.P_engine_failure;
+        } else {
+            both = update_col != 0;
+        }
+        // actions (:126-137)
+        AgentIO io_lon, io_col;
+        double h_lon[NH], h_col[NH];
+        io_lon.s0 = obs[C.lon.ac_state];
+        io_lon.s1 = obs[C.lon.tracked_state] - ref_slot(ref, C.lon.tracked_state);
+        io_lon.fwd = true;
+        act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U>(nlon, io_lon.s0, io_lon.s1, C.lon.scale,
+                                                                   C.lon.final_activation, h_lon, io_lon.f);
+        io_col.fwd = both;
+        if (both) {
+            io_col.s0 = obs[C.col.ac_state];
+            io_col.s1 = obs[C.col.tracked_state] - ref_slot(ref, C.col.tracked_state);
+            act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U>(ncol, io_col.s0, io_col.s1, C.col.scale,
+                                                                       C.col.final_activation, h_col, io_col.f);
+        } else {
+            act[0] = pid_collective(C, obs, g, trim[0], pid[0]);
+        }
+        if (exc_phase && P.excitation != nullptr && k < P.exc_len) {                                      // :173-174
+#pragma unroll
+            for (int i = 0; i < 4; ++i) act[i] += P.excitation[4 * k + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) act[i] = clip01_nan(act[i]);                                          // :176
+        // env.step (:179; heli_models.py:464-475)
+        const Controls ctl = make_controls(P.K, act[0], act[1], act[2], act[3]);
+        double nxt[NS];
+        rk4_step(P.K, ctl, obs, P_out, P_avail, C.dt, nxt);
+        const bool done = t > C.t_max;
+        t += C.dt;
+        gen[H6_GEN_A] = t < C.amp_t[0] ? C.amp[0] : (t < C.amp_t[1] ? C.amp[1] : C.amp[2]);              // :180-185
+        double nref[3];
+        gen_get_ref(C, task, gen, obs, t, nref);                                                          // :186 (pre-step obs)
+        // RLS (:189; model.py:27-59)
+        if (skip) {
+            skip = 0;
+        } else {
+            double X[NR], Y[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { X[i] = obs[i] - b.rls_x[i * ld + e]; Y[i] = nxt[i] - obs[i]; }
+            X[NS] = act[0] - b.rls_u[e];
+            X[NS + 1] = act[1] - b.rls_u[ld + e];
+            rls_update<SYM>(W, cov, ld, X, Y, C.rls_gamma, inv_gamma);
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) b.rls_x[i * ld + e] = obs[i];
+        b.rls_u[e] = act[0];
+        b.rls_u[ld + e] = act[1];
+        // agents (:192-201)
+        double r_col = 0, r_lon = 0;
+        if (update_col) {
+            agent_step_update(C.col, ncol, lr[0], lr[1], W, ld, obs, nxt, ref, nref, io_col, h_col, r_col,
+                              C.col.tau == 1.0 && col_updates > 0);
+            col_updates += 1;
+        }
+        agent_step_update(C.lon, nlon, lr[2], lr[3], W, ld, obs, nxt, ref, nref, io_lon, h_lon, r_lon,
+                          C.lon.tau == 1.0 && ticks_done > 0);
+        acc[0] += r_col;
+        acc[1] += r_lon;
+        if (k >= C.win_lo && k < C.win_hi) acc[2] += r_lon;                                               // :256
+        // termination (:207-218), evaluated on the pre-step observation
+        const double R2D = 180.0 / 3.14159265358979323846;
+        int fl = done ? H6_FLAG_TMAX : 0;
+        if (fabs(obs[7] * R2D) > C.limit_pitch || fabs(obs[6] * R2D) > C.limit_roll) fl |= H6_FLAG_ENVELOPE;
+        if (act[0] != act[0] || act[1] != act[1] || act[2] != act[2] || act[3] != act[3]) fl |= H6_FLAG_NAN;
+        if (C.run_mode == H6_MODE_TEST2 && obs[11] > 0) fl |= H6_FLAG_LANDED;
+        if (P.traj.out != nullptr && e < P.traj.n_traj) {                                                  // util.py:30-66
+            double* o = P.traj.out + (int64_t)it * H6_TRAJ_ROWS * P.traj.ld_traj + e;
+            const int64_t lt = P.traj.ld_traj;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) o[i * lt] = obs[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) o[(NS + i) * lt] = ref[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[(NS + 3 + i) * lt] = act[i];
+            o[22 * lt] = r_col; o[23 * lt] = r_lon; o[24 * lt] = P_out; o[25 * lt] = 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) obs[i] = nxt[i];                                                     // :222-223
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ref[i] = nref[i];
+        step = k + 1;
+        ticks_done += 1;
+        if (fl) { flags = fl; term = k; break; }
+    }
+    if (P.traj.out != nullptr && e < P.traj.n_traj) {       // rows of ticks that were not executed: alive = 0
+        for (int it = ticks_done; it < P.n_ticks; ++it)
+            P.traj.out[((int64_t)it * H6_TRAJ_ROWS + 25) * P.traj.ld_traj + e] = 0.0;
+    }
+    if (C.lon.tau == 1.0 && ticks_done > 1) {               // target critic := critic (rows 7nh.. := rows 3nh..)
+#pragma unroll 1
+        for (int r = 0; r < 4 * NH; ++r) nlon.v[7 * NH + r] = nlon.v[3 * NH + r];
+    }
+    if (C.col.tau == 1.0 && col_updates > 1) {
+#pragma unroll 1
+        for (int r = 0; r < 4 * NH; ++r) ncol.v[7 * NH + r] = ncol.v[3 * NH + r];
+    }
+    if (SYM && ticks_done > 0) {                            // restore the full matrix for the callers
+#pragma unroll 1
+        for (int i = 0; i < NR - 1; ++i) {                  // one row per step: its loads are issued together
+            double r[NR];
+#pragma unroll
+            for (int j = 1; j < NR; ++j)
+                if (j > i) r[j] = cov[(int64_t)(i * NR + j) * ld];
+#pragma unroll
+            for (int j = 1; j < NR; ++j)
+                if (j > i) cov[(int64_t)(j * NR + i) * ld] = r[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) b.state[i * ld + e] = obs[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { b.ref[i * ld + e] = ref[i]; b.acc[i * ld + e] = acc[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { b.pid[i * ld + e] = pid[i]; b.lr[i * ld + e] = lr[i]; }
+#pragma unroll
+    for (int i = 0; i < H6_GEN_ROWS; ++i) b.gen[i * ld + e] = gen[i];
+    b.t[e] = t; b.P_out[e] = P_out; b.P_avail[e] = P_avail;
+    b.task[e] = task; b.step[e] = step; b.update_col[e] = update_col; b.excitation_phase[e] = exc_phase;
+    b.rls_skip[e] = skip;
+    if (flags) { b.flags[e] = flags; b.term_step[e] = term; }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -533,8 +780,8 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
         LoopParams P;
         P.C = *cfg; P.K = make_modelk(); P.b = *b; P.excitation = excitation; P.exc_len = exc_len; P.n_ticks = n_ticks;
         if (traj != nullptr) P.traj = *traj; else { P.traj.out = nullptr; P.traj.n_traj = 0; P.traj.ld_traj = 0; }
-        if (cfg->rls_symmetric) closed_loop_kernel<true><<<grid_for(b->n), LOOP_BLOCK, LOOP_SMEM, st>>>(P);
-        else closed_loop_kernel<false><<<grid_for(b->n), LOOP_BLOCK, LOOP_SMEM, st>>>(P);
+        if (cfg->rls_symmetric) closed_loop_kernel<true><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+        else closed_loop_kernel<false><<<grid_for(b->n), BLOCK, 0, st>>>(P);
         const int rc = check_launch("h6 closed_loop_kernel");
         if (rc != H3_OK) return rc;
     }
@@ -556,9 +803,9 @@ int h6_closed_loop_info(const H6Config* cfg, int32_t* block, int32_t* blocks_per
     cudaError_t err = cudaFuncGetAttributes(&a, fn);
     if (err != cudaSuccess) { set_error("cudaFuncGetAttributes: %s", cudaGetErrorString(err)); return H3_E_CUDA; }
     int nb = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, LOOP_BLOCK, LOOP_SMEM);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, BLOCK, 0);
     if (err != cudaSuccess) { set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor: %s", cudaGetErrorString(err)); return H3_E_CUDA; }
-    if (block) *block = LOOP_BLOCK;
+    if (block) *block = BLOCK;
     if (blocks_per_sm) *blocks_per_sm = nb;
     if (regs) *regs = a.numRegs;
     if (local_bytes) *local_bytes = (int32_t)a.localSizeBytes;

@@ -24,6 +24,9 @@ constexpr int LOOP_BLOCK = 128;
 #ifndef H6_MINB
 #define H6_MINB 4
 #endif
+#ifndef H6_U
+#define H6_U 2      // hidden units per chunk of the agent loops (NH: fully unrolled, no local arrays)
+#endif
 #ifndef H6_DEPTH
 #define H6_DEPTH 1    // covariance groups (9 elements) in flight ahead of the one being consumed
 #endif
@@ -159,7 +162,7 @@ H3_DEV void agent_learn(const H3AgentHyper& h, Net& net, double lr_a, double lr_
                  n1 = sm[AG_N1 * LOOP_BLOCK], dr = sm[AG_DR * LOOP_BLOCK];
     double hh[NH], scr[NH], f;
     // the actor forward pass of (obs, ref) with the pre-update weights (== get_action's pass, agents.py:169)
-    (void)h3::actor_forward<double, NH, 2>(net, s0, s1, h.scale, h.final_activation, hh, f);
+    (void)h3::actor_forward<double, NH, H6_U>(net, s0, s1, h.scale, h.final_activation, hh, f);
     double F[2][2], G[2];                                               // agents.py:130-140, post-update W
     const int idx[2] = {h.ac_state, h.tracked_state};
 #pragma unroll
@@ -172,8 +175,8 @@ H3_DEV void agent_learn(const H3AgentHyper& h, Net& net, double lr_a, double lr_
     H.gamma = h.gamma; H.lr_a = lr_a; H.lr_c = lr_c; H.tau = h.tau; H.scale = h.scale;
     // tau == 1: after one update the target critic IS the critic (agents.py:196), so later ticks of the launch
     // neither read nor write its rows; they are refreshed from the critic at launch exit
-    if (tau1_fast) h3::agent_update<double, NH, 2, true>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
-    else h3::agent_update<double, NH, 2, false>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
+    if (tau1_fast) h3::agent_update<double, NH, H6_U, true>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
+    else h3::agent_update<double, NH, H6_U, false>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
 }
 
 H3_DEV void phase_fence() { asm volatile("" ::: "memory"); }
@@ -232,8 +235,8 @@ H3_DEV int tick_simulate(const LoopParams& P, int64_t e, int it, double* sm, int
     double hh[NH], f;
     const double lon_s0 = obs[C.lon.ac_state], lon_s1 = obs[C.lon.tracked_state] - ref_slot(ref, C.lon.tracked_state);
     const double col_s0 = obs[C.col.ac_state], col_s1 = obs[C.col.tracked_state] - ref_slot(ref, C.col.tracked_state);
-    act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, 2>(nlon, lon_s0, lon_s1, C.lon.scale, C.lon.final_activation, hh, f);
-    if (both) act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, 2>(ncol, col_s0, col_s1, C.col.scale, C.col.final_activation, hh, f);
+    act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U>(nlon, lon_s0, lon_s1, C.lon.scale, C.lon.final_activation, hh, f);
+    if (both) act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U>(ncol, col_s0, col_s1, C.col.scale, C.col.final_activation, hh, f);
     else act[0] = pid_collective(C, obs, g, trim[0], pid[0]);
     if (exc_phase && P.excitation != nullptr && k < P.exc_len) {                                          // :173-174
 #pragma unroll
