@@ -252,13 +252,13 @@ def bench_6dof(torch, device, n=262144, ticks=50, reps=3, no_cpu=False):
     if not no_cpu:
         from oracle import c_oracle6 as C6
         cfg = C6.default_config(excitation=exc, step_switch=100)
-        E = C6.fresh_episodes(256, cfg, seed=1)
+        E = C6.fresh_episodes(4096, cfg, seed=1)
         C6.run(E, cfg, 20)
         t0 = time.perf_counter()
         total = C6.run(E, cfg, 180)
         wall = time.perf_counter() - t0
         res["cpu_baseline"] = {"value": total / wall, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                               "sample": "256 episodes x 180 ticks (100 phase 1 + 100 phase 2 incl. warm-up), C oracle "
+                               "sample": "4096 episodes x 180 ticks (80 phase 1 + 100 phase 2 after 20 warm-up ticks), C oracle "
                                          "oracle/heli6dof_ref.c, 1 thread, %.1f s" % wall}
     return res
 
