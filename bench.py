@@ -234,7 +234,9 @@ def bench_6dof(torch, device, n=262144, ticks=50, reps=3, no_cpu=False):
         res[name] = {"env_steps_per_s": (st["sum_ticks"] - before) / sec, "ms_per_launch": sec / reps * 1e3,
                      "alive_fraction": st["n_alive"] / st["n"]}
         if name == "phase2":
-            res["kernel"] = loop.info()
+            res["path"] = "split: sim_kernel (thread per episode) + learn_kernel (17 warps per 32 episodes), tiled " \
+                          "W / covariance / networks (DESIGN.md section 9)"
+            res["fused_kernel_info"] = loop.info()
         del loop
     # algorithmic HBM words per env-step: W 255 r+w, symmetric covariance 153 r+w, the
     # networks (tau = 1: actor 30 + critic 40 per agent, r+w), model input / regressor rows 17 r+w

@@ -29,6 +29,7 @@ extern "C" {
 #define H6_N_REG 17     /* RLS regressors: 15 state + 2 action increments (train.py:189: actions[:2]) */
 #define H6_N_HIDDEN 10  /* params.py: n_hidden_actor = n_hidden_critic = 10 for both agents */
 #define H6_N_STATS 10
+#define H6_WORK_ROWS 44
 
 #define H6_FLAG_TMAX 1
 #define H6_FLAG_NAN 2
@@ -84,6 +85,9 @@ typedef struct H6Config {
     int32_t rls_symmetric;     /* 1: covariance known symmetric; only its upper triangle is read and updated
                                   during a launch, the lower one is mirrored at launch exit */
     int32_t win_lo, win_hi;    /* score window on the lon reward (train.py:256: [5000, 6000)) */
+    int32_t target_synced;     /* bit 0 (col) / bit 1 (lon): the caller asserts target critic == critic at entry; with
+                                  tau == 1 the split path then never reads the target rows (agents.py:196) */
+    int32_t pad_;
     H3AgentHyper col, lon;     /* gamma, tau, scale, reward_weight, tracked_state, ac_state, channel,
                                   final_activation; the learning rates live per episode in H6Batch.lr */
 } H6Config;
@@ -114,6 +118,11 @@ typedef struct H6Batch {
     int32_t* update_col; /* [ld] train.py:94, :122 */
     int32_t* excitation_phase; /* [ld] train.py:93, :118 */
     double* acc;         /* [3][ld] sum r_col, sum r_lon, sum r_lon inside the score window */
+    double* work;        /* [H6_WORK_ROWS][ld] scratch of the split path (simulate / learn kernels), or NULL:
+                            h6_closed_loop then runs the fused one-thread-per-episode kernel */
+    int64_t tile;        /* 0: rls_W, rls_cov, col_net, lon_net are plain `[row][ld]`; 32: they are tiled
+                            `[ceil(n/32)][rows][32]` (32 episodes' rows contiguous: sequential HBM pages for the
+                            streaming kernels), see h6_tile_pack.  Only h6_closed_loop accepts tiled buffers. */
 } H6Batch;
 
 /* Optional per-tick log of h6_closed_loop (what Logger.log_states records, util.py:30-66), for the first
@@ -175,6 +184,11 @@ int h6_rls_predict(const H6Batch* b, const double* state, const double* action, 
  * sum r_col, sum r_lon, sum window r_lon, sum ticks}; NULL to skip. */
 int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitation, int32_t exc_len,
                    int32_t n_ticks, const H6Traj* traj, double* stats, void* stats_scratch, void* stream);
+
+/* Layout conversion of one `[rows][ld]` array of n episodes to / from the tiled form `[ceil(n/32)][rows][32]`
+ * (H6Batch.tile = 32); to_tiled != 0: plain -> tiled, else tiled -> plain.  The tiled buffer holds
+ * ceil(n/32) * rows * 32 doubles. */
+int h6_tile_pack(const double* src, double* dst, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream);
 
 /* Bytes of device scratch h6_closed_loop needs next to `stats`. */
 int64_t h6_stats_scratch_bytes(int64_t n);

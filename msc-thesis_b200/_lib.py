@@ -62,13 +62,14 @@ class H3Traj(C.Structure):
 
 # ---- 6-DOF (include/heli6dof.h) ------------------------------------------------------------------------------
 H6_N_STATE, H6_N_ACTION, H6_N_REG, H6_N_HIDDEN, H6_N_STATS, H6_TRAJ_ROWS, H6_GEN_ROWS = 15, 4, 17, 10, 10, 26, 8
+H6_WORK_ROWS = 44
 H6_FLAG_TMAX, H6_FLAG_NAN, H6_FLAG_ENVELOPE, H6_FLAG_LANDED = 1, 2, 4, 8
 H6_TASKS = {None: 0, "hover": 1, "train_lon": 2, "train_col": 3, "velocity": 4, "descent": 5}
 H6_MODES = {"train": 0, "test_1": 1, "test_2": 2, "free": 3}
 H6_STATS_FIELDS = ("n", "n_alive", "n_tmax", "n_nan", "n_envelope", "n_landed", "sum_r_col", "sum_r_lon",
                    "sum_window_r_lon", "sum_ticks")
 H6_EXPORTS = ("h6_engine_power", "h6_trim", "h6_env_derivatives", "h6_env_step", "h6_pid_collective", "h6_pid_latped",
-              "h6_refgen_get_ref", "h6_refgen_set_task", "h6_rls_update", "h6_rls_predict", "h6_closed_loop",
+              "h6_refgen_get_ref", "h6_refgen_set_task", "h6_rls_update", "h6_rls_predict", "h6_closed_loop", "h6_tile_pack",
               "h6_stats_scratch_bytes", "h6_closed_loop_info")
 
 
@@ -80,16 +81,16 @@ class H6Config(C.Structure):
                 ("amp", C.c_double * 3), ("amp_t", C.c_double * 2), ("lr_decay", C.c_double),
                 ("run_mode", C.c_int32), ("step_switch", C.c_int32), ("exc_off_step", C.c_int32),
                 ("rls_symmetric", C.c_int32), ("win_lo", C.c_int32), ("win_hi", C.c_int32),
-                ("col", H3AgentHyper), ("lon", H3AgentHyper)]
+                ("target_synced", C.c_int32), ("pad_", C.c_int32), ("col", H3AgentHyper), ("lon", H3AgentHyper)]
 
 
 H6_BATCH_FIELDS = ("state", "t", "P_out", "P_avail", "ref", "pid", "gen", "task", "trim_act", "phi_trim", "lr", "rls_W",
                    "rls_cov", "rls_x", "rls_u", "rls_skip", "col_net", "lon_net", "step", "flags", "term_step",
-                   "update_col", "excitation_phase", "acc")
+                   "update_col", "excitation_phase", "acc", "work")
 
 
 class H6Batch(C.Structure):
-    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS]
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS] + [("tile", C.c_int64)]
 
 
 class H6Traj(C.Structure):
@@ -151,6 +152,7 @@ def lib():
     L.h6_rls_update.argtypes = [c6, b6, vp, vp, vp, vp]
     L.h6_rls_predict.argtypes = [b6, vp, vp, vp, vp]
     L.h6_closed_loop.argtypes = [c6, b6, vp, i32, i32, C.POINTER(H6Traj), vp, vp, vp]
+    L.h6_tile_pack.argtypes = [vp, vp, i32, i64, i64, i32, vp]
     L.h6_stats_scratch_bytes.argtypes = [i64]
     L.h6_stats_scratch_bytes.restype = i64
     L.h6_closed_loop_info.argtypes = [c6] + [C.POINTER(i32)] * 4

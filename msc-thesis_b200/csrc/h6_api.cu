@@ -49,6 +49,19 @@ struct GVec {               // one episode's column of a `[rows][ld]` global arr
     H3_DEV double& operator[](int i) { return p[(int64_t)i * ld]; }
 };
 typedef NetAcc<double, NH, GVec> Net;
+struct TVec {               // one episode's column of a tiled `[tile][rows][32]` array: compile-time row stride
+    static constexpr bool kFence = false;
+    double* p;
+    int64_t ld;             // unused (kept so both vectors are set up the same way)
+    H3_DEV double& operator[](int i) { return p[i * 32]; }
+};
+typedef NetAcc<double, NH, TVec> NetTiled;
+template <bool TILED> struct NetOf { typedef Net type; };
+template <> struct NetOf<true> { typedef NetTiled type; };
+
+// H6Batch.tile: offset of episode e's column and the row stride of a `rows`-row array (plain or tiled)
+H3_DEV int64_t tile_off(const H6Batch& b, int64_t e, int rows) { return b.tile ? (e >> 5) * ((int64_t)rows * 32) + (e & 31) : e; }
+H3_DEV int64_t tile_ld(const H6Batch& b) { return b.tile ? 32 : b.ld; }
 
 // ----------------------------------------------------------------------------------------------
 // RecursiveLeastSquares.update (model.py:41-59), n = 17, m = 15, on global-memory W / cov.
@@ -137,7 +150,8 @@ struct AgentIO {            // one agent's per-tick inputs, kept between get_act
     bool fwd;
 };
 
-H3_DEV void agent_step_update(const H3AgentHyper& h, Net& net, double lr_a, double lr_c, const double* __restrict__ W,
+template <typename NetT>
+H3_DEV void agent_step_update(const H3AgentHyper& h, NetT& net, double lr_a, double lr_c, const double* __restrict__ W,
                               int64_t ld, const double (&obs)[NS], const double (&nxt)[NS], const double (&ref)[3],
                               const double (&nref)[3], AgentIO& io, double (&hh)[NH], double& reward, bool tau1_fast) {
     const int ac = h.ac_state, tr = h.tracked_state;
@@ -169,7 +183,7 @@ H3_DEV void agent_step_update(const H3AgentHyper& h, Net& net, double lr_a, doub
         h3::agent_update<double, NH, H6_U, false>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
 }
 
-template <bool SYM>
+template <bool SYM, bool TILED>
 __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __grid_constant__ LoopParams P) {
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
@@ -190,11 +204,12 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
     const double phi_trim = b.phi_trim[e];
     int task = b.task[e], step = b.step[e], update_col = b.update_col[e], exc_phase = b.excitation_phase[e];
     int skip = b.rls_skip[e], term = -1;
-    double* __restrict__ W = b.rls_W + e;
-    double* __restrict__ cov = b.rls_cov + e;
-    Net ncol, nlon;
-    ncol.v.p = b.col_net + e; ncol.v.ld = ld;
-    nlon.v.p = b.lon_net + e; nlon.v.ld = ld;
+    const int64_t lw = TILED ? 32 : b.ld;                   // row stride of W / cov / networks (a constant when tiled)
+    double* __restrict__ W = b.rls_W + tile_off(b, e, NR * NS);
+    double* __restrict__ cov = b.rls_cov + tile_off(b, e, NR * NR);
+    typename NetOf<TILED>::type ncol, nlon;
+    ncol.v.p = b.col_net + tile_off(b, e, 11 * NH); ncol.v.ld = lw;
+    nlon.v.p = b.lon_net + tile_off(b, e, 11 * NH); nlon.v.ld = lw;
     const double inv_gamma = 1.0 / C.rls_gamma;
     int ticks_done = 0, col_updates = 0;
 
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
             for (int i = 0; i < NS; ++i) { X[i] = obs[i] - b.rls_x[i * ld + e]; Y[i] = nxt[i] - obs[i]; }
             X[NS] = act[0] - b.rls_u[e];
             X[NS + 1] = act[1] - b.rls_u[ld + e];
-            rls_update<SYM>(W, cov, ld, X, Y, C.rls_gamma, inv_gamma);
+            rls_update<SYM>(W, cov, lw, X, Y, C.rls_gamma, inv_gamma);
         }
 #pragma unroll
         for (int i = 0; i < NS; ++i) b.rls_x[i * ld + e] = obs[i];
@@ -277,11 +292,11 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
         // agents (:192-201)
         double r_col = 0, r_lon = 0;
         if (update_col) {
-            agent_step_update(C.col, ncol, lr[0], lr[1], W, ld, obs, nxt, ref, nref, io_col, h_col, r_col,
+            agent_step_update(C.col, ncol, lr[0], lr[1], W, lw, obs, nxt, ref, nref, io_col, h_col, r_col,
                               C.col.tau == 1.0 && col_updates > 0);
             col_updates += 1;
         }
-        agent_step_update(C.lon, nlon, lr[2], lr[3], W, ld, obs, nxt, ref, nref, io_lon, h_lon, r_lon,
+        agent_step_update(C.lon, nlon, lr[2], lr[3], W, lw, obs, nxt, ref, nref, io_lon, h_lon, r_lon,
                           C.lon.tau == 1.0 && ticks_done > 0);
         acc[0] += r_col;
         acc[1] += r_lon;
@@ -329,10 +344,10 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
             double r[NR];
 #pragma unroll
             for (int j = 1; j < NR; ++j)
-                if (j > i) r[j] = cov[(int64_t)(i * NR + j) * ld];
+                if (j > i) r[j] = cov[(int64_t)(i * NR + j) * lw];
 #pragma unroll
             for (int j = 1; j < NR; ++j)
-                if (j > i) cov[(int64_t)(j * NR + i) * ld] = r[j];
+                if (j > i) cov[(int64_t)(j * NR + i) * lw] = r[j];
         }
     }
 #pragma unroll
@@ -348,6 +363,12 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
     b.rls_skip[e] = skip;
     if (flags) { b.flags[e] = flags; b.term_step[e] = term; }
 }
+
+}  // namespace h6
+
+#include "h6_split.cuh"
+
+namespace h6 {
 
 // ----------------------------------------------------------------------------------------------
 // statistics: deterministic two-stage reduction (block partials in scratch, then one block)
@@ -654,6 +675,17 @@ __global__ void __launch_bounds__(BLOCK) rls_predict_kernel(H6Batch b, const dou
     }
 }
 
+__global__ void __launch_bounds__(256) tile_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows,
+                                                        int64_t n, int64_t ld, int to_tiled) {
+    const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    if (e >= n) return;
+    const int64_t tb = (e >> 5) * ((int64_t)rows * 32) + (e & 31);
+    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+        if (to_tiled) dst[tb + (int64_t)r * 32] = src[(int64_t)r * ld + e];
+        else dst[(int64_t)r * ld + e] = src[tb + (int64_t)r * 32];
+    }
+}
+
 static bool check_agents(const H6Config* cfg, const char* who) {
     for (const H3AgentHyper* h : {&cfg->col, &cfg->lon}) {
         if (h->n_hidden != NH) { set_error("%s: the 6-DOF kernels are compiled for n_hidden = %d, got %d", who, NH, h->n_hidden); return false; }
@@ -770,7 +802,7 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
     for (const void* p : need)
         if (p == nullptr) { set_error("h6_closed_loop: H6Batch has a null field"); return H3_E_ARG; }
     if (b->n < 0 || b->ld < b->n || n_ticks < 0 || (excitation == nullptr && exc_len > 0) ||
-        cfg->run_mode < H6_MODE_TRAIN || cfg->run_mode > H6_MODE_FREE || (stats != nullptr && stats_scratch == nullptr)) {
+        cfg->run_mode < H6_MODE_TRAIN || cfg->run_mode > H6_MODE_FREE || (b->tile != 0 && b->tile != 32) || (stats != nullptr && stats_scratch == nullptr)) {
         set_error("h6_closed_loop: bad argument");
         return H3_E_ARG;
     }
@@ -780,8 +812,30 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
         LoopParams P;
         P.C = *cfg; P.K = make_modelk(); P.b = *b; P.excitation = excitation; P.exc_len = exc_len; P.n_ticks = n_ticks;
         if (traj != nullptr) P.traj = *traj; else { P.traj.out = nullptr; P.traj.n_traj = 0; P.traj.ld_traj = 0; }
-        if (cfg->rls_symmetric) closed_loop_kernel<true><<<grid_for(b->n), BLOCK, 0, st>>>(P);
-        else closed_loop_kernel<false><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+        if (b->work != nullptr) {
+            // split path: per tick one simulate launch (which first applies the agent updates of the previous tick)
+            // and one wide RLS launch; a final learn-only launch completes the last tick.  (Running the two halves of
+            // a batch on two streams to overlap the FP64-bound and the HBM-bound kernel was measured: no gain, each
+            // kernel fills the SMs' registers and the other stream's blocks only run in its tail.)
+            const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;
+            const unsigned gs = grid_for(b->n), gl = (unsigned)((b->n + 31) / 32);
+            for (int it = 0; it <= n_ticks; ++it) {
+                const int mode = it == n_ticks ? (1 | 4) : ((it > 0 ? 1 : 0) | 2);
+                if (til) sim_kernel<true><<<gs, 128, 0, st>>>(P, it, mode); else sim_kernel<false><<<gs, 128, 0, st>>>(P, it, mode);
+                if (it == n_ticks) {
+                    if (sym) { if (til) mirror_kernel<true><<<gl, LEARN_BLOCK, 0, st>>>(*b); else mirror_kernel<false><<<gl, LEARN_BLOCK, 0, st>>>(*b); }
+                } else if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+                else if (sym) learn_kernel<true, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+                else if (til) learn_kernel<false, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+                else learn_kernel<false, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+            }
+        } else {
+            const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;
+            if (sym && til) closed_loop_kernel<true, true><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+            else if (sym) closed_loop_kernel<true, false><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+            else if (til) closed_loop_kernel<false, true><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+            else closed_loop_kernel<false, false><<<grid_for(b->n), BLOCK, 0, st>>>(P);
+        }
         const int rc = check_launch("h6 closed_loop_kernel");
         if (rc != H3_OK) return rc;
     }
@@ -794,11 +848,18 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
     return H3_OK;
 }
 
+int h6_tile_pack(const double* src, double* dst, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream) {
+    if (!src || !dst || rows <= 0 || n < 0 || ld < n) { set_error("h6_tile_pack: bad argument"); return H3_E_ARG; }
+    if (n == 0) return H3_OK;
+    tile_pack_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, n, ld, to_tiled);
+    return check_launch("h6 tile_pack_kernel");
+}
+
 int64_t h6_stats_scratch_bytes(int64_t n) { return (int64_t)stat_blocks(n) * H6_N_STATS * (int64_t)sizeof(double); }
 
 int h6_closed_loop_info(const H6Config* cfg, int32_t* block, int32_t* blocks_per_sm, int32_t* regs, int32_t* local_bytes) {
     const bool sym = cfg != nullptr && cfg->rls_symmetric;
-    const void* fn = sym ? (const void*)closed_loop_kernel<true> : (const void*)closed_loop_kernel<false>;
+    const void* fn = sym ? (const void*)closed_loop_kernel<true, true> : (const void*)closed_loop_kernel<false, true>;
     cudaFuncAttributes a;
     cudaError_t err = cudaFuncGetAttributes(&a, fn);
     if (err != cudaSuccess) { set_error("cudaFuncGetAttributes: %s", cudaGetErrorString(err)); return H3_E_CUDA; }

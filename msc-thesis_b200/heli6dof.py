@@ -492,6 +492,15 @@ class ClosedLoop6DOF:
         self.stats_dev = torch.zeros(L.H6_N_STATS, dtype=F64, device=dev)
         nbytes = int(L.lib().h6_stats_scratch_bytes(n))
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=F64, device=dev)
+        # scratch of the split path (simulate / learn kernels); split=False runs the fused one-thread-per-episode kernel
+        self.work = torch.zeros(L.H6_WORK_ROWS, n, dtype=F64, device=dev)
+        self.split = True
+        # tiled copies `[ceil(N/32)][rows][32]` of the streamed arrays (W, covariance, networks): inside run() the kernels
+        # work on these (32 episodes' rows are contiguous in HBM); they are packed / unpacked once per run() call
+        self.tiled = True
+        nt = (n + 31) // 32
+        self._tiles = {k: torch.zeros(nt * rows * 32, dtype=F64, device=dev)
+                       for k, rows in (("rls_W", NR * NS), ("rls_cov", NR * NR), ("col_net", 11 * NH), ("lon_net", 11 * NH))}
         self.launches = 0
 
     # -- C-ABI structs ----------------------------------------------------------------------------------------
@@ -513,19 +522,41 @@ class ClosedLoop6DOF:
         cfg.step_switch, cfg.exc_off_step = self.step_switch, 1000
         cfg.rls_symmetric = int(bool(self.rls.assume_symmetric))
         cfg.win_lo, cfg.win_hi = self.score_window
+        cfg.target_synced = self._target_synced()
         for h, agent in ((cfg.col, self.agent_col), (cfg.lon, self.agent_lon)):
             fill_agent(h, agent)
             h.scale = float(scalar(agent.actor.scale))
         return cfg
 
+    def _target_synced(self):
+        """bit 0 (col) / bit 1 (lon): target critic == critic right now (true after any update with tau = 1)."""
+        bits = 0
+        for bit, a in ((1, self.agent_col), (2, self.agent_lon)):
+            nh = a.n_hidden
+            if torch.equal(a.net[7 * nh:11 * nh], a.net[3 * nh:7 * nh]):
+                bits |= bit
+        return bits
+
+    def _plain(self):
+        return {"rls_W": self.rls._W, "rls_cov": self.rls._cov, "col_net": self.agent_col.net, "lon_net": self.agent_lon.net}
+
+    def _pack(self, to_tiled):
+        lib, st, n = L.lib(), L.stream_ptr(self.device), self.n
+        for k, plain in self._plain().items():
+            src, dst = (plain, self._tiles[k]) if to_tiled else (self._tiles[k], plain)
+            L.check(lib.h6_tile_pack(L.ptr(src), L.ptr(dst), plain.shape[0], n, n, int(to_tiled), st))
+
     def batch(self):
         env, rls = self.env, self.rls
-        return _batch(self.n, state=env.state, t=env._t, P_out=env.P_out, P_avail=env.P_available, ref=self.ref3,
+        big = self._tiles if self.tiled else self._plain()
+        b = _batch(self.n, state=env.state, t=env._t, P_out=env.P_out, P_avail=env.P_available, ref=self.ref3,
                       pid=self.pid, gen=self.gen.gen, task=self.gen.task_code, trim_act=self.trim_act,
-                      phi_trim=self.phi_trim, lr=self.lr, rls_W=rls._W, rls_cov=rls._cov, rls_x=rls.x, rls_u=rls.u,
-                      rls_skip=rls._skip, col_net=self.agent_col.net, lon_net=self.agent_lon.net, step=env.step_count,
+                      phi_trim=self.phi_trim, lr=self.lr, rls_W=big["rls_W"], rls_cov=big["rls_cov"], rls_x=rls.x, rls_u=rls.u,
+                      rls_skip=rls._skip, col_net=big["col_net"], lon_net=big["lon_net"], step=env.step_count,
                       flags=env.flags, term_step=env.term_step, update_col=self.update_col,
-                      excitation_phase=self.excitation_phase, acc=self.acc)
+                      excitation_phase=self.excitation_phase, acc=self.acc, work=self.work if self.split else None)
+        b.tile = 32 if self.tiled else 0
+        return b
 
     # -- running ----------------------------------------------------------------------------------------------
     def run(self, n_ticks, record=0):
@@ -535,6 +566,8 @@ class ClosedLoop6DOF:
         lib, st = L.lib(), L.stream_ptr(self.device)
         exc, exc_len = (None, 0) if self.excitation is None else (self.excitation, self.excitation.shape[0])
         traj_out = torch.zeros(n_ticks, L.H6_TRAJ_ROWS, record, dtype=F64, device=self.device) if record else None
+        if self.tiled:
+            self._pack(True)
         done = 0
         while done < n_ticks:
             m = min(self.ticks_per_launch, n_ticks - done)
@@ -547,6 +580,8 @@ class ClosedLoop6DOF:
                                        L.ptr(self.stats_dev) if last else None, L.ptr(self._scratch) if last else None, st))
             self.launches += 1
             done += m
+        if self.tiled:
+            self._pack(False)
         self._sync_objects()
         return traj_out
 

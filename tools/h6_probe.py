@@ -1,5 +1,6 @@
 """Timing probe of the fused 6-DOF kernel: N episodes, phase 1 (PID collective) and phase 2 (both agents)."""
 import importlib
+import os
 import sys
 import time
 
@@ -18,7 +19,9 @@ def main():
         ep = dict(H6.env_params_train, step_switch=switch)
         loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device="cuda", init="batched",
                                    ticks_per_launch=ticks)
-        print("info", loop.info())
+        loop.split = os.environ.get("H6_SPLIT", "1") != "0"
+        loop.tiled = os.environ.get("H6_TILED", "1") != "0"
+        print("info", loop.info(), "split", loop.split)
         loop.run(ticks)
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
