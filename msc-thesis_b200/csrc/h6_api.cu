@@ -1,12 +1,10 @@
 // 6-DOF part of the C ABI (include/heli6dof.h): the fused closed-loop kernel of train.py:109-224 and the
 // un-fused per-object kernels (trim, derivatives, open-loop step, PIDs, reference generator, RLS 17x15).
 //
-// Fused kernel, round-1 design: one thread per episode, n_ticks ticks per launch.  The helicopter state, the
-// PID / reference-generator words and the bookkeeping stay in registers for the whole launch; the incremental
-// model (W 17x15, covariance 17x17: 3.2-4.4 KB per episode) and the two networks do not fit on chip next to
-// enough threads, so they are streamed from HBM every tick with fully coalesced `[row][episode]` accesses:
-// the kernel is HBM-bound by construction and reads/writes each element once per tick
-// (covariance: the upper triangle only while it is known symmetric).
+// Two paths behind h6_closed_loop: the split path (h6_split.cuh: a one-thread-per-episode simulate kernel + a
+// 17-warps-per-32-episodes RLS kernel per tick, default when H6Batch.work is given) and the fused kernel below (one
+// thread per episode streams its own W / covariance / networks from HBM every tick; latency-bound, kept for callers
+// without a work buffer).  DESIGN.md section 9.
 #include <cstdio>
 #include <cstring>
 

@@ -63,6 +63,15 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
     double t = b.t[e], P_out = b.P_out[e], P_avail = b.P_avail[e];
     int task = b.task[e], update_col = b.update_col[e], exc_phase = b.excitation_phase[e];
     const int k = b.step[e];
+    // everything the end of the tick needs from memory is requested now, with the state, so that its latency is
+    // covered by the tick's arithmetic instead of being exposed after the RK4 step
+    const int skip = b.rls_skip[e];
+    double xprev[NS], uprev[2], acc[3];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) xprev[i] = b.rls_x[i * ld + e];
+    uprev[0] = b.rls_u[e]; uprev[1] = b.rls_u[ld + e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] = b.acc[i * ld + e];
 
     const ObsTrig g = obs_trig(obs);
     double act[4];
@@ -109,6 +118,19 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) act[i] = clip01_nan(act[i]);                                              // :176
+    // regressor of the RLS update (:189; model.py:41-46): known before the model step
+    if (skip) b.rls_skip[e] = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if (!skip) wk[(WR_X + i) * ld] = obs[i] - xprev[i];
+        b.rls_x[i * ld + e] = obs[i];
+    }
+    if (!skip) {
+        wk[(WR_X + NS) * ld] = act[0] - uprev[0];
+        wk[(WR_X + NS + 1) * ld] = act[1] - uprev[1];
+    }
+    b.rls_u[e] = act[0];
+    b.rls_u[ld + e] = act[1];
     // env.step (:179; heli_models.py:464-475)
     const Controls ctl = make_controls(P.K, act[0], act[1], act[2], act[3]);
     double nxt[NS];
@@ -118,21 +140,9 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
     gen[H6_GEN_A] = t < C.amp_t[0] ? C.amp[0] : (t < C.amp_t[1] ? C.amp[1] : C.amp[2]);                  // :180-185
     double nref[3];
     gen_get_ref(C, task, gen, obs, t, nref);                                                              // :186 (pre-step obs)
-    // hand-over to phase L: regressor / target of the RLS update (:189; model.py:41-46) ...
-    const int skip = b.rls_skip[e];
-    if (skip) b.rls_skip[e] = 0;
+    // hand-over to phase L: target of the RLS update ...
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        if (!skip) wk[(WR_X + i) * ld] = obs[i] - b.rls_x[i * ld + e];
-        wk[(WR_Y + i) * ld] = nxt[i] - obs[i];
-        b.rls_x[i * ld + e] = obs[i];
-    }
-    if (!skip) {
-        wk[(WR_X + NS) * ld] = act[0] - b.rls_u[e];
-        wk[(WR_X + NS + 1) * ld] = act[1] - b.rls_u[ld + e];
-    }
-    b.rls_u[e] = act[0];
-    b.rls_u[ld + e] = act[1];
+    for (int i = 0; i < NS; ++i) wk[(WR_Y + i) * ld] = nxt[i] - obs[i];
     // ... and the agents' inputs: augmented states, reward and its slope (:192-201; agents.py:123-128, :142-150)
     const double et_lon = nxt[C.lon.tracked_state] - ref_slot(ref, C.lon.tracked_state);
     const double et_col = nxt[C.col.tracked_state] - ref_slot(ref, C.col.tracked_state);
@@ -149,9 +159,9 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
     sc[AG_N1 * ld] = nxt[C.col.tracked_state] - ref_slot(nref, C.col.tracked_state);
     sc[AG_DR * ld] = -2 * et_col * C.col.reward_weight;
     wk[WR_FLAGS * ld] = (double)(WF_ACTIVE | (skip ? 0 : WF_RLS) | (update_col ? WF_COL : 0));
-    b.acc[e] += r_col;
-    b.acc[ld + e] += r_lon;
-    if (k >= C.win_lo && k < C.win_hi) b.acc[2 * ld + e] += r_lon;                                        // :256
+    b.acc[e] = acc[0] + r_col;
+    b.acc[ld + e] = acc[1] + r_lon;
+    if (k >= C.win_lo && k < C.win_hi) b.acc[2 * ld + e] = acc[2] + r_lon;                                // :256
     // termination (:207-218), evaluated on the pre-step observation
     const double R2D = 180.0 / 3.14159265358979323846;
     int fl = done ? H6_FLAG_TMAX : 0;
