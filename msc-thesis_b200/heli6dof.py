@@ -384,6 +384,33 @@ class RecursiveLeastSquares6:
     def gradient_action(self):
         return self.W[NS:NR].transpose(0, 1)
 
+    def state_dict(self):
+        return {"W": self.W.cpu(), "cov": self.cov.cpu(), "x": self.x.cpu(), "u": self.u.cpu(), "skip": self._skip.cpu(),
+                "gamma": self.gamma, "covariance": self.covariance, "state_size": self.state_size,
+                "action_size": self.action_size, "constant": self.constant}
+
+    def load_state_dict(self, d):
+        self.gamma, self.covariance = d["gamma"], d["covariance"]
+        self.W.copy_(d["W"].to(self._W)); self.cov.copy_(d["cov"].to(self._cov))
+        self.x.copy_(d["x"].to(self.x)); self.u.copy_(d["u"].to(self.u)); self._skip.copy_(d["skip"].to(self._skip))
+        self.assume_symmetric = bool(torch.equal(self.cov, self.cov.transpose(0, 1)))
+
+    def save(self, path):
+        """model.py:94-96 pickles the estimator (train.py:238: rls.pkl); here the CPU state dict is pickled."""
+        import pickle
+        with open(path, 'wb') as f:
+            pickle.dump(self.state_dict(), f)
+
+    @classmethod
+    def load(cls, path, **kwargs):
+        import pickle
+        with open(path, 'rb') as f:
+            d = pickle.load(f)
+        obj = cls(state_size=d["state_size"], action_size=d["action_size"], gamma=d["gamma"], covariance=d["covariance"],
+                  constant=d["constant"], n_envs=d["W"].shape[-1], **kwargs)
+        obj.load_state_dict(d)
+        return obj
+
 
 # ------------------------------------------------------------------------------------------------------------
 class DHPAgent6DOF(DHPAgent):
@@ -611,6 +638,31 @@ class ClosedLoop6DOF:
         ok = (self.env.flags & (L.H6_FLAG_NAN | L.H6_FLAG_ENVELOPE)) == 0
         return ok, score
 
+    def to_dataframe(self, log, episode=0, t0=0.0):
+        """The log of one recorded episode as the DataFrame Logger.finalize builds (util.py:30-66, :99): columns t, u, v,
+        w, p, q, r, phi, theta, psi, x, y, z, Pav, Peng, omega, ref (the 15-vector with NaN in unset slots), col, lon,
+        lat, ped, r1, r2.  `t` is env.t after the step, accumulated from t0 like heli_models.py:473."""
+        import pandas as pd
+        rows = log[:, :, episode].detach().cpu().numpy()
+        rows = rows[rows[:, 25] > 0]
+        t, acc = np.empty(len(rows)), float(t0)
+        for i in range(len(rows)):
+            acc = acc + self.env.dt
+            t[i] = acc
+        pav = float(self.env.P_available[episode])
+        df = pd.DataFrame({"t": t})
+        for i, name in enumerate(("u", "v", "w", "p", "q", "r", "phi", "theta", "psi", "x", "y", "z")):
+            df[name] = rows[:, i]
+        df["Pav"] = pav
+        df["Peng"] = np.clip(rows[:, 24], 0, pav)
+        df["omega"] = rows[:, 14]
+        ref = np.full((len(rows), NS), np.nan)
+        ref[:, 0], ref[:, 7], ref[:, 11] = rows[:, 15], rows[:, 16], rows[:, 17]
+        df["ref"] = list(ref)
+        for i, name in enumerate(("col", "lon", "lat", "ped", "r1", "r2")):
+            df[name] = rows[:, 18 + i]
+        return df
+
     def info(self):
         cfg = self.config()
         vals = [C.c_int32() for _ in range(4)]
@@ -658,3 +710,73 @@ def train(mode, env_params, ac_params, rls_params, pid_params, excitation, n_env
     log = loop.run(env_params['n_steps'] + 2, record=record)              # the loop ends by itself at t > t_max
     ok, score = loop.scores()
     return loop, ok, score, log
+
+
+# ------------------------------------------------------------------------------------------------------------
+# main.mp_train (main.py:48-89): grid of lon hyper-parameters x seeds; every (setting, seed) pair is one episode
+# ------------------------------------------------------------------------------------------------------------
+# main.py:107-112
+SWEEP_GRID = {"tau_target_critic": (0.01, 0.1, 1.0), "nn_stdev": (0.05, 0.1, 0.2), "discount_factor": (0.7, 0.8, 0.9, 0.95, 0.99),
+              "learning_rate_actor": (2, 5, 10), "learning_rate_critic": (2, 5, 10)}
+
+
+def _seeded_normal(rows, seeds, salt):
+    """N(0, 1) draws that depend only on (seed, salt): results do not depend on how the sweep is sharded."""
+    out = torch.empty(rows, len(seeds), dtype=F64)
+    for i, sd in enumerate(seeds):
+        g = torch.Generator().manual_seed(int(sd) * 7919 + salt)
+        out[:, i] = torch.randn(rows, generator=g, dtype=F64)
+    return out
+
+
+def mp_train(settings, num_seeds=100, excitation=None, device=None, rank=0, world=1, n_ticks=None, json_dir=None,
+             env_params=None):
+    """main.mp_train: settings = list of (tau, nn_stdev, gamma, lr_actor, lr_critic) applied to the lon agent
+    (main.py:60-65).  tau and gamma are launch-uniform in the kernels, so the settings are grouped by (tau, gamma) and
+    each group runs as one batch of len(group) * num_seeds episodes (sharded over `world` ranks); learning rates and the
+    initial weights are per episode.  Returns {setting: {'success': [...], 'average_rms': [...]}} like the JSON files of
+    main.py:85-89 (written to json_dir if given; with world > 1 every rank holds its shard's entries only)."""
+    import itertools
+    import json
+    import os
+    from .distributed import shard_range
+    ep = dict(env_params_train if env_params is None else env_params)
+    n_ticks = ep["n_steps"] if n_ticks is None else n_ticks
+    results = {}
+    key = lambda s: (float(s[0]), float(s[2]))
+    for (tau, gamma), grp in itertools.groupby(sorted(settings, key=key), key=key):
+        grp = list(grp)
+        setting_of = np.repeat(np.arange(len(grp)), num_seeds)
+        seed_of = np.tile(np.arange(num_seeds), len(grp))
+        lo, hi = shard_range(len(setting_of), rank, world)
+        if hi <= lo:
+            continue
+        n = hi - lo
+        ap = copy.deepcopy(ac_params_train)
+        ap['lon']['tau_target_critic'], ap['lon']['discount_factor'] = tau, gamma
+        loop = make_closed_loop(n, "train", env_params=ep, ac_params=ap, excitation=excitation, device=device, init="batched")
+        sel = np.array([grp[i] for i in setting_of[lo:hi]], dtype=np.float64)
+        dev = loop.device
+        loop.lr[2] = torch.as_tensor(sel[:, 3], device=dev)
+        loop.lr[3] = torch.as_tensor(sel[:, 4], device=dev)
+        std = torch.as_tensor(sel[:, 1])
+        for agent, salt, s in ((loop.agent_lon, 1, std), (loop.agent_col, 2, torch.full((n,), ap['col']['nn_stdev_actor'], dtype=F64))):
+            w = _seeded_normal(7 * NH, seed_of[lo:hi], salt) * s              # actor (3 nh) + critic (4 nh) rows
+            agent.net[:7 * NH] = w.to(dev)
+            agent.net[7 * NH:] = agent.net[3 * NH:7 * NH]                     # target critic = critic (agents.py:107)
+        loop.run(n_ticks + 2)
+        ok, score = loop.scores()
+        ok, score = ok.cpu().numpy(), score.cpu().numpy()
+        for j, st in enumerate(grp):
+            m = setting_of[lo:hi] == j
+            if m.any():
+                # train.py:258-264: (1, score) on success, (0, 0) otherwise
+                results[str(tuple(st))] = {"success": [int(v) for v in ok[m]],
+                                           "average_rms": [float(sc) if o else 0.0 for o, sc in zip(ok[m], score[m])]}
+        del loop
+    if json_dir is not None:
+        os.makedirs(json_dir, exist_ok=True)
+        for k, v in results.items():
+            with open(os.path.join(json_dir, k + ".json"), "w") as f:
+                json.dump(v, f)
+    return results

@@ -188,3 +188,44 @@ def test_object_api_tick_matches_fused_tick():
     assert H.rel_err(a_lon.net.cpu().numpy(), fused.agent_lon.net.cpu().numpy()) < 1e-9
     assert H.rel_err(col_pid.hdot_corr.cpu().numpy(), fused.pid[0].cpu().numpy()) < 1e-9
     assert H.rel_err(next_ref[[0, 7, 11]].cpu().numpy(), fused.ref3.cpu().numpy()) < 1e-9
+
+
+def test_log_dataframe_has_the_reference_logger_columns():
+    """ClosedLoop6DOF.to_dataframe against the reference run's own log (Logger.log_states, util.py:30-66)."""
+    g = H.load("h6_train_short.npz")
+    snap = {k[5:]: v for k, v in g.items() if k.startswith("snap_")}
+    loop = H.build_loop({k: v[:1] for k, v in snap.items()}, "train", step_switch=int(g["step_switch"]),
+                        excitation_=H.excitation())
+    log = loop.run(300, record=1)
+    df = loop.to_dataframe(log)
+    assert list(df.columns) == ["t", "u", "v", "w", "p", "q", "r", "phi", "theta", "psi", "x", "y", "z", "Pav", "Peng",
+                                "omega", "ref", "col", "lon", "lat", "ped", "r1", "r2"]
+    assert len(df) == 300
+    assert H.rel_err(df["t"].to_numpy(), g["traj_t"][:300]) < 1e-14
+    assert H.rel_err(df[["u", "v", "w", "p", "q", "r", "phi", "theta", "psi", "x", "y", "z"]].to_numpy(),
+                     g["traj_state"][:300, :12]) < 1e-7
+    assert H.rel_err(df[["col", "lon", "lat", "ped"]].to_numpy(), g["traj_actions"][:300]) < 1e-7
+    assert H.rel_err(df[["r1", "r2"]].to_numpy(), g["traj_rewards"][:300], floor=1e-9) < 1e-5
+    assert H.rel_err(df["Peng"].to_numpy(), g["traj_P_out"][:300]) < 1e-7
+    ref = np.stack(df["ref"].to_numpy())
+    assert np.isnan(ref[:, 1]).all() and H.rel_err(ref[:, [0, 7, 11]], g["traj_ref"][:300]) < 1e-7
+
+
+def test_sweep_driver_is_shard_independent():
+    """main.mp_train equivalent: (setting, seed) episodes give the same result whether the sweep runs on one rank or
+    is sharded over two; settings with different (tau, gamma) run as separate batches."""
+    H6 = pkg()
+    settings = [(1.0, 0.1, 0.95, 5, 5), (1.0, 0.2, 0.95, 2, 10), (0.1, 0.1, 0.8, 5, 5)]
+    ep = dict(H6.env_params_train, step_switch=40, n_steps=90)
+    one = H6.mp_train(settings, num_seeds=3, excitation=H.excitation(), device=DEV, n_ticks=90, env_params=ep)
+    assert set(one) == {str(tuple(s)) for s in settings}
+    merged = {}
+    for rank in range(2):
+        part = H6.mp_train(settings, num_seeds=3, excitation=H.excitation(), device=DEV, rank=rank, world=2, n_ticks=90,
+                           env_params=ep)
+        for k, v in part.items():
+            merged.setdefault(k, {"success": [], "average_rms": []})
+            merged[k]["success"] += v["success"]
+            merged[k]["average_rms"] += v["average_rms"]
+    assert merged == one
+    assert all(len(v["success"]) == 3 for v in one.values())

@@ -109,6 +109,16 @@ def test_6dof_host_objects_fail_loudly_without_gpu():
     rls = H6.RecursiveLeastSquares6(**H6.rls_params, n_envs=4, device="cpu")
     assert rls.W.shape == (17, 15, 4) and float(rls.cov[3, 3, 0]) == 1e8 and rls.skip_update
     assert H6.env_params_train["step_switch"] == 6000 and H6.env_params_test2["n_steps"] == 3000
+    rls.W[3, 2, 1] = 0.25
+    rls.cov[1, 4, 2] = 7.0
+    rls.skip_update = False
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        rls.save(os.path.join(d, "rls.pkl"))                          # train.py:238
+        back = H6.RecursiveLeastSquares6.load(os.path.join(d, "rls.pkl"), device="cpu")
+    assert torch.equal(back.W, rls.W) and torch.equal(back.cov, rls.cov) and not back.skip_update
+    assert not back.assume_symmetric                                  # the loaded covariance is not symmetric bit for bit
+    assert len(list(__import__("itertools").product(*H6.SWEEP_GRID.values()))) == 3 * 3 * 5 * 3 * 3   # main.py:107-112
     lim, which = H6.envelope_limits_reached(torch.tensor([[0.0] * 6 + [0.0, 1.6] + [0.0] * 7, [0.0] * 6 + [-1.56, 0.0] + [0.0] * 7,
                                                           [0.0] * 15]).T.contiguous())
     assert lim.tolist() == [True, True, False] and which.tolist() == [1, 2, 0]
