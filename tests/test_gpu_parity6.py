@@ -229,3 +229,93 @@ def test_sweep_driver_is_shard_independent():
             merged[k]["average_rms"] += v["average_rms"]
     assert merged == one
     assert all(len(v["success"]) == 3 for v in one.values())
+
+
+@pytest.mark.parametrize("split,tiled", [(False, False), (False, True), (True, False)])
+def test_every_kernel_path_agrees_with_the_fixtures(split, tiled):
+    """The non-default paths of h6_closed_loop (fused kernel, plain layout) on the teacher-forced training ticks
+    and on a 60-tick free run through the switch against the default path."""
+    g = H.load("h6_ticks.npz")
+    info = g["info"]
+    sel = np.nonzero(info[:, 7] == 0)[0]
+    pre = {k[4:]: v[sel] for k, v in g.items() if k.startswith("pre_")}
+    loop = H.build_loop(pre, "train", excitation_=H.excitation())
+    loop.split, loop.tiled = split, tiled
+    loop.run(1)
+    got = H.loop_state(loop)
+    for j, i in enumerate(sel):
+        H.compare(got, g, j, i, 1e-9, "post_")
+        assert int(got["flags"][j]) == int(info[i, 6])
+    H6 = pkg()
+    ep = dict(H6.env_params_train, step_switch=30)
+    runs = []
+    for sp, ti in ((True, True), (split, tiled)):
+        lp = H6.make_closed_loop(96, "train", env_params=ep, excitation=H.excitation(), device=DEV, init="batched",
+                                 generator=torch.Generator().manual_seed(9), ticks_per_launch=25)
+        lp.split, lp.tiled = sp, ti
+        lp.run(60)
+        runs.append(H.loop_state(lp))
+    for k in H.REAL_KEYS:
+        assert H.rel_err(runs[1][k], runs[0][k]) < 1e-9, k
+    assert np.array_equal(runs[1]["step"], runs[0]["step"])
+
+
+def test_heterogeneous_batch_random_trims_against_c_oracle():
+    """Every episode trimmed at its own speed / flight-path angle / altitude (device Newton solve per episode), its own
+    learning rates and networks; 50 free-running ticks through the switch against the C oracle, episode by episode.
+    A ragged batch size exercises the partial tile and the partial block."""
+    H6 = pkg()
+    n = 203
+    rng = np.random.default_rng(12)
+    v, fpa, alt = rng.uniform(5, 30, n), rng.uniform(-4, 4, n), rng.uniform(0, 200, n)
+    ep = dict(H6.env_params_train, step_switch=25, initial_velocity=v, initial_flight_path_angle=fpa, initial_altitude=0.0)
+    loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=H.excitation(), device=DEV, init="batched",
+                               generator=torch.Generator().manual_seed(4), ticks_per_launch=20)
+    # per-episode altitude: trim again with the altitudes (make_closed_loop's collective PID holds one h_ref)
+    st, ct = loop.env.trim(v, fpa, alt)
+    assert (loop.env.trim_iterations > 0).all()
+    loop.ref3.copy_(st[[0, 7, 11]])
+    loop.phi_trim.copy_(st[6])
+    loop.lr.copy_(torch.as_tensor(rng.uniform(0.01, 5.0, (4, n)), device=DEV))
+    cfg = C6.default_config(excitation=H.excitation(), step_switch=25)
+    E = C6.fresh_episodes(n, cfg, seed=0)
+    s0 = H.loop_state(loop)
+    for i in range(n):
+        sc, cc, pc, _ = C6.trim(v[i], fpa[i], alt[i])
+        assert H.rel_err(s0["state"][i], sc) < 1e-8 and abs(s0["P_out"][i] - pc) <= 1e-8 * abs(pc)
+    # start the oracle from the device trims, so that the comparison is of the loop, not of Newton's last digits
+    E["s"], E["P_out"], E["ref"] = s0["state"], s0["P_out"], s0["ref"]
+    E["trim_act"], E["phi_trim"] = loop.env.trim_controls.cpu().numpy().T, loop.phi_trim.cpu().numpy()
+    E["lr"] = s0["lr"]
+    for name in ("col", "lon"):
+        E[name] = np.concatenate([s0[name + "_" + k].reshape(n, -1) for k in H.NET_KEYS], axis=1)
+    loop.run(50)
+    C6.run(E, cfg, 50)
+    got = H.loop_state(loop)
+    assert np.array_equal(got["step"], E["step"]) and np.array_equal(got["flags"], E["flags"])
+    for i in range(n):
+        assert H.rel_err(got["state"][i], E[i]["s"]) < 1e-7, i
+        assert H.rel_err(got["rls_W"][i], E[i]["W"]) < 1e-6, i
+    assert loop.stats()["n"] == n
+
+
+def test_open_loop_rollout_matches_c_oracle_steps():
+    """h6_env_step over many ticks (trim controls + excitation.npy, engine lag, clock) against the oracle's RK4."""
+    H6 = pkg()
+    n, ticks = 70, 400
+    exc = H.excitation()
+    env = H6.Helicopter6DOF(dt=0.01, t_max=120, n_envs=n, device=DEV)
+    v = np.linspace(0.0, 40.0, n)
+    env.trim(v, 0.0, 0.0)
+    s = env.state.cpu().numpy().T.copy()
+    ctl = env.trim_controls.cpu().numpy().T.copy()
+    p = env.P_out.cpu().numpy().copy()
+    out = env.rollout(ticks, excitation=exc, record=n)
+    for i in (0, 1, n // 2, n - 1):
+        si, pi = s[i], float(p[i])
+        for k in range(ticks):
+            si, pi = C6.step(np.clip(ctl[i] + exc[k], 0, 1), si, pi)
+            if k in (0, 99, ticks - 1):
+                assert H.rel_err(out[k, :, i].cpu().numpy(), si) < 1e-9, (i, k)
+        assert abs(float(env.P_out[i]) - pi) <= 1e-9 * abs(pi)
+    assert abs(env.t - ticks * 0.01) < 1e-9 and int(env.step_count[0]) == ticks
