@@ -811,18 +811,23 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
         P.C = *cfg; P.K = make_modelk(); P.b = *b; P.excitation = excitation; P.exc_len = exc_len; P.n_ticks = n_ticks;
         if (traj != nullptr) P.traj = *traj; else { P.traj.out = nullptr; P.traj.n_traj = 0; P.traj.ld_traj = 0; }
         if (b->work != nullptr) {
-            // split path: per tick one simulate launch (which first applies the agent updates of the previous tick)
-            // and one wide RLS launch; a final learn-only launch completes the last tick.  (Running the two halves of
+            // split path: per tick the agent updates of the previous tick, one simulate launch and one wide RLS
+            // launch; a final agents launch completes the last tick.  (Running the two halves of
             // a batch on two streams to overlap the FP64-bound and the HBM-bound kernel was measured: no gain, each
             // kernel fills the SMs' registers and the other stream's blocks only run in its tail.)
             const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;
             const unsigned gs = grid_for(b->n), gl = (unsigned)((b->n + 31) / 32);
+            const dim3 ga(gs, 2);
             for (int it = 0; it <= n_ticks; ++it) {
-                const int mode = it == n_ticks ? (1 | 4) : ((it > 0 ? 1 : 0) | 2);
-                if (til) sim_kernel<true><<<gs, 128, 0, st>>>(P, it, mode); else sim_kernel<false><<<gs, 128, 0, st>>>(P, it, mode);
+                if (it > 0) {
+                    if (til) agents_kernel<true><<<ga, 128, 0, st>>>(P, it == n_ticks); else agents_kernel<false><<<ga, 128, 0, st>>>(P, it == n_ticks);
+                }
                 if (it == n_ticks) {
                     if (sym) { if (til) mirror_kernel<true><<<gl, LEARN_BLOCK, 0, st>>>(*b); else mirror_kernel<false><<<gl, LEARN_BLOCK, 0, st>>>(*b); }
-                } else if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+                    break;
+                }
+                if (til) sim_kernel<true><<<gs, 128, 0, st>>>(P, it); else sim_kernel<false><<<gs, 128, 0, st>>>(P, it);
+                if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
                 else if (sym) learn_kernel<true, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
                 else if (til) learn_kernel<false, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
                 else learn_kernel<false, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);

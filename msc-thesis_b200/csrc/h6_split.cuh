@@ -1,9 +1,9 @@
 // Split form of the 6-DOF closed loop (train.py:109-224): per tick one launch of each of two kernels that are
 // shaped for opposite bounds, instead of one register allocation for both.
 //
-//   sim_kernel   ("S", one thread per episode, up to 255 registers, no spills): the pending IDHP updates of the
-//                previous tick, then PIDs, reference generator, actor forward passes and the RK4 step of the
-//                15-state model.  FP64 / latency work on ~60 words of per-episode state.
+//   agents_kernel (one thread per (episode, agent), 16 warps per SM): the IDHP updates of the previous tick.
+//   sim_kernel   ("S", one thread per episode, 168 registers): PIDs, reference generator, actor forward passes and
+//                the RK4 step of the 15-state model.  FP64 / latency work on ~60 words of per-episode state.
 //   learn_kernel ("L", 17 warps per 32 episodes): the 17x15 RLS update.  Lanes are episodes (coalesced
 //                `[row][episode]` accesses), warp r owns row r of the covariance (cov.X, its downdate) and column r
 //                of W (prediction error + update): every thread has 17 independent loads in flight and there are 34
@@ -196,53 +196,51 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
 }
 
 
-// mode bit 0: apply the pending agent updates of the previous tick; bit 1: simulate one tick; bit 2: last launch
-// of the call (tau == 1 fast path: refresh the target critic rows from the critic).
-//   fast_lon / fast_col: tau == 1 and the target critic equals the critic at call entry (H6Config.target_synced):
-//   the target rows are then neither read nor written by the updates (agents.py:196 makes them equal again).
-#ifndef H6_SIM_MINB
-#define H6_SIM_MINB 3
-#endif
+// The IDHP updates of the tick that learn_kernel just completed (they need its W): one thread per (episode,
+// agent), blockIdx.y = 0 lon, 1 col, 128 registers -> 16 warps per SM to hide the latency of the weight loads.
+//   fast: tau == 1 and the target critic equals the critic at call entry (H6Config.target_synced): the target rows
+//   are then neither read nor written by the updates (agents.py:196 makes them equal again); they are refreshed from
+//   the critic after an episode's last update of the call (`final`, or the episode has just ended).
 template <bool TILED>
-__global__ void __launch_bounds__(128, H6_SIM_MINB) sim_kernel(const __grid_constant__ LoopParams P, int it, int mode) {
+__global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ LoopParams P, int final) {
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
     if (e >= b.n) return;
+    const double* wk = b.work + e;
+    const int wf = (int)wk[WR_FLAGS * ld];
+    const bool col = blockIdx.y == 1;
+    if (!(wf & WF_ACTIVE) || (col && !(wf & WF_COL))) return;
+    const H3AgentHyper& h = col ? C.col : C.lon;
+    const bool fast = h.tau == 1.0 && (C.target_synced & (col ? 1 : 2));
+    const int64_t lw = TILED ? 32 : ld;
+    const double* __restrict__ W = b.rls_W + tile_off(b, e, NR * NS);
+    typename NetOf<TILED>::type net;
+    net.v.p = (col ? b.col_net : b.lon_net) + tile_off(b, e, 11 * NH); net.v.ld = lw;
+    const int o = col ? 0 : 2;
+    agent_learn(h, net, b.lr[o * ld + e], b.lr[(o + 1) * ld + e], W, lw, ld, wk + (col ? WR_COL : WR_LON) * ld, fast);
+    if (fast && (final || b.flags[e] != 0)) {
+#pragma unroll 4
+        for (int r = 0; r < 4 * NH; ++r) net.v[7 * NH + r] = net.v[3 * NH + r];
+    }
+}
+
+#ifndef H6_SIM_MINB
+#define H6_SIM_MINB 3
+#endif
+// One tick of PIDs, reference generator, actions and the RK4 model step for every live episode.
+template <bool TILED>
+__global__ void __launch_bounds__(128, H6_SIM_MINB) sim_kernel(const __grid_constant__ LoopParams P, int it) {
+    const H6Batch& b = P.b;
+    const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
+    if (e >= b.n) return;
     double* wk = b.work + e;
-    const bool fast_lon = C.lon.tau == 1.0 && (C.target_synced & 2), fast_col = C.col.tau == 1.0 && (C.target_synced & 1);
-    if (mode & 1) {
-        const int wf = (int)wk[WR_FLAGS * ld];
-        if (wf & WF_ACTIVE) {
-            const int64_t lw = TILED ? 32 : ld;
-            const double* __restrict__ W = b.rls_W + tile_off(b, e, NR * NS);
-            typename NetOf<TILED>::type ncol, nlon;
-            ncol.v.p = b.col_net + tile_off(b, e, 11 * NH); ncol.v.ld = lw;
-            nlon.v.p = b.lon_net + tile_off(b, e, 11 * NH); nlon.v.ld = lw;
-            if (wf & WF_COL) agent_learn(C.col, ncol, b.lr[e], b.lr[ld + e], W, lw, ld, wk + WR_COL * ld, fast_col);
-            agent_learn(C.lon, nlon, b.lr[2 * ld + e], b.lr[3 * ld + e], W, lw, ld, wk + WR_LON * ld, fast_lon);
-            if ((mode & 4) || b.flags[e] != 0) {     // last launch of the call, or the episode's last update
-                if (fast_lon) {
-#pragma unroll 4
-                    for (int r = 0; r < 4 * NH; ++r) nlon.v[7 * NH + r] = nlon.v[3 * NH + r];
-                }
-                if (fast_col && (wf & WF_COL)) {
-#pragma unroll 4
-                    for (int r = 0; r < 4 * NH; ++r) ncol.v[7 * NH + r] = ncol.v[3 * NH + r];
-                }
-            }
-        }
-    }
-    if (mode & 2) {
-        if (b.flags[e] != 0) {                              // frozen: the episode has ended
-            wk[WR_FLAGS * ld] = 0.0;
-            if (P.traj.out != nullptr && e < P.traj.n_traj) P.traj.out[((int64_t)it * H6_TRAJ_ROWS + 25) * P.traj.ld_traj + e] = 0.0;
-            return;
-        }
-        tick_simulate<TILED>(P, e, it, wk);
-    } else {
+    if (b.flags[e] != 0) {                                  // frozen: the episode has ended
         wk[WR_FLAGS * ld] = 0.0;
+        if (P.traj.out != nullptr && e < P.traj.n_traj) P.traj.out[((int64_t)it * H6_TRAJ_ROWS + 25) * P.traj.ld_traj + e] = 0.0;
+        return;
     }
+    tick_simulate<TILED>(P, e, it, wk);
 }
 
 // RecursiveLeastSquares.update (model.py:41-59), n = 17, m = 15: 32 episodes per block (lanes), 17 warps.
