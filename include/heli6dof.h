@@ -30,6 +30,7 @@ extern "C" {
 #define H6_N_HIDDEN 10  /* params.py: n_hidden_actor = n_hidden_critic = 10 for both agents */
 #define H6_N_STATS 10
 #define H6_WORK_ROWS 44
+#define H6_HIST_ROWS 50   /* per tick: X (17), cov.X (17), 1/d (1; 0 = no RLS update that tick), Y (15) */
 
 #define H6_FLAG_TMAX 1
 #define H6_FLAG_NAN 2
@@ -120,6 +121,13 @@ typedef struct H6Batch {
     double* acc;         /* [3][ld] sum r_col, sum r_lon, sum r_lon inside the score window */
     double* work;        /* [H6_WORK_ROWS][ld] scratch of the split path (simulate / learn kernels), or NULL:
                             h6_closed_loop then runs the fused one-thread-per-episode kernel */
+    double* hist;        /* [hist_len][H6_HIST_ROWS][ld] or NULL.  With a history buffer the split path updates only
+                            the columns of W the agents read (their ac_state / tracked_state columns, agents.py:130-140)
+                            every tick; the other columns -- independent recursions that nothing reads inside the
+                            loop -- are brought up to date from the recorded (X, cov.X, 1/d, Y) every hist_len ticks
+                            and at the end of the call, with W held in registers: same arithmetic, a third less
+                            HBM traffic per tick */
+    int64_t hist_len;
     int64_t tile;        /* 0: rls_W, rls_cov, col_net, lon_net are plain `[row][ld]`; 32: they are tiled
                             `[ceil(n/32)][rows][32]` (32 episodes' rows contiguous: sequential HBM pages for the
                             streaming kernels), see h6_tile_pack.  Only h6_closed_loop accepts tiled buffers. */

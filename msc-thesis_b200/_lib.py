@@ -62,7 +62,7 @@ class H3Traj(C.Structure):
 
 # ---- 6-DOF (include/heli6dof.h) ------------------------------------------------------------------------------
 H6_N_STATE, H6_N_ACTION, H6_N_REG, H6_N_HIDDEN, H6_N_STATS, H6_TRAJ_ROWS, H6_GEN_ROWS = 15, 4, 17, 10, 10, 26, 8
-H6_WORK_ROWS = 44
+H6_WORK_ROWS, H6_HIST_ROWS = 44, 50
 H6_FLAG_TMAX, H6_FLAG_NAN, H6_FLAG_ENVELOPE, H6_FLAG_LANDED = 1, 2, 4, 8
 H6_TASKS = {None: 0, "hover": 1, "train_lon": 2, "train_col": 3, "velocity": 4, "descent": 5}
 H6_MODES = {"train": 0, "test_1": 1, "test_2": 2, "free": 3}
@@ -90,7 +90,7 @@ H6_BATCH_FIELDS = ("state", "t", "P_out", "P_avail", "ref", "pid", "gen", "task"
 
 
 class H6Batch(C.Structure):
-    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS] + [("tile", C.c_int64)]
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS] + [("hist", C.c_void_p), ("hist_len", C.c_int64), ("tile", C.c_int64)]
 
 
 class H6Traj(C.Structure):

@@ -818,6 +818,16 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
             const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;
             const unsigned gs = grid_for(b->n), gl = (unsigned)((b->n + 31) / 32);
             const dim3 ga(gs, 2);
+            // columns of W the agents read (agents.py:130-140); with a history buffer only these are updated every tick
+            const unsigned live = (1u << cfg->col.ac_state) | (1u << cfg->col.tracked_state) | (1u << cfg->lon.ac_state) |
+                                  (1u << cfg->lon.tracked_state);
+            const bool lazy = b->hist != nullptr && b->hist_len > 0;
+            const int T = lazy ? (int)(b->hist_len < LAZY_MAX_SLOTS ? b->hist_len : LAZY_MAX_SLOTS) : 1;
+            if (lazy) {
+                const int smem = LAZY_MAX_SLOTS * LAZY_ROWS * 32 * (int)sizeof(double);
+                cudaFuncSetAttribute(lazy_w_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                cudaFuncSetAttribute(lazy_w_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            }
             for (int it = 0; it <= n_ticks; ++it) {
                 if (it > 0) {
                     if (til) agents_kernel<true><<<ga, 128, 0, st>>>(P, it == n_ticks); else agents_kernel<false><<<ga, 128, 0, st>>>(P, it == n_ticks);
@@ -827,10 +837,17 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
                     break;
                 }
                 if (til) sim_kernel<true><<<gs, 128, 0, st>>>(P, it); else sim_kernel<false><<<gs, 128, 0, st>>>(P, it);
-                if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
-                else if (sym) learn_kernel<true, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
-                else if (til) learn_kernel<false, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
-                else learn_kernel<false, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma);
+                const int slot = it % T;
+                double* hs = lazy ? b->hist + (int64_t)slot * H6_HIST_ROWS * b->ld : nullptr;
+                if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                else if (sym) learn_kernel<true, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                else if (til) learn_kernel<false, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                else learn_kernel<false, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                if (lazy && (slot == T - 1 || it == n_ticks - 1)) {
+                    const size_t sm = (size_t)(slot + 1) * LAZY_ROWS * 32 * sizeof(double);
+                    if (til) lazy_w_kernel<true><<<gl, 32 * NS, sm, st>>>(*b, live, slot + 1);
+                    else lazy_w_kernel<false><<<gl, 32 * NS, sm, st>>>(*b, live, slot + 1);
+                }
             }
         } else {
             const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;

@@ -260,7 +260,8 @@ constexpr int LEARN_WARPS = NR, LEARN_BLOCK = 32 * LEARN_WARPS;
 constexpr int LEARN_CH = H6_LEARN_CH;
 
 template <bool SYM, bool TILED>
-__global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Batch b, double gamma) {
+__global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Batch b, double gamma, unsigned live_mask,
+                                                                           double* __restrict__ hist) {
     __shared__ double Xs[NR][32], cXs[NR][32], Xcs[SYM ? 1 : NR][32];
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * 32 + lane, ld = b.ld;
@@ -273,7 +274,15 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
     double* __restrict__ rowp = cov + (int64_t)(r * NR) * lw;       // element (r, j) at rowp[j * lw]
     const double* __restrict__ colp = cov + (int64_t)r * lw;          // element (j, r) at colp[j * NR * lw]
     double* __restrict__ wp = b.rls_W + tile_off(b, e, NR * NS) + (int64_t)r * lw;     // W(i, r) at wp[i * NS * lw]
-    Xs[r][lane] = on ? wk[(WR_X + r) * ld] : 0.0;
+    // hist != nullptr: this tick's slot of the history, [H6_HIST_ROWS][ld]; columns of W outside live_mask are not
+    // touched here but brought up to date later by lazy_w_kernel from the recorded X, cov.X, 1/d, Y
+    double* __restrict__ hs = hist != nullptr ? hist + e : nullptr;
+    const double xr = on ? wk[(WR_X + r) * ld] : 0.0;
+    Xs[r][lane] = xr;
+    if (hs != nullptr && in) {
+        if (on) hs[(int64_t)r * ld] = xr;
+        else if (r == 0) hs[(int64_t)(2 * NR) * ld] = 0.0;                     // 1/d = 0: no update this tick
+    }
     __syncthreads();
     double cx = 0, xc = 0;
     if (on) {
@@ -312,12 +321,14 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
     }
     cXs[r][lane] = cx;
     if (!SYM) Xcs[r][lane] = xc;
+    if (hs != nullptr && on) hs[(int64_t)(NR + r) * ld] = cx;
     __syncthreads();
     if (!on) return;
     double d = gamma;                                                           // model.py:55
 #pragma unroll
     for (int i = 0; i < NR; ++i) d += (SYM ? cXs[i][lane] : Xcs[i][lane]) * Xs[i][lane];
     const double inv_d = 1.0 / d, inv_gamma = 1.0 / gamma;
+    if (hs != nullptr && r == NR - 1) hs[(int64_t)(2 * NR) * ld] = inv_d;
     // model.py:59, row r (re-read: the row was loaded a moment ago by this warp, it is in L1 / L2)
     {
         const double gr = cx * inv_d;
@@ -335,7 +346,9 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
         }
     }
     // model.py:49-50, :58, column r of W
-    if (r < NS) {
+    if (r < NS && hs != nullptr && !((live_mask >> r) & 1u)) {
+        hs[(int64_t)(2 * NR + 1 + r) * ld] = wk[(WR_Y + r) * ld];
+    } else if (r < NS) {
         double w[NR], ya = wk[(WR_Y + r) * ld], yb = 0;
 #pragma unroll
         for (int i = 0; i < NR; ++i) w[i] = wp[(int64_t)(i * NS) * lw];
@@ -346,6 +359,61 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
         const double err = (ya - yb) * inv_d;
 #pragma unroll
         for (int i = 0; i < NR; ++i) wp[(int64_t)(i * NS) * lw] = w[i] + cXs[i][lane] * err;
+    }
+}
+
+// The columns of W that nothing reads inside the loop (all but the agents' ac_state / tracked_state columns): column
+// j of model.py:49-50, :58 is a recursion of its own (shared gain, own weights), so it can be advanced over n_slots
+// recorded ticks in one go with its 17 weights in registers.  32 episodes per block, warp j = column j.
+// The recorded X, cov.X and 1/d of the block's 32 episodes are first staged in shared memory by all 15 warps
+// (independent coalesced loads: bandwidth-bound), then every lazy column runs its recursion out of shared memory.
+constexpr int LAZY_ROWS = 2 * NR + 1;
+constexpr int LAZY_MAX_SLOTS = 8;                               // 8 * 35 * 256 B = 72 KB of shared memory per block
+template <bool TILED>
+__global__ void __launch_bounds__(32 * NS, 2) lazy_w_kernel(H6Batch b, unsigned live_mask, int n_slots) {
+    extern __shared__ double hsm[];                             // [n_slots][LAZY_ROWS][32]
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int64_t e = (int64_t)blockIdx.x * 32 + lane, ld = b.ld;
+    const bool in = e < b.n;
+    const bool lazy_col = !((live_mask >> j) & 1u);
+    const int64_t lw = TILED ? 32 : ld;
+    double* __restrict__ wp = b.rls_W + tile_off(b, in ? e : 0, NR * NS) + (int64_t)j * lw;
+    double w[NR], y[LAZY_MAX_SLOTS];
+    if (in && lazy_col) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) w[i] = wp[(int64_t)(i * NS) * lw];
+#pragma unroll
+        for (int t = 0; t < LAZY_MAX_SLOTS; ++t)
+            if (t < n_slots) y[t] = b.hist[((int64_t)t * H6_HIST_ROWS + 2 * NR + 1 + j) * ld + e];
+    }
+    for (int idx = j; idx < n_slots * LAZY_ROWS; idx += NS) {
+        const int t = idx / LAZY_ROWS, row = idx - t * LAZY_ROWS;
+        hsm[idx * 32 + lane] = in ? b.hist[((int64_t)t * H6_HIST_ROWS + row) * ld + e] : 0.0;
+    }
+    __syncthreads();
+    if (!in || !lazy_col) return;
+    bool touched = false;
+#pragma unroll
+    for (int t = 0; t < LAZY_MAX_SLOTS; ++t) {
+        if (t < n_slots) {
+            const double* __restrict__ hs = hsm + (t * LAZY_ROWS) * 32 + lane;
+            const double inv_d = hs[(2 * NR) * 32];
+            if (inv_d != 0.0) {
+                double ya = y[t], yb = 0;
+#pragma unroll
+                for (int i = 0; i < NR; i += 2) ya -= hs[i * 32] * w[i];
+#pragma unroll
+                for (int i = 1; i < NR; i += 2) yb += hs[i * 32] * w[i];
+                const double err = (ya - yb) * inv_d;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) w[i] = w[i] + hs[(NR + i) * 32] * err;
+                touched = true;
+            }
+        }
+    }
+    if (touched) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) wp[(int64_t)(i * NS) * lw] = w[i];
     }
 }
 

@@ -528,6 +528,12 @@ class ClosedLoop6DOF:
         nt = (n + 31) // 32
         self._tiles = {k: torch.zeros(nt * rows * 32, dtype=F64, device=dev)
                        for k, rows in (("rls_W", NR * NS), ("rls_cov", NR * NR), ("col_net", 11 * NH), ("lon_net", 11 * NH))}
+        # lazy=True: only the 4 columns of W the agents read are updated every tick, the other 11 are advanced every
+        # hist_len ticks from a recorded history (H6Batch.hist).  Same results, 28 % less RLS traffic, but measured no
+        # faster (the per-tick kernel loses as much efficiency as the catch-up kernel costs), so it is off by default
+        self.lazy = False
+        self.hist_len = 8
+        self._hist = None
         self.launches = 0
 
     # -- C-ABI structs ----------------------------------------------------------------------------------------
@@ -583,6 +589,10 @@ class ClosedLoop6DOF:
                       flags=env.flags, term_step=env.term_step, update_col=self.update_col,
                       excitation_phase=self.excitation_phase, acc=self.acc, work=self.work if self.split else None)
         b.tile = 32 if self.tiled else 0
+        if self.split and self.lazy:
+            if self._hist is None or self._hist.shape[0] != self.hist_len:
+                self._hist = torch.zeros(self.hist_len, L.H6_HIST_ROWS, self.n, dtype=F64, device=self.device)
+            b.hist, b.hist_len = L.ptr(self._hist).value, self.hist_len
         return b
 
     # -- running ----------------------------------------------------------------------------------------------

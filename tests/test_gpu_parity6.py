@@ -231,8 +231,9 @@ def test_sweep_driver_is_shard_independent():
     assert all(len(v["success"]) == 3 for v in one.values())
 
 
-@pytest.mark.parametrize("split,tiled", [(False, False), (False, True), (True, False)])
-def test_every_kernel_path_agrees_with_the_fixtures(split, tiled):
+@pytest.mark.parametrize("split,tiled,lazy", [(False, False, False), (False, True, False), (True, False, False),
+                                              (True, True, True), (True, False, True)])
+def test_every_kernel_path_agrees_with_the_fixtures(split, tiled, lazy):
     """The non-default paths of h6_closed_loop (fused kernel, plain layout) on the teacher-forced training ticks
     and on a 60-tick free run through the switch against the default path."""
     g = H.load("h6_ticks.npz")
@@ -240,7 +241,7 @@ def test_every_kernel_path_agrees_with_the_fixtures(split, tiled):
     sel = np.nonzero(info[:, 7] == 0)[0]
     pre = {k[4:]: v[sel] for k, v in g.items() if k.startswith("pre_")}
     loop = H.build_loop(pre, "train", excitation_=H.excitation())
-    loop.split, loop.tiled = split, tiled
+    loop.split, loop.tiled, loop.lazy = split, tiled, lazy
     loop.run(1)
     got = H.loop_state(loop)
     for j, i in enumerate(sel):
@@ -249,10 +250,10 @@ def test_every_kernel_path_agrees_with_the_fixtures(split, tiled):
     H6 = pkg()
     ep = dict(H6.env_params_train, step_switch=30)
     runs = []
-    for sp, ti in ((True, True), (split, tiled)):
+    for which, (sp, ti) in enumerate(((True, True), (split, tiled))):
         lp = H6.make_closed_loop(96, "train", env_params=ep, excitation=H.excitation(), device=DEV, init="batched",
                                  generator=torch.Generator().manual_seed(9), ticks_per_launch=25)
-        lp.split, lp.tiled = sp, ti
+        lp.split, lp.tiled, lp.lazy, lp.hist_len = sp, ti, (lazy if which == 1 else False), 7
         lp.run(60)
         runs.append(H.loop_state(lp))
     for k in H.REAL_KEYS:

@@ -84,7 +84,7 @@ int main(void) {
                                                   ("lat_gains", "amp", "run_mode", "win_hi", "col", "lon")]
     assert [int(x) for x in lines[2].split()] == [getattr(L.H6Batch, k).offset for k in
                                                   ("state", "trim_act", "rls_skip", "acc")]
-    assert len(L.H6_BATCH_FIELDS) == 25 and L.H6Batch.tile.offset == L.H6Batch.work.offset + 8
+    assert len(L.H6_BATCH_FIELDS) == 25 and L.H6Batch.tile.offset == L.H6Batch.work.offset + 24
 
 
 def test_6dof_host_objects_fail_loudly_without_gpu():

@@ -21,6 +21,8 @@ def main():
                                    ticks_per_launch=ticks)
         loop.split = os.environ.get("H6_SPLIT", "1") != "0"
         loop.tiled = os.environ.get("H6_TILED", "1") != "0"
+        loop.lazy = os.environ.get("H6_LAZY", "0") != "0"
+        loop.hist_len = int(os.environ.get("H6_HIST", "8"))
         print("info", loop.info(), "split", loop.split)
         loop.run(ticks)
         torch.cuda.synchronize()
