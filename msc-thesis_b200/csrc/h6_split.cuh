@@ -46,8 +46,11 @@ H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr
 
 // Phase S of one tick (PIDs, reference generator, actions, RK4, bookkeeping) for one episode; leaves what
 // phase L needs in the work rows `wk` (global memory, [H6_WORK_ROWS][ld]).
+#ifndef H6_SIM_SMEM
+#define H6_SIM_SMEM 1
+#endif
 template <bool TILED>
-H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
+H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk, double* rk_sm) {
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t ld = b.ld;
@@ -134,7 +137,11 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk) {
     // env.step (:179; heli_models.py:464-475)
     const Controls ctl = make_controls(P.K, act[0], act[1], act[2], act[3]);
     double nxt[NS];
+#if H6_SIM_SMEM
+    rk4_step_smem(P.K, ctl, obs, P_out, P_avail, C.dt, nxt, rk_sm, 128);
+#else
     rk4_step(P.K, ctl, obs, P_out, P_avail, C.dt, nxt);
+#endif
     const bool done = t > C.t_max;
     t += C.dt;
     gen[H6_GEN_A] = t < C.amp_t[0] ? C.amp[0] : (t < C.amp_t[1] ? C.amp[1] : C.amp[2]);                  // :180-185
@@ -240,7 +247,8 @@ __global__ void __launch_bounds__(128, H6_SIM_MINB) sim_kernel(const __grid_cons
         if (P.traj.out != nullptr && e < P.traj.n_traj) P.traj.out[((int64_t)it * H6_TRAJ_ROWS + 25) * P.traj.ld_traj + e] = 0.0;
         return;
     }
-    tick_simulate<TILED>(P, e, it, wk);
+    __shared__ double rk_tile[H6_SIM_SMEM ? 30 * 128 : 1];
+    tick_simulate<TILED>(P, e, it, wk, rk_tile + threadIdx.x);
 }
 
 // RecursiveLeastSquares.update (model.py:41-59), n = 17, m = 15: 32 episodes per block (lanes), 17 warps.
