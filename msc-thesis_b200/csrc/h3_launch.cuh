@@ -236,6 +236,12 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
             return H3_E_CUDA;
         }
     }
+#ifdef H3_WIDE_IMPL
+    if constexpr (std::is_same<ET, double>::value && std::is_same<NT, double>::value) {
+        // launches in which both agents learn, main_3dof.py configuration: the 16-warps-per-32-episodes kernel
+        if (col && wide_eligible(cfg, b, step0, n_ticks, ref_table, traj)) return launch_wide(P, stream);
+    }
+#endif
     k.fn<<<(unsigned)grid, k.block, k.smem, stream>>>(P);
     err = cudaGetLastError();
     if (err != cudaSuccess) {

@@ -514,3 +514,24 @@ def test_compaction_changes_nothing_but_the_order(h3):
         assert sp[k] == sc[k], k
     for k in ("sum_r_col", "sum_r_lon"):
         assert abs(sp[k] - sc[k]) <= 1e-9 * abs(sp[k])
+
+
+def test_wide_kernel_option_matches_the_default_kernel(h3, monkeypatch):
+    """csrc/h3_wide.cuh (16 warps per 32 episodes; opt-in with H3_WIDE=1, slower than the default kernel): same
+    results as the one-thread-per-episode kernel on launches where both agents learn."""
+    import bench
+    outs = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("H3_WIDE", wide)
+        loop = bench.make_workload(h3, torch, 777, "f64", torch.device("cuda", 0), seed=5, store=0, ticks=40)
+        loop.switch_step = 40
+        loop.run(40)
+        loop.run(80)
+        outs.append((loop.env.state.clone(), loop.rls.W.clone(), loop.rls.cov.clone(), loop.agent_col.net.clone(),
+                     loop.agent_lon.net.clone(), loop.env.flags.clone(), loop.stats()))
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        scale = a.abs().max().item()
+        assert (a - b).abs().max().item() <= 1e-9 * scale
+    assert torch.equal(outs[0][5], outs[1][5])
+    assert outs[0][6]["sum_ticks"] == outs[1][6]["sum_ticks"] and outs[0][6]["n_alive"] == outs[1][6]["n_alive"]
+    assert abs(outs[0][6]["sum_r_lon"] - outs[1][6]["sum_r_lon"]) <= 1e-9 * abs(outs[0][6]["sum_r_lon"])
