@@ -320,3 +320,28 @@ def test_open_loop_rollout_matches_c_oracle_steps():
                 assert H.rel_err(out[k, :, i].cpu().numpy(), si) < 1e-9, (i, k)
         assert abs(float(env.P_out[i]) - pi) <= 1e-9 * abs(pi)
     assert abs(env.t - ticks * 0.01) < 1e-9 and int(env.step_count[0]) == ticks
+
+
+@pytest.mark.parametrize("mode_id,mode", [(1, "test_1"), (2, "test_2")])
+def test_free_running_test_episodes_end_like_the_reference(mode_id, mode):
+    """Whole test_1 / test_2 episodes from tick 0 (agents and RLS of the trained fixture run): terminal tick and flags
+    bit-exact against the reference run; the OEI landing (test_2) also reproduces the final state and the C oracle's."""
+    g = H.load("h6_ticks.npz")
+    info = g["info"]
+    pre = {k[4:]: v for k, v in g.items() if k.startswith("pre_")}
+    sel = np.nonzero((info[:, 7] == mode_id) & (pre["step"] == 0))[0][:1]
+    last = np.nonzero(info[:, 7] == mode_id)[0]
+    j = last[np.argmax(pre["step"][last])]
+    loop = H.build_loop({k: v[sel] for k, v in pre.items()}, mode, excitation_=H.excitation(), ticks_per_launch=700)
+    log = loop.run(4100 if mode == "test_1" else 1800, record=1)
+    got = H.loop_state(loop)
+    assert int(got["term_step"][0]) == int(pre["step"][j]) and int(got["flags"][0]) == int(info[j, 6])
+    assert int(got["step"][0]) == int(pre["step"][j]) + 1
+    assert int(log[:, 25, 0].sum().item()) == int(pre["step"][j]) + 1          # ticks logged as executed
+    if mode == "test_2":
+        assert H.rel_err(got["state"][0], g["post_state"][j]) < 1e-6
+        df = loop.to_dataframe(log)
+        assert float(df["Pav"].iloc[0]) == float(df["Pav"].iloc[-1])          # Pav column = P_available at export time
+        assert abs(float(df["z"].iloc[-1]) - float(pre["state"][j][11])) < 1e-6
+        st = loop.stats()
+        assert st["n_landed"] == 1 and st["n_alive"] == 0

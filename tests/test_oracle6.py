@@ -125,3 +125,31 @@ def test_restart_from_every_snapshot_is_tight():
         e = E[i:i + 1].copy()
         C6.run(e, cfg, ticks[i + 1] - ticks[i])
         compare_snapshot(C6.unpack_episode(e[0]), g, i + 1, 1e-9, "snap_")
+
+
+def _episode_from_tick0(mode_id):
+    g = load("h6_ticks.npz")
+    info = g["info"]
+    pre = {k[4:]: v for k, v in g.items() if k.startswith("pre_")}
+    sel = np.nonzero((info[:, 7] == mode_id) & (pre["step"] == 0))[0][:1]
+    last = np.nonzero(info[:, 7] == mode_id)[0]
+    j = last[np.argmax(pre["step"][last])]
+    return g, info, pre, sel, j
+
+
+def test_free_running_test_episodes_end_like_the_reference():
+    """train.py test_1 (hover, accelerate, decelerate; ends on t > t_max) and test_2 (descent, engine failure at
+    tick 1000, flare at 12.93 s; ends on touch-down) from tick 0 to the end: the terminal tick and flags are the
+    reference's; the OEI landing also reproduces the final state."""
+    exc = excitation()
+    for mode_id, mode, kw in ((1, "test_1", dict(t_max=40, step_switch=6000, h_ref=0)),
+                              (2, "test_2", dict(t_max=30, step_switch=3000, h_ref=30))):
+        g, info, pre, sel, j = _episode_from_tick0(mode_id)
+        E = C6.pack_snapshots({k: v[sel] for k, v in pre.items()})
+        C6.run(E, C6.default_config(run_mode=mode, excitation=exc, **kw), 5000)
+        assert int(E[0]["term_step"]) == int(pre["step"][j]) and int(E[0]["flags"]) == int(info[j, 6])
+        assert int(E[0]["step"]) == int(pre["step"][j]) + 1
+        if mode == "test_2":
+            assert int(E[0]["flags"]) == C6.FLAG_LANDED and rel_err(E[0]["s"], g["post_state"][j]) < 1e-6
+        else:
+            assert int(E[0]["flags"]) == C6.FLAG_TMAX
