@@ -216,7 +216,7 @@ def bench_6dof(torch, device, n=262144, ticks=50, reps=3, no_cpu=False):
     H6 = importlib.import_module("msc-thesis_b200.heli6dof")
     exc = np.load(os.path.join(ROOT, "tests", "golden", "h6_excitation.npz"))["excitation"]
     res = {"episodes": n, "ticks_per_launch": ticks, "dtype": "f64"}
-    for name, switch in (("phase1", 10 ** 6), ("phase2", 0)):
+    for name, switch in (("phase1", 10 ** 6), ("phase2", 1)):     # switch at tick 1: both agents learn from then on
         ep = dict(H6.env_params_train, step_switch=switch)
         loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device=device, init="batched",
                                    generator=torch.Generator().manual_seed(2), ticks_per_launch=ticks)

@@ -15,7 +15,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
     ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     exc = np.load("tests/golden/h6_excitation.npz")["excitation"]
-    for switch in (10 ** 6, 0):
+    for switch in (10 ** 6, 1):      # 1: the collective agent takes over (and learns) from tick 1 on
         ep = dict(H6.env_params_train, step_switch=switch)
         loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device="cuda", init="batched",
                                    ticks_per_launch=ticks)
@@ -34,7 +34,7 @@ def main():
         ms = ev0.elapsed_time(ev1)
         st = loop.stats()
         print("phase %d: n=%d ticks=%d  %.3f ms  -> %.3e env-steps/s  alive %.4f" %
-              (1 if switch else 2, n, ticks, ms, n * ticks / ms * 1e3, st["n_alive"] / st["n"]))
+              (1 if switch > 1 else 2, n, ticks, ms, n * ticks / ms * 1e3, st["n_alive"] / st["n"]))
 
 
 if __name__ == "__main__":
