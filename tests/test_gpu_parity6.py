@@ -345,3 +345,55 @@ def test_free_running_test_episodes_end_like_the_reference(mode_id, mode):
         assert abs(float(df["z"].iloc[-1]) - float(pre["state"][j][11])) < 1e-6
         st = loop.stats()
         assert st["n_landed"] == 1 and st["n_alive"] == 0
+
+
+@pytest.mark.parametrize("n,split,tiled", [(1, True, True), (31, True, True), (33, True, True), (129, True, False),
+                                           (95, False, False), (250, False, True)])
+def test_ragged_batch_sizes_and_guard_words(n, split, tiled):
+    """Batch sizes that do not fill a tile (32 episodes), a warp or a block, on every kernel path: guard words placed
+    directly before and after every buffer h6_closed_loop touches stay intact (compute-sanitizer is closed on this
+    pool), and episode 0 equals the same episode of a batch of one."""
+    H6 = pkg()
+    ep = dict(H6.env_params_train, step_switch=8)
+
+    def make(m):
+        lp = H6.make_closed_loop(m, "train", env_params=ep, excitation=H.excitation(), device=DEV, init="batched",
+                                 generator=torch.Generator().manual_seed(21), ticks_per_launch=6)
+        lp.split, lp.tiled = split, tiled
+        return lp
+
+    loop, one = make(n), make(1)
+    for src, dst in ((loop.agent_col.net, one.agent_col.net), (loop.agent_lon.net, one.agent_lon.net)):
+        dst.copy_(src[:, :1])
+    pad, canary = 64, 1234.5
+    guarded = []
+
+    def guard(owner, attr, key=None):
+        t = getattr(owner, attr) if key is None else getattr(owner, attr)[key]
+        fill = canary if t.dtype == torch.float64 else 12345
+        flat = torch.full((t.numel() + 2 * pad,), fill, dtype=t.dtype, device=t.device)
+        flat[pad:pad + t.numel()] = t.reshape(-1)
+        view = flat[pad:pad + t.numel()].view(t.shape)
+        if key is None:
+            setattr(owner, attr, view)
+        else:
+            getattr(owner, attr)[key] = view
+        guarded.append((flat, fill))
+
+    for owner, attr in ((loop.env, "state"), (loop.env, "_t"), (loop.env, "P_out"), (loop.env, "P_available"),
+                        (loop.env, "step_count"), (loop.env, "flags"), (loop.env, "term_step"), (loop.rls, "_W"),
+                        (loop.rls, "_cov"), (loop.rls, "x"), (loop.rls, "u"), (loop.rls, "_skip"), (loop.agent_col, "net"),
+                        (loop.agent_lon, "net"), (loop, "acc"), (loop, "ref3"), (loop, "pid"), (loop, "lr"), (loop, "work"),
+                        (loop, "update_col"), (loop, "excitation_phase"), (loop.gen, "gen"), (loop.gen, "task_code")):
+        guard(owner, attr)
+    for key in list(loop._tiles):
+        guard(loop, "_tiles", key)
+    loop.run(20)
+    one.run(20)
+    for flat, fill in guarded:
+        assert bool((flat[:pad] == fill).all()) and bool((flat[-pad:] == fill).all())
+    a, b = H.loop_state(loop), H.loop_state(one)
+    for k in H.REAL_KEYS:
+        assert H.rel_err(a[k][0], b[k][0]) < 1e-12, k
+    st = loop.stats()
+    assert st["n"] == n and st["sum_ticks"] == 20.0 * n and int(a["update_col"].sum()) == n
