@@ -87,6 +87,40 @@ int main(void) {
     assert len(L.H6_BATCH_FIELDS) == 25 and L.H6Batch.tile.offset == L.H6Batch.work.offset + 24
 
 
+def test_6dof_abi_rejects_bad_arguments_before_touching_the_gpu():
+    """Error convention of include/heli6dof.h: negative status + h3_last_error() text, never an exception or a launch,
+    for null buffers, inconsistent sizes and unsupported configurations."""
+    lib = h3.lib()
+    cfg, b = L.H6Config(), L.H6Batch()
+    b.n, b.ld = 8, 8
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == -1
+    assert b"null field" in lib.h3_last_error()
+    assert lib.h6_closed_loop(None, ctypes.byref(b), None, 0, 10, None, None, None, None) == -1
+    assert lib.h6_trim(None, None, None, 1.0, None, None, None, None, 4, 4, None) == -1
+    assert lib.h6_env_derivatives(None, None, None, None, 0, 0.01, None, 4, 4, None) == -1
+    assert lib.h6_env_step(ctypes.byref(cfg), ctypes.byref(b), None, None, 0, 5, None, 0, 0, None) == -1
+    assert lib.h6_rls_update(ctypes.byref(cfg), ctypes.byref(b), None, None, None, None) == -1
+    assert lib.h6_tile_pack(None, None, 4, 8, 8, 1, None) == -1
+    fake = ctypes.c_void_p(256)                     # non-null placeholder: validation must stop before any access
+    for k in L.H6_BATCH_FIELDS:
+        if k not in ("work",):
+            setattr(b, k, fake)
+    b.ld = 4                                        # ld < n
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == -1
+    b.ld, b.tile = 8, 16                            # only 0 or 32
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == -1
+    b.tile = 0
+    cfg.col.n_hidden, cfg.lon.n_hidden = 6, 10      # compiled for 10 / 10
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == -2
+    assert b"n_hidden" in lib.h3_last_error()
+    cfg.col.n_hidden = cfg.lon.n_hidden = 10
+    cfg.col.tracked_state = 15                      # outside the 15-state observation
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == -2
+    # n == 0 / n_ticks == 0: nothing to do, no launch
+    cfg.col.tracked_state, b.n = 11, 0
+    assert lib.h6_closed_loop(ctypes.byref(cfg), ctypes.byref(b), None, 0, 10, None, None, None, None) == 0
+
+
 def test_6dof_host_objects_fail_loudly_without_gpu():
     """The 6-DOF classes can be constructed on the CPU (plumbing), every compute call raises: no fallback."""
     import importlib
