@@ -706,10 +706,53 @@ def make_closed_loop(n_envs, mode="train", env_params=None, ac_params=None, rls_
                           excitation=excitation, load_agents=load_agents, ticks_per_launch=ticks_per_launch)
 
 
+class Logger:
+    """What util.Logger holds after finalize() (util.py:6-106) for ONE episode of a batch: `state_history` (DataFrame
+    with the columns of log_states) and `weight_history` = {'col' | 'lon': {'ci', 'co', 'ai', 'ao', 'dsda', 'dsds'}}
+    (DataFrames indexed by env.t, one row per log_weights call) -- the inputs of plotting.plot_stats,
+    plot_neural_network_weights and plot_rls_weights."""
+
+    def __init__(self, params):
+        self.training_parameters = params
+        self.state_history = None
+        self.weight_history = {a: {k: [] for k in ("ci", "co", "ai", "ao", "dsda", "dsds")} for a in ("col", "lon")}
+        self._t = []
+        self.finalized = False
+
+    def log_weights(self, t, agents, rls_estimator, episode=0):
+        """util.py:68-80 for one episode of the batch."""
+        self._t.append(float(t))
+        for agent in agents:
+            nh, w = agent.n_hidden, agent.net[:, episode].detach().cpu().numpy()
+            h = self.weight_history[agent.control_channel_str]
+            h["ai"].append(w[0:2 * nh].copy()); h["ao"].append(w[2 * nh:3 * nh].copy())
+            h["ci"].append(w[3 * nh:5 * nh].copy()); h["co"].append(w[5 * nh:7 * nh].copy())
+            Fm, Gm = agent.get_transition_matrices(rls_estimator)
+            h["dsds"].append(Fm[:, :, episode].detach().cpu().numpy().ravel().copy())
+            h["dsda"].append(Gm[:, :, episode].detach().cpu().numpy().ravel().copy())
+
+    def finalize(self, state_history):
+        import pandas as pd
+        if self.finalized:
+            raise ValueError("Attempting to call logger.finalize(), but log is already finalized. ")      # util.py:84-85
+        self.state_history = state_history
+        self.weight_history = {a: {k: pd.DataFrame(data=v, index=self._t) for k, v in h.items()}
+                               for a, h in self.weight_history.items()}
+        self.finalized = True
+
+    def save(self, path):
+        import pickle
+        with open(path, 'wb') as f:
+            pickle.dump(self, f)
+
+
 def train(mode, env_params, ac_params, rls_params, pid_params, excitation, n_envs=1, seed=0, device=None,
-          load_agents=False, agents=None, record=0):
+          load_agents=False, agents=None, record=0, return_logs=False, save_weights=False, weight_save_interval=10,
+          log_episode=0):
     """train.train (train.py:20-264) for N episodes: runs the whole episode in fused launches and returns
-    (ClosedLoop6DOF, success (N,) bool, score (N,), log or None)."""
+    (ClosedLoop6DOF, success (N,) bool, score (N,), log or None).  return_logs=True: the last element is a Logger for
+    episode `log_episode` (state history; with save_weights the network / RLS histories every weight_save_interval
+    ticks, train.py:193-195 -- the loop then runs in launches of that many ticks)."""
     loop = make_closed_loop(n_envs, mode, env_params, ac_params, rls_params, pid_params, excitation=excitation,
                             load_agents=load_agents, device=device, seed=seed)
     if agents is not None:                                                # train.py:68-72
@@ -717,9 +760,32 @@ def train(mode, env_params, ac_params, rls_params, pid_params, excitation, n_env
         loop.rls._W.copy_(agents["rls_W"]); loop.rls._cov.copy_(agents["rls_cov"])
         loop.rls.x.copy_(agents["rls_x"]); loop.rls.u.copy_(agents["rls_u"]); loop.rls._skip.copy_(agents["rls_skip"])
         loop.rls.assume_symmetric = bool(torch.equal(loop.rls.cov, loop.rls.cov.transpose(0, 1)))
-    log = loop.run(env_params['n_steps'] + 2, record=record)              # the loop ends by itself at t > t_max
+    total = env_params['n_steps'] + 2                                     # the loop ends by itself at t > t_max
+    if not return_logs:
+        log = loop.run(total, record=record)
+        ok, score = loop.scores()
+        return loop, ok, score, log
+    rec = max(int(record), log_episode + 1)
+    logger = Logger(params=ac_params)
+    if save_weights:
+        # log_weights fires after the updates of ticks 0, k, 2k, ... (train.py:194): launches of 1, k, k, ... ticks
+        logs, done, chunk = [], 0, 1
+        while done < total and bool((loop.env.flags[log_episode] == 0).item()):
+            m = min(chunk, total - done)
+            logs.append(loop.run(m, record=rec))
+            done += m
+            chunk = int(weight_save_interval)
+            on_grid = (done - 1) % int(weight_save_interval) == 0     # `step % weight_save_interval == 0`, train.py:194
+            if on_grid and (bool((loop.env.flags[log_episode] == 0).item()) or int(loop.env.term_step[log_episode]) == done - 1):
+                logger.log_weights(float(loop.env._t[log_episode]), [loop.agent_col, loop.agent_lon], loop.rls, log_episode)
+        if done < total:
+            logs.append(loop.run(total - done, record=rec))               # the other episodes of the batch
+        log = torch.cat(logs)
+    else:
+        log = loop.run(total, record=rec)
+    logger.finalize(loop.to_dataframe(log, episode=log_episode))
     ok, score = loop.scores()
-    return loop, ok, score, log
+    return loop, ok, score, logger
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -397,3 +397,26 @@ def test_ragged_batch_sizes_and_guard_words(n, split, tiled):
         assert H.rel_err(a[k][0], b[k][0]) < 1e-12, k
     st = loop.stats()
     assert st["n"] == n and st["sum_ticks"] == 20.0 * n and int(a["update_col"].sum()) == n
+
+
+def test_train_returns_a_logger_like_the_reference():
+    """train(return_logs=True, save_weights=True): state history with Logger.log_states' columns and weight histories
+    logged after ticks 0, 10, 20, ... (train.py:193-195), equal to the weights of an unlogged run at those ticks."""
+    H6 = pkg()
+    ep = dict(H6.env_params_train, step_switch=20, n_steps=58, t_max=120)
+    loop, ok, score, logger = H6.train("train", ep, H6.ac_params_train, H6.rls_params, H6.pid_params, H.excitation(),
+                                       n_envs=3, seed=4, device=DEV, return_logs=True, save_weights=True,
+                                       weight_save_interval=10, log_episode=1)
+    assert logger.finalized and len(logger.state_history) == 60 and bool(ok.all())
+    wh = logger.weight_history
+    assert set(wh) == {"col", "lon"} and set(wh["lon"]) == {"ci", "co", "ai", "ao", "dsda", "dsds"}
+    assert wh["lon"]["ai"].shape == (6, 20) and wh["col"]["co"].shape == (6, 20) and wh["lon"]["dsds"].shape == (6, 4)
+    assert np.allclose(wh["lon"]["ai"].index.to_numpy(), [0.01, 0.11, 0.21, 0.31, 0.41, 0.51], atol=1e-12)
+    plain = H6.make_closed_loop(3, "train", env_params=ep, excitation=H.excitation(), device=DEV, seed=4)
+    plain.run(31)                                                        # state after the updates of tick 30
+    nh = 10
+    assert H.rel_err(wh["lon"]["ai"].iloc[3].to_numpy(), plain.agent_lon.net[:2 * nh, 1].cpu().numpy()) < 1e-12
+    assert H.rel_err(wh["col"]["ci"].iloc[3].to_numpy(), plain.agent_col.net[3 * nh:5 * nh, 1].cpu().numpy()) < 1e-12
+    Fm, Gm = plain.agent_lon.get_transition_matrices(plain.rls)
+    assert H.rel_err(wh["lon"]["dsds"].iloc[3].to_numpy(), Fm[:, :, 1].cpu().numpy().ravel(), floor=1e-12) < 1e-9
+    assert H.rel_err(wh["lon"]["dsda"].iloc[3].to_numpy(), Gm[:, :, 1].cpu().numpy().ravel(), floor=1e-12) < 1e-9
