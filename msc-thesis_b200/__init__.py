@@ -22,6 +22,7 @@ from .heli_models import Helicopter3DOF
 from .host_batch import HostBatchPipeline, loop_result_tensors, loop_state_tensors
 from .model import RecursiveLeastSquares
 from . import sweep
+from . import heli6dof
 
 __all__ = ["Helicopter3DOF", "CollectivePID3DOF", "RecursiveLeastSquares", "DHPAgent", "DHPActor", "DHPCritic",
            "ClosedLoop3DOF", "TRAJ_COLUMNS", "sinusoid_ref_table", "excitation_signal", "load_excitation",

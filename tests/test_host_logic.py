@@ -313,7 +313,15 @@ def test_sweep_grid_and_compat_modules():
                           ("PID", "CollectivePID3DOF")):
             sys.modules.pop(mod, None)
             assert getattr(importlib.import_module(mod), name) is getattr(h3, name)
+        H6 = h3.heli6dof
+        for mod, names in (("heli_models", ("Helicopter6DOF",)), ("PID", ("CollectivePID6DOF", "LatPedPID")),
+                           ("util", ("Logger", "RefGenerator", "envelope_limits_reached")),
+                           ("params", ("ac_params_train", "env_params_test2", "pid_params", "rls_params")),
+                           ("train", ("train", "mp_train"))):
+            sys.modules.pop(mod, None)
+            for name in names:
+                assert getattr(importlib.import_module(mod), name) is getattr(H6, name)
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
-        for mod in ("agents", "model", "heli_models", "PID"):
+        for mod in ("agents", "model", "heli_models", "PID", "util", "params", "train"):
             sys.modules.pop(mod, None)
