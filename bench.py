@@ -299,6 +299,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1 and os.environ.get("H3_NUMA_BIND", "1") != "0":
+        # one process per GPU: keep this rank (and the pinned host buffers of the e2e leg) on the GPU's NUMA node
+        numa_cpus = h3.distributed.bind_to_gpu_numa_node(local)
     if world > 1:
         if "H3_KEEP_NCCL_DEBUG" not in os.environ:
             os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout; stdout carries ONE JSON line
@@ -405,6 +409,7 @@ def main():
             "phase1_ms_per_launch_rank0": p1_ms, "alive_fraction_end": alive_frac,
             "env_steps_timed": env_steps, "stats": stats_all,
             "roofline": roofline, "clocks": clocks, "gpu_launches": K,
+            "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
         }
 
     # ---- e2e: same metric through the public API from HOST buffers (H2D + launch + D2H every step) ----
