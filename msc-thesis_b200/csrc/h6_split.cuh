@@ -1,5 +1,5 @@
-// Split form of the 6-DOF closed loop (train.py:109-224): per tick one launch of each of two kernels that are
-// shaped for opposite bounds, instead of one register allocation for both.
+// Split form of the 6-DOF closed loop (train.py:109-224): per tick one launch of each of three kernels that are
+// shaped for opposite bounds, instead of one register allocation for all of the tick.
 //
 //   agents_kernel (one thread per (episode, agent), 16 warps per SM): the IDHP updates of the previous tick.
 //   sim_kernel   ("S", one thread per episode, 168 registers): PIDs, reference generator, actor forward passes and
@@ -11,7 +11,9 @@
 //                one-thread-per-episode kernel is (profiles/r01_h6_summary.txt).
 //
 // What L needs from S (regressor X, target Y, the agents' augmented states and reward slopes, flags) travels
-// through H6Batch.work, `[H6_WORK_ROWS][ld]` in global memory (44 of the tick's ~1100 words).
+// through H6Batch.work, `[H6_WORK_ROWS][ld]` in global memory (44 of the tick's ~1100 words).  W, the covariance and
+// the networks are normally tiled (H6Batch.tile = 32: compile-time row stride, accesses are base + immediate).
+// lazy_w_kernel is the optional catch-up of the W columns nothing reads inside the loop (H6Batch.hist).
 // Included by h6_api.cu after GVec / Net / LoopParams / NS / NR / NH.
 #pragma once
 
