@@ -535,3 +535,39 @@ def test_wide_kernel_option_matches_the_default_kernel(h3, monkeypatch):
     assert torch.equal(outs[0][5], outs[1][5])
     assert outs[0][6]["sum_ticks"] == outs[1][6]["sum_ticks"] and outs[0][6]["n_alive"] == outs[1][6]["n_alive"]
     assert abs(outs[0][6]["sum_r_lon"] - outs[1][6]["sum_r_lon"]) <= 1e-9 * abs(outs[0][6]["sum_r_lon"])
+
+
+def test_host_batch_pipeline_compact_and_full_formats_agree(h3):
+    """HostBatchPipeline (the e2e path): a host-resident batch streamed chunk by chunk gives the results of running the
+    same episodes device-resident, with the compact host format (covariance upper triangle, no tau = 1 target critic)
+    and with the full one."""
+    import bench
+    dev = torch.device("cuda", 0)
+
+    def make(n):
+        lp = bench.make_workload(h3, torch, n, "f64", dev, seed=3, store=0, ticks=30)
+        lp.switch_step = 45
+        return lp
+
+    outs = []
+    for compact in (True, False):
+        pipe = h3.HostBatchPipeline(make, 512, n_slots=2, compact=compact)
+        pipe.slots[0].run(30)
+        pipe.k0, pipe.t0 = pipe.slots[0].k, pipe.slots[0].env.t
+        chunks = pipe.host_chunks_from(pipe.slots[0], 3)
+        res = pipe.result_buffers(3)
+        pipe.run(chunks, res, 30)
+        torch.cuda.synchronize()
+        outs.append((sum(t.numel() * t.element_size() for t in chunks[0]), [[t.clone() for t in r] for r in res]))
+    assert outs[0][0] < 0.85 * outs[1][0]                       # 17 % fewer bytes per chunk
+    ref = make(512)
+    ref.run(30)
+    ref.run(30)
+    want = [t.cpu() for t in h3.host_batch.loop_result_tensors(ref)]
+    for nbytes, res in outs:
+        for r in res:
+            for got, w in zip(r, want):
+                if got.dtype.is_floating_point:
+                    assert (got - w).abs().max().item() <= 1e-9 * max(w.abs().max().item(), 1e-30)
+                else:
+                    assert torch.equal(got, w)
