@@ -4,4 +4,4 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from msc_thesis_b200.heli6dof import mp_train, train  # noqa: E402,F401
+from msc_thesis_b200.heli6dof import mp_test, mp_train, train  # noqa: E402,F401

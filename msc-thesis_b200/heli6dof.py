@@ -788,6 +788,17 @@ def train(mode, env_params, ac_params, rls_params, pid_params, excitation, n_env
     return loop, ok, score, logger
 
 
+def mp_test(mode, env_params, ac_params, agents, num_seeds=100, device=None):
+    """main.mp_test (main.py:92-103): the test scenario `mode` ('test_1' / 'test_2') for num_seeds episodes that all
+    start from the saved agents / RLS estimator `agents` (train.py:68-72; a dict with 'col', 'lon' (110, 1|N) network
+    blocks and 'rls_W', 'rls_cov', 'rls_x', 'rls_u', 'rls_skip').  Returns (successful_trials, scores) as the reference
+    gathers them, plus the ClosedLoop6DOF for further inspection."""
+    loop, ok, score, _ = train(mode, env_params, ac_params, rls_params, pid_params, None, n_envs=num_seeds, seed=0,
+                               device=device, load_agents=True, agents=agents)
+    ok, score = ok.cpu().numpy(), score.cpu().numpy()
+    return [int(v) for v in ok], [float(sc) if o else 0.0 for o, sc in zip(ok, score)], loop
+
+
 # ------------------------------------------------------------------------------------------------------------
 # main.mp_train (main.py:48-89): grid of lon hyper-parameters x seeds; every (setting, seed) pair is one episode
 # ------------------------------------------------------------------------------------------------------------

@@ -420,3 +420,22 @@ def test_train_returns_a_logger_like_the_reference():
     Fm, Gm = plain.agent_lon.get_transition_matrices(plain.rls)
     assert H.rel_err(wh["lon"]["dsds"].iloc[3].to_numpy(), Fm[:, :, 1].cpu().numpy().ravel(), floor=1e-12) < 1e-9
     assert H.rel_err(wh["lon"]["dsda"].iloc[3].to_numpy(), Gm[:, :, 1].cpu().numpy().ravel(), floor=1e-12) < 1e-9
+
+
+def test_mp_test_runs_the_oei_landing_for_every_seed():
+    """main.mp_test equivalent: test_2 (one engine inoperative landing) for 5 episodes that load the trained agents and
+    RLS estimator of the fixture run; every one touches down on the reference's tick."""
+    H6 = pkg()
+    g = H.load("h6_ticks.npz")
+    info = g["info"]
+    pre = {k[4:]: v for k, v in g.items() if k.startswith("pre_")}
+    i0 = int(np.nonzero((info[:, 7] == 2) & (pre["step"] == 0))[0][0])
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device=DEV)
+    net = lambda name: T(np.concatenate([pre[name + "_" + k][i0].reshape(-1) for k in H.NET_KEYS]).reshape(-1, 1))
+    agents = {"col": net("col"), "lon": net("lon"), "rls_W": T(pre["rls_W"][i0].reshape(-1, 1)),
+              "rls_cov": T(pre["rls_cov"][i0].reshape(-1, 1)), "rls_x": T(pre["rls_x"][i0].reshape(-1, 1)),
+              "rls_u": T(pre["rls_u"][i0].reshape(-1, 1)),
+              "rls_skip": torch.full((1,), int(pre["rls_skip"][i0]), dtype=torch.int32, device=DEV)}
+    ok, scores, loop = H6.mp_test("test_2", H6.env_params_test2, H6.ac_params_test, agents, num_seeds=5, device=DEV)
+    assert ok == [1] * 5 and len(scores) == 5
+    assert (loop.env.flags == 8).all() and (loop.env.term_step == 1751).all()
