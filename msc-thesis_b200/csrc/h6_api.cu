@@ -5,7 +5,9 @@
 // 17-warps-per-32-episodes RLS kernel per tick, default when H6Batch.work is given) and the fused kernel below (one
 // thread per episode streams its own W / covariance / networks from HBM every tick; latency-bound, kept for callers
 // without a work buffer).  DESIGN.md section 9.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "h3_tick.cuh"
@@ -684,6 +686,27 @@ __global__ void __launch_bounds__(256) tile_pack_kernel(const double* __restrict
     }
 }
 
+// H6Batch of the episodes [off, off + cnt): every pointer advanced by `off` columns (off is a multiple of 32)
+static H6Batch sub_batch(const H6Batch& src, int64_t off, int64_t cnt) {
+    H6Batch b = src;
+    const int64_t tiles = off / 32;
+    auto adv = [&](double*& p, int rows) { if (p) p += b.tile ? tiles * (int64_t)rows * 32 : off; };
+    double** plain[] = {&b.state, &b.t, &b.P_out, &b.P_avail, &b.ref, &b.pid, &b.gen, &b.lr, &b.rls_x, &b.rls_u, &b.acc, &b.work};
+    for (double** p : plain) if (*p) *p += off;
+    b.trim_act += off;
+    b.phi_trim += off;
+    int32_t** ints[] = {&b.task, &b.rls_skip, &b.step, &b.flags, &b.term_step, &b.update_col, &b.excitation_phase};
+    for (int32_t** p : ints) if (*p) *p += off;
+    adv(b.rls_W, NR * NS); adv(b.rls_cov, NR * NR); adv(b.col_net, 11 * NH); adv(b.lon_net, 11 * NH);
+    b.n = cnt;
+    b.hist = nullptr; b.hist_len = 0;
+    return b;
+}
+
+#ifndef H6_MIX_MIN
+#define H6_MIX_MIN 16384      // batches at least this large run the overlapped (mixed-role) launches
+#endif
+
 static bool check_agents(const H6Config* cfg, const char* who) {
     for (const H3AgentHyper* h : {&cfg->col, &cfg->lon}) {
         if (h->n_hidden != NH) { set_error("%s: the 6-DOF kernels are compiled for n_hidden = %d, got %d", who, NH, h->n_hidden); return false; }
@@ -817,6 +840,35 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
             // kernel fills the SMs' registers and the other stream's blocks only run in its tail.)
             const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;
             const unsigned gs = grid_for(b->n), gl = (unsigned)((b->n + 31) / 32);
+            const bool lazy_req = b->hist != nullptr && b->hist_len > 0;
+            const char* mix_env = getenv("H6_MIX");                    // H6_MIX=1 opts in (not the default until measured)
+            const bool mix_enabled = mix_env != nullptr && mix_env[0] == '1';
+            if (mix_enabled && traj == nullptr && !lazy_req && b->n >= H6_MIX_MIN) {
+                // overlapped launches: halves A = [0, nA), B = [nA, n); every launch runs role S on one half and role L
+                // on the other (mixed_kernel), alternating; 2 launches per tick
+                const int64_t nA = ((b->n / 2 + 127) / 128) * 128, nB = b->n - nA;
+                LoopParams PA = P, PB = P;
+                PA.b = sub_batch(*b, 0, nA);
+                PB.b = sub_batch(*b, nA, nB);
+                auto mix = [&](const LoopParams& S, int it_s, int mode_s, bool with_s, const H6Batch& Lb, bool with_l) {
+                    const int64_t n_s = with_s ? (S.b.n + MIX_BLOCK - 1) / MIX_BLOCK : 0, n_l = with_l ? (Lb.n + 31) / 32 : 0;
+                    const int64_t groups = std::max<int64_t>(n_s, (n_l + 3) / 4);
+                    if (groups == 0) return;
+                    const unsigned g = (unsigned)(5 * groups);
+                    if (sym && til) mixed_kernel<true, true><<<g, MIX_BLOCK, 0, st>>>(S, it_s, mode_s, n_s, Lb, cfg->rls_gamma, n_l);
+                    else if (sym) mixed_kernel<true, false><<<g, MIX_BLOCK, 0, st>>>(S, it_s, mode_s, n_s, Lb, cfg->rls_gamma, n_l);
+                    else if (til) mixed_kernel<false, true><<<g, MIX_BLOCK, 0, st>>>(S, it_s, mode_s, n_s, Lb, cfg->rls_gamma, n_l);
+                    else mixed_kernel<false, false><<<g, MIX_BLOCK, 0, st>>>(S, it_s, mode_s, n_s, Lb, cfg->rls_gamma, n_l);
+                };
+                mix(PA, 0, 2, true, PB.b, false);                                   // S(A, 0)
+                for (int it = 0; it < n_ticks; ++it) {
+                    mix(PB, it, (it > 0 ? 1 : 0) | 2, true, PA.b, true);            // S(B, it) [+ agents(B, it-1)] || L(A, it)
+                    const bool last = it == n_ticks - 1;
+                    mix(PA, it + 1, last ? (1 | 4) : (1 | 2), true, PB.b, true);    // agents(A, it) + S(A, it+1) || L(B, it)
+                }
+                mix(PB, n_ticks, 1 | 4, true, PA.b, false);                         // agents(B, last)
+                if (sym) { if (til) mirror_kernel<true><<<gl, LEARN_BLOCK, 0, st>>>(*b); else mirror_kernel<false><<<gl, LEARN_BLOCK, 0, st>>>(*b); }
+            } else {
             const dim3 ga(gs, 2);
             // columns of W the agents read (agents.py:130-140); with a history buffer only these are updated every tick
             const unsigned live = (1u << cfg->col.ac_state) | (1u << cfg->col.tracked_state) | (1u << cfg->lon.ac_state) |
@@ -848,6 +900,7 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
                     if (til) lazy_w_kernel<true><<<gl, 32 * NS, sm, st>>>(*b, live, slot + 1);
                     else lazy_w_kernel<false><<<gl, 32 * NS, sm, st>>>(*b, live, slot + 1);
                 }
+            }
             }
         } else {
             const bool sym = cfg->rls_symmetric != 0, til = b->tile != 0;

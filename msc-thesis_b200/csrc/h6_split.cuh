@@ -427,6 +427,143 @@ __global__ void __launch_bounds__(32 * NS, 2) lazy_w_kernel(H6Batch b, unsigned 
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Overlapped form: ONE launch holds blocks of two roles that work on the two halves of the batch --
+//   role S (agents of the previous tick + simulate, one thread per episode, 128 episodes per block) on half A,
+//   role L (the RLS update, 4 warps per 32 episodes, every warp a few rows with 17 loads in flight) on half B --
+// so the FP64 / latency-bound work of one half and the HBM-bound work of the other share every SM (the block
+// scheduler interleaves them: 1 S block per 4 L blocks in launch order).  The next launch swaps the halves; launch
+// boundaries carry the dependencies (L needs S's hand-over rows, the agents need L's W).
+// ----------------------------------------------------------------------------------------------
+constexpr int MIX_BLOCK = 128, MIX_LWARPS = MIX_BLOCK / 32;
+
+template <bool SYM, bool TILED>
+H3_DEV void learn_role(const H6Batch& b, double gamma, int64_t blk, double* smem) {
+    double (*Xs)[32] = reinterpret_cast<double (*)[32]>(smem);
+    double (*cXs)[32] = reinterpret_cast<double (*)[32]>(smem + NR * 32);
+    double (*Xcs)[32] = reinterpret_cast<double (*)[32]>(smem + 2 * NR * 32);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t e = blk * 32 + lane, ld = b.ld;
+    const bool in = e < b.n;
+    const int64_t ec = in ? e : 0;
+    const int wf = in ? (int)b.work[WR_FLAGS * ld + e] : 0;
+    const bool on = (wf & (WF_ACTIVE | WF_RLS)) == (WF_ACTIVE | WF_RLS);
+    const double* __restrict__ wk = b.work + ec;
+    const int64_t lw = TILED ? 32 : ld;
+    double* __restrict__ cov = b.rls_cov + tile_off(b, ec, NR * NR);
+    double* __restrict__ W = b.rls_W + tile_off(b, ec, NR * NS);
+    for (int r = w; r < NR; r += MIX_LWARPS) Xs[r][lane] = on ? wk[(WR_X + r) * ld] : 0.0;
+    __syncthreads();
+    double cxr[(NR + MIX_LWARPS - 1) / MIX_LWARPS];
+#pragma unroll
+    for (int q = 0; q < (NR + MIX_LWARPS - 1) / MIX_LWARPS; ++q) {
+        const int r = w + q * MIX_LWARPS;
+        double cx = 0, xc = 0;
+        if (r < NR && on) {
+            double c[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) c[j] = (SYM && j < r) ? cov[(int64_t)(j * NR + r) * lw] : cov[(int64_t)(r * NR + j) * lw];
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) { if (j & 1) a1 += c[j] * Xs[j][lane]; else a0 += c[j] * Xs[j][lane]; }   // model.py:53
+            cx = a0 + a1;
+            if (!SYM) {
+#pragma unroll
+                for (int i = 0; i < NR; ++i) c[i] = cov[(int64_t)(i * NR + r) * lw];
+                a0 = 0; a1 = 0;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) { if (i & 1) a1 += Xs[i][lane] * c[i]; else a0 += Xs[i][lane] * c[i]; }   // :54
+                xc = a0 + a1;
+            }
+        }
+        cxr[q] = cx;
+        if (r < NR) { cXs[r][lane] = cx; if (!SYM) Xcs[r][lane] = xc; }
+    }
+    __syncthreads();
+    if (!on) return;
+    double d = gamma;                                                           // model.py:55
+#pragma unroll
+    for (int i = 0; i < NR; ++i) d += (SYM ? cXs[i][lane] : Xcs[i][lane]) * Xs[i][lane];
+    const double inv_d = 1.0 / d, inv_gamma = 1.0 / gamma;
+#pragma unroll
+    for (int q = 0; q < (NR + MIX_LWARPS - 1) / MIX_LWARPS; ++q) {
+        const int r = w + q * MIX_LWARPS;
+        if (r >= NR) break;
+        {                                                                       // model.py:59, row r
+            const double gr = cxr[q] * inv_d;
+            double c[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                if (!SYM || j >= r) c[j] = cov[(int64_t)(r * NR + j) * lw];
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                if (!SYM || j >= r) cov[(int64_t)(r * NR + j) * lw] = (c[j] - gr * (SYM ? cXs[j][lane] : Xcs[j][lane])) * inv_gamma;
+        }
+        if (r < NS) {                                                           // model.py:49-50, :58, column r of W
+            double wv[NR], ya = wk[(WR_Y + r) * ld], yb = 0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) wv[i] = W[(int64_t)(i * NS + r) * lw];
+#pragma unroll
+            for (int i = 0; i < NR; i += 2) ya -= Xs[i][lane] * wv[i];
+#pragma unroll
+            for (int i = 1; i < NR; i += 2) yb += Xs[i][lane] * wv[i];
+            const double err = (ya - yb) * inv_d;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) W[(int64_t)(i * NS + r) * lw] = wv[i] + cXs[i][lane] * err;
+        }
+    }
+}
+
+// mode_s bit 0: apply the pending agent updates of half A's previous tick; bit 1: simulate one tick; bit 2: the
+// episode's updates of this call end here (refresh tau == 1 target critics).  n_s / n_l: blocks of each role.
+template <bool SYM, bool TILED>
+__global__ void __launch_bounds__(MIX_BLOCK, H6_SIM_MINB) mixed_kernel(const __grid_constant__ LoopParams PS, int it_s, int mode_s,
+                                                                       int64_t n_s, H6Batch bl, double gamma, int64_t n_l) {
+    __shared__ double smem[30 * MIX_BLOCK];                 // RK4 arrays (role S) / X, cov.X rows (role L)
+    const int64_t q = blockIdx.x / 5;
+    const int r5 = blockIdx.x % 5;
+    if (r5 != 0) {                                          // role L: 4 of every 5 blocks
+        const int64_t blk = 4 * q + (r5 - 1);
+        if (blk < n_l) learn_role<SYM, TILED>(bl, gamma, blk, smem);
+        return;
+    }
+    if (q >= n_s) return;
+    const H6Config& C = PS.C;
+    const H6Batch& b = PS.b;
+    const int64_t e = q * MIX_BLOCK + threadIdx.x, ld = b.ld;
+    if (e >= b.n) return;
+    double* wk = b.work + e;
+    if (mode_s & 1) {
+        const int wf = (int)wk[WR_FLAGS * ld];
+        if (wf & WF_ACTIVE) {
+            const int64_t lw = TILED ? 32 : ld;
+            const double* __restrict__ W = b.rls_W + tile_off(b, e, NR * NS);
+            typename NetOf<TILED>::type ncol, nlon;
+            ncol.v.p = b.col_net + tile_off(b, e, 11 * NH); ncol.v.ld = lw;
+            nlon.v.p = b.lon_net + tile_off(b, e, 11 * NH); nlon.v.ld = lw;
+            const bool fast_lon = C.lon.tau == 1.0 && (C.target_synced & 2), fast_col = C.col.tau == 1.0 && (C.target_synced & 1);
+            if (wf & WF_COL) agent_learn(C.col, ncol, b.lr[e], b.lr[ld + e], W, lw, ld, wk + WR_COL * ld, fast_col);
+            agent_learn(C.lon, nlon, b.lr[2 * ld + e], b.lr[3 * ld + e], W, lw, ld, wk + WR_LON * ld, fast_lon);
+            if ((mode_s & 4) || b.flags[e] != 0) {
+                if (fast_lon) {
+#pragma unroll 4
+                    for (int r = 0; r < 4 * NH; ++r) nlon.v[7 * NH + r] = nlon.v[3 * NH + r];
+                }
+                if (fast_col && (wf & WF_COL)) {
+#pragma unroll 4
+                    for (int r = 0; r < 4 * NH; ++r) ncol.v[7 * NH + r] = ncol.v[3 * NH + r];
+                }
+            }
+        }
+    }
+    if (mode_s & 2) {
+        if (b.flags[e] != 0) { wk[WR_FLAGS * ld] = 0.0; return; }
+        tick_simulate<TILED>(PS, e, it_s, wk, smem + threadIdx.x);
+    } else {
+        wk[WR_FLAGS * ld] = 0.0;
+    }
+}
+
 // lower triangle := upper triangle (once per call, after the last tick): thread = (episode, row)
 template <bool TILED>
 __global__ void __launch_bounds__(LEARN_BLOCK) mirror_kernel(H6Batch b) {

@@ -439,3 +439,29 @@ def test_mp_test_runs_the_oei_landing_for_every_seed():
     ok, scores, loop = H6.mp_test("test_2", H6.env_params_test2, H6.ac_params_test, agents, num_seeds=5, device=DEV)
     assert ok == [1] * 5 and len(scores) == 5
     assert (loop.env.flags == 8).all() and (loop.env.term_step == 1751).all()
+
+
+def test_overlapped_launches_match_the_three_kernel_sequence(monkeypatch):
+    """Batches of at least 16,384 episodes run the mixed-role launches (role S on one half of the batch, role L on the
+    other, alternating); same results as the agents / simulate / learn kernel sequence, on a batch whose halves are
+    ragged, through the switch and with terminated episodes in both halves."""
+    H6 = pkg()
+    n = 16384 + 200
+    ep = dict(H6.env_params_train, step_switch=6)
+    outs = []
+    for mix in ("1", "0"):
+        monkeypatch.setenv("H6_MIX", mix)
+        lp = H6.make_closed_loop(n, "train", env_params=ep, excitation=H.excitation(), device=DEV, init="batched",
+                                 generator=torch.Generator().manual_seed(2), ticks_per_launch=7)
+        lp.env.state[7, 5] = 1.57            # beyond the pitch envelope: ends on its first tick (half A)
+        lp.env.state[6, n - 3] = -1.57       # roll envelope (half B)
+        lp.run(7)
+        lp.run(8)
+        outs.append((H.loop_state(lp), lp.stats()))
+    a, b = outs[0][0], outs[1][0]
+    for k in H.REAL_KEYS:
+        assert H.rel_err(a[k], b[k]) < 1e-9, k
+    for k in ("step", "flags", "term_step", "update_col", "task"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["flags"][5] == 4 and a["flags"][n - 3] == 4 and a["term_step"][5] == 0 and int((a["flags"] != 0).sum()) == 2
+    assert outs[0][1]["sum_ticks"] == outs[1][1]["sum_ticks"] == 15.0 * (n - 2) + 2
