@@ -210,7 +210,7 @@ def make_workload(h3, torch, n, precision, device, seed, store, ticks):
     return loop
 
 
-def bench_6dof(torch, device, n=262144, ticks=50, reps=3, no_cpu=False):
+def bench_6dof(torch, device, n=262144, ticks=100, reps=2, no_cpu=False):
     """Device-resident throughput of the fused 6-DOF loop (include/heli6dof.h: h6_closed_loop), the HBM bytes it
     moves per env-step against the measured HBM peak, and the C oracle (oracle/heli6dof_ref.c) on one host core."""
     H6 = importlib.import_module("msc-thesis_b200.heli6dof")
