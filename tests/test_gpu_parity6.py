@@ -465,3 +465,29 @@ def test_overlapped_launches_match_the_three_kernel_sequence(monkeypatch):
         assert np.array_equal(a[k], b[k]), k
     assert a["flags"][5] == 4 and a["flags"][n - 3] == 4 and a["term_step"][5] == 0 and int((a["flags"] != 0).sum()) == 2
     assert outs[0][1]["sum_ticks"] == outs[1][1]["sum_ticks"] == 15.0 * (n - 2) + 2
+
+
+def test_free_mode_with_host_driven_events_equals_train_mode():
+    """H6_MODE_FREE: no scheduled events inside the kernel; the host applies train.py:113-123 between launches through the
+    objects (RefGenerator.set_task / get_ref, learning-rate decay, update_col) -- same episode as H6_MODE_TRAIN."""
+    H6 = pkg()
+    n, switch = 40, 15
+    ep = dict(H6.env_params_train, step_switch=switch)
+    make = lambda mode: H6.make_closed_loop(n, mode, env_params=ep, ac_params=H6.ac_params_train, excitation=H.excitation(),
+                                            device=DEV, init="batched", generator=torch.Generator().manual_seed(8),
+                                            ticks_per_launch=50)
+    auto, free = make("train"), make("free")
+    auto.run(switch + 12)
+    env, gen = free.env, free.gen
+    gen.set_task(task="train_lon", t=0, obs=env.state, velocity_filter_target=0)          # train.py:115-116
+    free.ref3.copy_(gen.get_ref(env.state, env.t)[[0, 7, 11]])
+    free.run(switch)
+    free.lr[2:4] *= 0.1                                                                   # :120-121
+    free.update_col.fill_(1)                                                              # :122
+    gen.set_task("train_col", t=env.t, obs=env.state, z_start=env.state[11])              # :123
+    free.run(12)
+    a, b = H.loop_state(auto), H.loop_state(free)
+    for k in H.REAL_KEYS:
+        assert H.rel_err(a[k], b[k]) < 1e-12, k
+    for k in ("step", "flags", "task", "update_col", "excitation_phase"):
+        assert np.array_equal(a[k], b[k]), k
