@@ -151,43 +151,73 @@ def test_random_batch_against_c_oracle():
 
 def test_object_api_tick_matches_fused_tick():
     """The statements of train.py:109-224 executed through the per-object methods (LatPedPID, CollectivePID6DOF,
-    DHPAgent6DOF, Helicopter6DOF.step, RefGenerator, RecursiveLeastSquares6) against the fused kernel."""
+    DHPAgent6DOF, Helicopter6DOF.step, RefGenerator, RecursiveLeastSquares6) against the fused kernel, through the switch
+    to the collective agent (learning-rate decay, set_task train_col, both agents updating)."""
     H6 = pkg()
     exc = H.excitation()
-    n, ticks = 64, 12
+    n, ticks, switch = 64, 14, 8
+    ep = dict(H6.env_params_train, step_switch=switch)
     gen = torch.Generator().manual_seed(3)
-    fused = H6.make_closed_loop(n, "train", excitation=exc, device=DEV, init="batched", generator=gen)
-    obj = H6.make_closed_loop(n, "train", excitation=exc, device=DEV, init="batched")
+    fused = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device=DEV, init="batched", generator=gen)
+    obj = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device=DEV, init="batched")
     obj.agent_col.net.copy_(fused.agent_col.net); obj.agent_lon.net.copy_(fused.agent_lon.net)
     fused.run(ticks)
     env, lat_pid, col_pid, rg, rls = obj.env, obj.lat_pid, obj.col_pid, obj.gen, obj.rls
-    a_col, a_lon = obj.agent_col, obj.agent_lon
-    trim = env.trim_controls.clone()
+    agent_col, agent_lon = obj.agent_col, obj.agent_lon
+    trim_actions = env.trim_controls.clone()
     observation, ref = env.state.clone(), env.state.clone()
     e4 = torch.as_tensor(exc, device=DEV)
+    update_col = False
+    rewards = torch.zeros(2, n, dtype=torch.float64, device=DEV)
+
+    def update_agent(agent, i):                                                           # train.py:100-106
+        rewards[i], dr_ds = agent.get_reward(next_observation, ref)
+        F, G = agent.get_transition_matrices(rls)
+        agent.update_networks(observation, next_observation, ref, next_ref, dr_ds, F, G)
+
     for step in range(ticks):
         lateral_cyclic, pedal = lat_pid(observation)
         if step == 0:
             rg.set_task(task="train_lon", t=0, obs=observation, velocity_filter_target=0)
             ref = rg.get_ref(observation, env.t)
-        actions = torch.stack([col_pid(observation), trim[1] - 0.5 + a_lon.get_action(observation, ref), lateral_cyclic, pedal])
+        elif step == switch:
+            agent_lon.learning_rate_actor *= 0.1
+            agent_lon.learning_rate_critic *= 0.1
+            update_col = True
+            rg.set_task("train_col", t=env.t, obs=observation, z_start=observation[11])
+        if step < switch:
+            actions = torch.stack([col_pid(observation), trim_actions[1] - 0.5 + agent_lon.get_action(observation, ref),
+                                   lateral_cyclic, pedal])
+        else:
+            actions = torch.stack([trim_actions[0] - 0.5 + agent_col.get_action(observation, ref),
+                                   trim_actions[1] - 0.5 + agent_lon.get_action(observation, ref), lateral_cyclic, pedal])
         actions = actions + e4[step].reshape(4, 1)
         actions = torch.clip(actions, 0, 1)
         next_observation, _, done = env.step(actions)
         rg.A = 10 if env.t < 20 else (15 if env.t < 40 else 20)
         next_ref = rg.get_ref(observation, env.t)
         rls.update(observation, actions[:2], next_observation)
-        reward, dr_ds = a_lon.get_reward(next_observation, ref)
-        F, G = a_lon.get_transition_matrices(rls)
-        a_lon.update_networks(observation, next_observation, ref, next_ref, dr_ds, F, G)
+        if update_col:
+            update_agent(agent_col, 0)
+        update_agent(agent_lon, 1)
         assert not H6.envelope_limits_reached(observation)[0].any() and not done.any()
         observation, ref = next_observation, next_ref
     assert H.rel_err(env.state.cpu().numpy(), fused.env.state.cpu().numpy()) < 1e-9
     assert H.rel_err(rls.W.cpu().numpy(), fused.rls.W.cpu().numpy()) < 1e-9
     assert H.rel_err(rls.cov.cpu().numpy(), fused.rls.cov.cpu().numpy()) < 1e-9
-    assert H.rel_err(a_lon.net.cpu().numpy(), fused.agent_lon.net.cpu().numpy()) < 1e-9
+    assert H.rel_err(agent_lon.net.cpu().numpy(), fused.agent_lon.net.cpu().numpy()) < 1e-9
+    assert H.rel_err(agent_col.net.cpu().numpy(), fused.agent_col.net.cpu().numpy()) < 1e-9
     assert H.rel_err(col_pid.hdot_corr.cpu().numpy(), fused.pid[0].cpu().numpy()) < 1e-9
     assert H.rel_err(next_ref[[0, 7, 11]].cpu().numpy(), fused.ref3.cpu().numpy()) < 1e-9
+    # RecursiveLeastSquares.predict (model.py:61-69) against its definition on the trained weights
+    pred = rls.predict(observation, actions[:2])
+    X = torch.cat([observation - rls.x, actions[:2] - rls.u])
+    want = observation + torch.einsum("ijn,in->jn", rls.W, X)
+    assert H.rel_err(pred.cpu().numpy(), want.cpu().numpy()) < 1e-12
+    # a virtual step leaves the state alone but advances the clock and the engine lag (heli_models.py:464-475)
+    before, t0 = env.state.clone(), env.t
+    nxt, _, _ = env.step(actions, virtual=True)
+    assert torch.equal(env.state, before) and not torch.equal(nxt, before) and env.t > t0
 
 
 def test_log_dataframe_has_the_reference_logger_columns():
