@@ -27,6 +27,9 @@ def test_trim_matches_reference():
     assert H.rel_err(st.cpu().numpy().T, g["state"]) < 1e-8
     assert H.rel_err(ct.cpu().numpy().T, g["controls"]) < 1e-8
     assert H.rel_err(env.P_out.cpu().numpy(), g["P_out"]) < 1e-8
+    # the trimmed state is an equilibrium of calculate_state_derivatives(trimming=True) (heli_models.py:781-785)
+    d = env.calculate_state_derivatives(ct, trimming=True)
+    assert float(d[:6].abs().max()) < 1e-6 and float(d[12:].abs().max()) < 1e-6
 
 
 def test_derivatives_and_step_match_reference():
