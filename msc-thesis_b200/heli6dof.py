@@ -712,12 +712,37 @@ class Logger:
     (DataFrames indexed by env.t, one row per log_weights call) -- the inputs of plotting.plot_stats,
     plot_neural_network_weights and plot_rls_weights."""
 
-    def __init__(self, params):
+    def __init__(self, params, episode=0):
         self.training_parameters = params
-        self.state_history = None
+        self.episode = episode                      # which episode of the batch the step-by-step calls record
+        self.state_history = []
         self.weight_history = {a: {k: [] for k in ("ci", "co", "ai", "ao", "dsda", "dsds")} for a in ("col", "lon")}
         self._t = []
         self.finalized = False
+
+    def log_states(self, t, observation, ref, actions, rewards, Pav, Peng):
+        """util.py:30-66 for episode `self.episode` of (rows, N) tensors (step-by-step use of the object API)."""
+        e = self.episode
+        pick = self._scalar
+        obs = observation[:, e].detach().cpu().numpy() if torch.is_tensor(observation) else np.asarray(observation)
+        rf = ref[:, e].detach().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+        act = actions[:, e].detach().cpu().numpy() if torch.is_tensor(actions) else np.asarray(actions)
+        rew = rewards[:, e].detach().cpu().numpy() if torch.is_tensor(rewards) and rewards.dim() == 2 else np.asarray(
+            [pick(r) for r in rewards])
+        pav, peng = pick(Pav), pick(Peng)
+        names = ("u", "v", "w", "p", "q", "r", "phi", "theta", "psi", "x", "y", "z")
+        row = {"t": pick(t)}
+        row.update({n: obs[i] for i, n in enumerate(names)})
+        row.update({"Pav": pav, "Peng": float(np.clip(peng, 0, pav)), "omega": obs[-1], "ref": rf, "col": act[0], "lon": act[1],
+                    "lat": act[2], "ped": act[3], "r1": rew[0], "r2": rew[1]})
+        self.state_history.append(row)
+
+    def _scalar(self, v):
+        """A Python float from a scalar, a 1-element tensor or a per-episode (N,) tensor."""
+        if not torch.is_tensor(v):
+            return float(v)
+        v = v.reshape(-1)
+        return float(v[self.episode] if v.numel() > 1 else v[0])
 
     def log_weights(self, t, agents, rls_estimator, episode=0):
         """util.py:68-80 for one episode of the batch."""
@@ -731,11 +756,13 @@ class Logger:
             h["dsds"].append(Fm[:, :, episode].detach().cpu().numpy().ravel().copy())
             h["dsda"].append(Gm[:, :, episode].detach().cpu().numpy().ravel().copy())
 
-    def finalize(self, state_history):
+    def finalize(self, state_history=None):
+        """util.py:82-101; state_history: a ready DataFrame (fused runs, ClosedLoop6DOF.to_dataframe) instead of the rows
+        collected by log_states."""
         import pandas as pd
         if self.finalized:
             raise ValueError("Attempting to call logger.finalize(), but log is already finalized. ")      # util.py:84-85
-        self.state_history = state_history
+        self.state_history = pd.DataFrame(self.state_history) if state_history is None else state_history
         self.weight_history = {a: {k: pd.DataFrame(data=v, index=self._t) for k, v in h.items()}
                                for a, h in self.weight_history.items()}
         self.finalized = True

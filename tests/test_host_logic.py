@@ -158,6 +158,31 @@ def test_6dof_host_objects_fail_loudly_without_gpu():
     assert lim.tolist() == [True, True, False] and which.tolist() == [1, 2, 0]
 
 
+def test_6dof_logger_collects_rows_like_util_logger():
+    """heli6dof.Logger.log_states / finalize (util.py:30-101) on CPU tensors: one row per call for the chosen episode."""
+    import importlib
+    H6 = importlib.import_module("msc-thesis_b200.heli6dof")
+    lg = H6.Logger(params={"x": 1}, episode=1)
+    n = 3
+    obs = torch.arange(15 * n, dtype=torch.float64).reshape(15, n)
+    ref = torch.full((15, n), float("nan"), dtype=torch.float64)
+    ref[7] = 0.1
+    act = torch.tensor([[0.5] * n, [0.6] * n, [0.4] * n, [0.3] * n], dtype=torch.float64)
+    rew = torch.tensor([[0.0] * n, [-1.0, -2.0, -3.0]], dtype=torch.float64)
+    for k in range(2):
+        lg.log_states(0.01 * (k + 1), obs + k, ref, act, rew, torch.full((n,), 5e5, dtype=torch.float64),
+                      torch.tensor([6e5, 4e5, 3e5], dtype=torch.float64))
+    lg.finalize()
+    df = lg.state_history
+    assert list(df.columns) == ["t", "u", "v", "w", "p", "q", "r", "phi", "theta", "psi", "x", "y", "z", "Pav", "Peng", "omega",
+                                "ref", "col", "lon", "lat", "ped", "r1", "r2"]
+    assert len(df) == 2 and df["u"].tolist() == [1.0, 2.0] and df["omega"].tolist() == [43.0, 44.0]
+    assert df["r2"].tolist() == [-2.0, -2.0] and df["Peng"].tolist() == [4e5, 4e5] and df["t"].tolist() == [0.01, 0.02]
+    assert np.isnan(df["ref"].iloc[0][0]) and df["ref"].iloc[0][7] == 0.1
+    with pytest.raises(ValueError):
+        lg.finalize()
+
+
 def test_default_env_params_are_the_reference_constants():
     p = L.default_env_params(0.01)
     assert (p.g, p.cl_alpha, p.blade_solidity, p.lock_number, p.cds, p.mass) == (9.81, 5.7, 0.075, 6, 1.5, 2200)
