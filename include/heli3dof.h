@@ -242,6 +242,14 @@ int h3_math_probe(int32_t fn, const double* x, double* y, double* y2, int64_t n,
  * times it with CUDA events on `stream`. dtype: H3_F64 | H3_F32. */
 int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_out, void* stream);
 
+/* Tensor memory (TMEM, 256 KB per SM on sm_100a) used as thread-private storage by the fused kernel: functional
+ * probe.  Launches `blocks` CTAs of `warps` (4 or 8) warps; every thread fills its 128 private doubles with
+ * (global thread index * 1024 + word), reads them back in the piece sizes the kernel uses (out[0..127][nthreads]),
+ * runs `reps` read-modify-write (+1) passes (out[128..135] = words 0..7 afterwards, out[136] = checksum of a
+ * dependent-load chain), and reports per-CTA cycle counts {rmw passes, dependent loads} in cycles[2][blocks].
+ * out: DEVICE [137][blocks*warps*32] doubles. */
+int h3_tmem_probe(int32_t warps, int32_t blocks, int32_t reps, double* out, int64_t* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

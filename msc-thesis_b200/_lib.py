@@ -25,7 +25,7 @@ HYPER_NAMES = ("gamma", "lr_actor", "lr_critic", "tau", "scale", "reward_weight"
 EXPORTS = ("h3_version", "h3_last_error", "h3_env_params_default", "h3_trim", "h3_env_step", "h3_get_ref",
            "h3_pid_collective", "h3_rls_update", "h3_rls_predict", "h3_agent_action", "h3_agent_reward",
            "h3_agent_transition", "h3_agent_update", "h3_closed_loop", "h3_stats_scratch_bytes",
-           "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak")
+           "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe")
 
 
 class H3EnvParams(C.Structure):
@@ -135,9 +135,10 @@ def lib():
     L.h3_closed_loop_info.argtypes = [cfgp, i32] + [C.POINTER(i32)] * 5
     L.h3_fma_peak.argtypes = [i32, i32, vp, dp, vp]
     L.h3_math_probe.argtypes = [i32, vp, vp, vp, i64, vp]
+    L.h3_tmem_probe.argtypes = [i32, i32, i32, vp, vp, vp]
     for name in ("h3_trim", "h3_env_step", "h3_get_ref", "h3_pid_collective", "h3_rls_update", "h3_rls_predict",
                  "h3_agent_action", "h3_agent_reward", "h3_agent_transition", "h3_agent_update", "h3_closed_loop",
-                 "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak"):
+                 "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe"):
         getattr(L, name).restype = C.c_int
     c6, b6 = C.POINTER(H6Config), C.POINTER(H6Batch)
     L.h6_engine_power.argtypes = [dp]

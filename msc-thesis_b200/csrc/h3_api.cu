@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "h3_launch.cuh"
+#include "h3_tmem.cuh"
 
 namespace h3 {
 
@@ -434,6 +435,79 @@ __global__ void __launch_bounds__(SMALL_BLOCK) math_probe_kernel(int fn, const d
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMEM as thread-private storage (h3_tmem.cuh): functional probe + ld/st cost in cycles
+// ---------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) tmem_probe_kernel(double* out, long long* cyc, int reps, int64_t nthreads) {
+    __shared__ uint32_t slot;
+    constexpr int NCOLS = 256 * (WARPS / 4);
+    const uint32_t base = tmem_alloc(&slot, NCOLS);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t addr = tmem_addr(base, 256 * (warp >> 2));       // 128 doubles of private storage per thread
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // fill: word w of thread gt = gt * 1024 + w
+#pragma unroll 1
+    for (int w0 = 0; w0 < 128; w0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (double)(gt * 1024 + w0 + i);
+        tmem_store<double, 16>(addr, w0, v);
+    }
+    tmem_wait_st();
+    // read back with odd-sized pieces at runtime offsets: 12-word units (x16 + x8), then the tail
+    {
+#pragma unroll 1
+        for (int k = 0; k < 10; ++k) {
+            double v[12];
+            tmem_load<double, 12>(addr, 12 * k, v);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) out[(int64_t)(12 * k + i) * nthreads + gt] = v[i];
+        }
+        double t[8];
+        tmem_load<double, 8>(addr, 120, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[(int64_t)(120 + i) * nthreads + gt] = t[i];
+    }
+    // read-modify-write round trip, as the agent update does: w += 1 for every word, `reps` times
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll 1
+        for (int k = 0; k < 10; ++k) {
+            double v[12];
+            tmem_load<double, 12>(addr, 12 * k, v);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] += 1.0;
+            tmem_store<double, 12>(addr, 12 * k, v);
+        }
+        tmem_wait_st();
+    }
+    long long t1 = clock64();
+    // dependent load latency: single-double loads whose address depends on the previous value
+    double acc = 0.0;
+    int w = 0;
+#pragma unroll 1
+    for (int r = 0; r < reps * 8; ++r) {
+        double v[1];
+        tmem_load<double, 1>(addr, w, v);
+        acc += v[0];
+        w = (w + 1 + (__double2loint(v[0]) & 0)) & 127;
+    }
+    long long t2 = clock64();
+    double fin[8];
+    tmem_load<double, 8>(addr, 0, fin);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[(int64_t)(128 + i) * nthreads + gt] = fin[i];
+    out[(int64_t)136 * nthreads + gt] = acc;
+    if (threadIdx.x == 0) {
+        cyc[2 * blockIdx.x] = t1 - t0;
+        cyc[2 * blockIdx.x + 1] = t2 - t1;
+    }
+    tmem_free(base, NCOLS);
+}
+
 static bool dtype_ok(int d) { return d == H3_F64 || d == H3_F32; }
 
 }  // namespace h3
@@ -788,6 +862,19 @@ int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_o
         fma_peak_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (float*)scratch_out);
     if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
     return check_launch("fma_peak_kernel");
+}
+
+int h3_tmem_probe(int32_t warps, int32_t blocks, int32_t reps, double* out, int64_t* cycles, void* stream) {
+    if ((warps != 4 && warps != 8) || blocks <= 0 || reps < 0 || !out || !cycles) {
+        set_error("h3_tmem_probe: bad argument");
+        return H3_E_ARG;
+    }
+    const int64_t nthreads = (int64_t)blocks * warps * 32;
+    if (warps == 4)
+        tmem_probe_kernel<4><<<blocks, 128, 0, (cudaStream_t)stream>>>(out, (long long*)cycles, reps, nthreads);
+    else
+        tmem_probe_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(out, (long long*)cycles, reps, nthreads);
+    return check_launch("tmem_probe_kernel");
 }
 
 }  // extern "C"

@@ -51,18 +51,19 @@ struct LoopParams {
     unsigned int* ticket;
 };
 
-template <typename NT>
+template <typename NT, bool CG = false>
 H3_DEV AgentH<NT> load_hyper(const H3AgentHyper& h, const double* per_ep, int64_t ld, int64_t e, double& w_r) {
     AgentH<NT> H;
     double gamma = h.gamma, lr_a = h.lr_actor, lr_c = h.lr_critic, tau = h.tau, scale = h.scale;
     w_r = h.reward_weight;
     if (per_ep != nullptr) {
-        gamma = per_ep[H3_HYPER_GAMMA * ld + e];
-        lr_a = per_ep[H3_HYPER_LR_ACTOR * ld + e];
-        lr_c = per_ep[H3_HYPER_LR_CRITIC * ld + e];
-        tau = per_ep[H3_HYPER_TAU * ld + e];
-        scale = per_ep[H3_HYPER_SCALE * ld + e];
-        w_r = per_ep[H3_HYPER_REWARD_WEIGHT * ld + e];
+        auto rd = [&](int row) { return CG ? __ldcg(per_ep + row * ld + e) : per_ep[row * ld + e]; };
+        gamma = rd(H3_HYPER_GAMMA);
+        lr_a = rd(H3_HYPER_LR_ACTOR);
+        lr_c = rd(H3_HYPER_LR_CRITIC);
+        tau = rd(H3_HYPER_TAU);
+        scale = rd(H3_HYPER_SCALE);
+        w_r = rd(H3_HYPER_REWARD_WEIGHT);
     }
     H.gamma = (NT)gamma;
     H.lr_a = (NT)lr_a;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "h3_closed_loop.cuh"
+#include "h3_closed_loop_tm.cuh"
 
 namespace h3 {
 
@@ -116,6 +117,53 @@ static KernelSel<ET, NT> sel_flags(bool col, int variant) {
     return sel_kernel<ET, NT, NHL, NHC, false, VAR_GENERAL>();
 }
 
+
+// ---- launches with the collective agent, lockstep: the tensor-memory kernel (h3_closed_loop_tm.cuh) ----
+#ifndef H3_TM
+#define H3_TM 1             // 0: keep the shared-memory-only variants (PAIR / 4-warp) for these launches
+#endif
+#ifndef H3_TM_WARPS
+#define H3_TM_WARPS 4       // warps per CTA of the tensor-memory kernel (8 / H3_TM_WARPS CTAs per SM)
+#endif
+#ifndef H3_TM_V
+#define H3_TM_V 2           // hidden units per TMEM round trip of the collective agent's update
+#endif
+constexpr size_t SMEM_PER_SM = 233472;          // 228 KB per SM, 1 KB of it reserved per resident CTA
+
+template <typename ET, typename NT, int NHL, int NHC, int VAR>
+struct TuneTm {
+    static constexpr bool HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
+    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, 32, H3_TM_WARPS> L32;
+    // eight warps per SM in one or two CTAs: the tile of a warp gets an eighth of what is left of the SM's shared memory
+    static constexpr int CTAS = 8 / H3_TM_WARPS;
+    static constexpr size_t room = (SMEM_PER_SM / CTAS - 1024 - L32::head_bytes) / L32::WARPS - 16;
+    static constexpr int fit = (int)(room / L32::bytes_per_col);       // columns incl. the idle lanes' dummy column
+    static constexpr int LANES = fit >= 32 ? 32 : fit - 1;
+    static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");
+    static constexpr int UF = (NHC % 5 == 0) ? 5 : ((NHC % 4 == 0) ? 4 : ((NHC % 3 == 0) ? 3 : ((NHC % 2 == 0) ? 2 : 1)));
+    static constexpr int V = (NHC % H3_TM_V == 0) ? H3_TM_V : 1;
+    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, H3_TM_WARPS> LY;
+};
+
+template <typename ET, typename NT, int NHL, int NHC, int VAR>
+static KernelSel<ET, NT> sel_tm() {
+    typedef TuneTm<ET, NT, NHL, NHC, VAR> T;
+    KernelSel<ET, NT> k;
+    k.fn = closed_loop_tm_kernel<ET, NT, NHL, NHC, T::HYP, T::TAU1L, T::LANES, H3_RD_P1, T::UF, T::V, H3_TM_WARPS>;
+    k.block = T::LY::WARPS * 32;
+    k.lanes = T::LANES;
+    k.warps = T::LY::WARPS;
+    k.smem = T::LY::smem_bytes;
+    return k;
+}
+
+template <typename ET, typename NT, int NHL, int NHC>
+static KernelSel<ET, NT> sel_flags(bool col, int variant, bool tm) {
+    if (col && tm && variant == VAR_FAST) return sel_tm<ET, NT, NHL, NHC, VAR_FAST>();
+    if (col && tm && variant == VAR_SWEEP) return sel_tm<ET, NT, NHL, NHC, VAR_SWEEP>();
+    return sel_flags<ET, NT, NHL, NHC>(col, variant);
+}
+
 template <typename ET, typename NT>
 int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const double* ref_table,
                        const double* excitation, int exc_len, int n_ticks, const H3Traj* traj, double* stats,
@@ -128,16 +176,20 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     const bool per_ep = b.col_hyper != nullptr || b.lon_hyper != nullptr;
     const int variant = (cfg.rls_symmetric == 0) ? VAR_GENERAL
                                                  : ((per_ep || cfg.lon.tau != 1.0) ? VAR_SWEEP : VAR_FAST);
+    // tensor-memory kernel: needs a warp-uniform tick index (lockstep) and the symmetric covariance
+    const bool tm = H3_TM && col && (step0 >= 0 || info_only != nullptr) && variant != VAR_GENERAL && cfg.store_policy != 3;
     KernelSel<ET, NT> k;
-    if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant);
+    if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant, tm);
 #ifndef H3_FAST_BUILD
-    else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant);
+    else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant, tm);
 #endif
     else {
         set_error("h3_closed_loop: hidden widths (lon %d, col %d) not compiled in (have 6/10, 8/8)", nhl, nhc);
         return H3_E_UNSUPPORTED;
     }
     cudaError_t err = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
+    if (err == cudaSuccess)         // every variant is sized to fill the SM's shared memory with co-resident CTAs
+        err = cudaFuncSetAttribute(k.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(smem=%zu): %s", k.smem, cudaGetErrorString(err));
         return H3_E_CUDA;
