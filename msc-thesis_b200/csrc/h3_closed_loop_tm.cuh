@@ -12,9 +12,9 @@
 // per SM with ONE lane per episode: the same occupancy as the PID-collective launches, no duplicated work.
 //
 // Layout of a thread's TMEM range (words of NT; a double is two columns): hidden unit k owns 12 words at 12 k
-//   [a1(k,0) a1(k,1) a2(k) h_a(k) | c1(k,0) c1(k,1) c2(0,k) c2(1,k) | t1(k,0) t1(k,1) t2(0,k) t2(1,k)]
-// followed by [f, s0, s1, -] of the forward pass.  One LDTM.x8 per unit feeds the forward pass, an x32 + x16
-// pair feeds two units of the update.
+//   [t1(k,0) t1(k,1) t2(0,k) t2(1,k) | c1(k,0) c1(k,1) c2(0,k) c2(1,k) | a1(k,0) a1(k,1) a2(k) h(k)]
+// followed by [f, s0, s1, -] of the forward pass.  Every pass of the agent's update (col_update_tm) reads one
+// contiguous piece per hidden unit.
 //
 // tcgen05.ld / st are warp-collective, so the warp stays converged: a terminated lane is not skipped, it keeps
 // executing on sanitised inputs with its bookkeeping frozen.  Its state is written to HBM at the tick it
@@ -32,7 +32,9 @@ struct ColTm {
     static constexpr int UNIT = 12;
     static constexpr int TAIL = UNIT * NH;
     static constexpr int WORDS = TAIL + 4;
-    enum { A10 = 0, A11, A2, HA, C10, C11, C20, C21, T10, T11, T20, T21 };
+    // target critic | critic | actor + a hidden activation (the actor's from the forward pass to pass A of the update,
+    // the critic's from there to pass C)
+    enum { T10 = 0, T11, T20, T21, C10, C11, C20, C21, A10, A11, A2, HA };
     // row of the `[11 nh][ld]` HBM block (include/heli3dof.h) that holds slot `w` of unit k (w != HA)
     H3_DEV static int row(int k, int w) {
         switch (w) {
@@ -59,20 +61,20 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
     typedef ColTm<NH> L;
     static_assert(NH % UF == 0, "group width must divide the hidden width");
     NT y = (NT)0;
-#pragma unroll
+#pragma unroll 1
     for (int k0 = 0; k0 < NH; k0 += UF) {
-        TmemBuf<NT, 4> b[UF];
+        TmemBuf<NT, 4> b[UF];               // a1(k,0) a1(k,1) a2(k) (h)
 #pragma unroll
-        for (int u = 0; u < UF; ++u) b[u].issue(tm, L::UNIT * (k0 + u));
+        for (int u = 0; u < UF; ++u) b[u].issue(tm, L::UNIT * (k0 + u) + L::A10);
         tmem_wait_ld();
         NT pre[UF], hk[UF];
 #pragma unroll
-        for (int u = 0; u < UF; ++u) pre[u] = b[u][L::A10] * s0 + b[u][L::A11] * s1;
+        for (int u = 0; u < UF; ++u) pre[u] = b[u][0] * s0 + b[u][1] * s1;
         M::template tanh_vec<UF>(pre, hk);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
-            y += b[u][L::A2] * hk[u];
+            y += b[u][2] * hk[u];
             const NT w[1] = {hk[u]};
             tmem_store<NT, 1>(tm, L::UNIT * (k0 + u) + L::HA, w);
         }
@@ -85,88 +87,109 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
 }
 
 // get_reward + get_transition_matrices + update_networks (agents.py:123-196) of the collective agent, closed form
-// as h3_tick.cuh: agent_update (same operation order), V hidden units per TMEM round trip.
-template <typename NT, int NH, int V>
+// as h3_tick.cuh: agent_update (same formulas, sums in the same order), arranged as three passes over the hidden
+// units so that every loop runs with a RUNTIME unit index (TMEM addresses are plain register arithmetic) and the
+// code is not replicated per chunk:
+//   T : target critic on s' (:171)            -> lambda_t2, hence the target and the actor's step size
+//   A : critic on s (:170), da/ds (:174), and the actor's SGD step (:184-186), which needs nothing from the other
+//       units; the critic's hidden activation then takes the slot of the actor's (no longer needed)
+//   C : critic SGD step (:187-188) and soft target update (:195-196)
+//   UP: hidden units per group of passes T and A (their tanh chains are interleaved); V2: units per group of pass C.
+template <typename NT, int NH, int UP, int V2>
 H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n1, NT dr0, NT dr, const NT (&F)[2][2],
                           const NT (&G)[2]) {
     typedef Math<NT> M;
     typedef ColTm<NH> L;
-    static_assert(NH % V == 0, "chunk width must divide the hidden width");
+    static_assert(NH % UP == 0 && NH % V2 == 0, "chunk widths must divide the hidden width");
     tmem_wait_st();                                     // the forward pass stored h_a and the tail
     NT tl[4];
     tmem_load<NT, 4>(tm, L::TAIL, tl);
     const NT f = tl[0], s0 = tl[1], s1 = tl[2];
     const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);
-    NT lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
-    NT hcs[NH];
-    // pass 1: critic(s), target_critic(s') (:170-171) and da/ds
+    // ---- pass T ----
+    NT lam2[2] = {(NT)0, (NT)0};
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += UP) {
+        TmemBuf<NT, 4> b[UP];               // t1(k,0) t1(k,1) t2(0,k) t2(1,k)
 #pragma unroll
-    for (int k0 = 0; k0 < NH; k0 += V) {
-        TmemBuf<NT, L::UNIT * V> b;
-        b.issue(tm, L::UNIT * k0);
+        for (int u = 0; u < UP; ++u) b[u].issue(tm, L::UNIT * (k0 + u) + L::T10);
         tmem_wait_ld();
-        NT pre[2 * V], ac[2 * V];
+        NT pre[UP], ht[UP];
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-            pre[u] = b[12 * u + L::C10] * s0 + b[12 * u + L::C11] * s1;
-            pre[V + u] = b[12 * u + L::T10] * n0 + b[12 * u + L::T11] * n1;
-        }
-        M::template tanh_vec<2 * V>(pre, ac);
+        for (int u = 0; u < UP; ++u) pre[u] = b[u][0] * n0 + b[u][1] * n1;
+        M::template tanh_vec<UP>(pre, ht);
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-            const NT hc = ac[u], ht = ac[V + u];
-            hcs[k0 + u] = hc;
-            lam1[0] += b[12 * u + L::C20] * hc;
-            lam1[1] += b[12 * u + L::C21] * hc;
-            lam2[0] += b[12 * u + L::T20] * ht;
-            lam2[1] += b[12 * u + L::T21] * ht;
-            const NT ha = b[12 * u + L::HA];
-            const NT pk = delta * b[12 * u + L::A2] * ((NT)1 - ha * ha);
-            da_ds[0] += b[12 * u + L::A10] * pk;
-            da_ds[1] += b[12 * u + L::A11] * pk;
+        for (int u = 0; u < UP; ++u) {
+            lam2[0] += b[u][2] * ht[u];
+            lam2[1] += b[u][3] * ht[u];
         }
     }
-    // target = dr_ds + gamma * lambda_t2 ; error_critic = lambda_t1 - target (F + G da_ds)  (:178-179)
+    // target = dr_ds + gamma * lambda_t2 (:178); actor step size lr_a * (target . G) (:184)
     const NT tg0 = dr0 + H.gamma * lam2[0];
     const NT tg1 = dr + H.gamma * lam2[1];
+    const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
+    // ---- pass A ----
+    NT lam1[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += UP) {
+        NT pre[UP], hc[UP];
+        {
+            TmemBuf<NT, 2> c1[UP];          // c1(k,0) c1(k,1)
+#pragma unroll
+            for (int u = 0; u < UP; ++u) c1[u].issue(tm, L::UNIT * (k0 + u) + L::C10);
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < UP; ++u) pre[u] = c1[u][0] * s0 + c1[u][1] * s1;
+        }
+        M::template tanh_vec<UP>(pre, hc);
+        __syncwarp();
+        TmemBuf<NT, 6> b[UP];               // c2(0,k) c2(1,k) a1(k,0) a1(k,1) a2(k) h_a(k)
+#pragma unroll
+        for (int u = 0; u < UP; ++u) b[u].issue(tm, L::UNIT * (k0 + u) + L::C20);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+            lam1[0] += b[u][0] * hc[u];
+            lam1[1] += b[u][1] * hc[u];
+            const NT ha = b[u][5], a2k = b[u][4];
+            const NT pk = delta * a2k * ((NT)1 - ha * ha);
+            da_ds[0] += b[u][2] * pk;
+            da_ds[1] += b[u][3] * pk;
+            const NT o[4] = {b[u][2] + ka * (pk * s0), b[u][3] + ka * (pk * s1), a2k + ka * (delta * ha), hc[u]};
+            tmem_store<NT, 4>(tm, L::UNIT * (k0 + u) + L::A10, o);
+        }
+    }
+    // error_critic = lambda_t1 - target (F + G da_ds)  (:179)
     NT e_c[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         e_c[j] = lam1[j] - (tg0 * (F[0][j] + G[0] * da_ds[j]) + tg1 * (F[1][j] + G[1] * da_ds[j]));
-    const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
     const NT one_m_tau = (NT)1 - H.tau;
-    // pass 2: SGD (:184-188) and the soft target update (:195-196)
+    tmem_wait_st();                                     // pass A stored the critic's hidden activations
+    // ---- pass C ----
+#pragma unroll 1
+    for (int k0 = 0; k0 < NH; k0 += V2) {
+        TmemBuf<NT, 8> b[V2];               // t1(k,:) t2(:,k) c1(k,:) c2(:,k)
+        TmemBuf<NT, 1> h[V2];               // critic hidden activation (in the h_a slot)
 #pragma unroll
-    for (int k0 = 0; k0 < NH; k0 += V) {
-        TmemBuf<NT, L::UNIT * V> b;
-        b.issue(tm, L::UNIT * k0);
+        for (int u = 0; u < V2; ++u) {
+            b[u].issue(tm, L::UNIT * (k0 + u) + L::T10);
+            h[u].issue(tm, L::UNIT * (k0 + u) + L::HA);
+        }
         tmem_wait_ld();
-        NT o[L::UNIT * V];
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-            const NT hc = hcs[k0 + u], ha = b[12 * u + L::HA];
-            const NT a2k = b[12 * u + L::A2], c20 = b[12 * u + L::C20], c21 = b[12 * u + L::C21];
-            const NT pk = delta * a2k * ((NT)1 - ha * ha);
+        for (int u = 0; u < V2; ++u) {
+            const NT hc = h[u][0], c20 = b[u][6], c21 = b[u][7];
             const NT back = (c20 * e_c[0] + c21 * e_c[1]) * ((NT)1 - hc * hc);
-            o[12 * u + L::A10] = b[12 * u + L::A10] + ka * (pk * s0);
-            o[12 * u + L::A11] = b[12 * u + L::A11] + ka * (pk * s1);
-            o[12 * u + L::A2] = a2k + ka * (delta * ha);
-            o[12 * u + L::HA] = ha;
-            const NT n10 = b[12 * u + L::C10] - H.lr_c * (back * s0);
-            const NT n11 = b[12 * u + L::C11] - H.lr_c * (back * s1);
+            const NT n10 = b[u][4] - H.lr_c * (back * s0);
+            const NT n11 = b[u][5] - H.lr_c * (back * s1);
             const NT n20 = c20 - H.lr_c * (e_c[0] * hc);
             const NT n21 = c21 - H.lr_c * (e_c[1] * hc);
-            o[12 * u + L::C10] = n10;
-            o[12 * u + L::C11] = n11;
-            o[12 * u + L::C20] = n20;
-            o[12 * u + L::C21] = n21;
-            o[12 * u + L::T10] = H.tau * n10 + one_m_tau * b[12 * u + L::T10];
-            o[12 * u + L::T11] = H.tau * n11 + one_m_tau * b[12 * u + L::T11];
-            o[12 * u + L::T20] = H.tau * n20 + one_m_tau * b[12 * u + L::T20];
-            o[12 * u + L::T21] = H.tau * n21 + one_m_tau * b[12 * u + L::T21];
+            const NT o[8] = {H.tau * n10 + one_m_tau * b[u][0], H.tau * n11 + one_m_tau * b[u][1],
+                             H.tau * n20 + one_m_tau * b[u][2], H.tau * n21 + one_m_tau * b[u][3], n10, n11, n20, n21};
+            tmem_store<NT, 8>(tm, L::UNIT * (k0 + u) + L::T10, o);
         }
-        tmem_store<NT, L::UNIT * V>(tm, L::UNIT * k0, o);
     }
     tmem_wait_st();                                     // the next tick's forward pass loads these columns
 }
@@ -188,7 +211,7 @@ template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int 
 struct TmLayout {
     static constexpr int WARPS = WARPS_;           // 4 or 8: warps w and w + 4 share a lane quadrant, own column ranges
     static constexpr int STRIDE = LANES < 32 ? LANES + 1 : 32;      // + one dummy column for the idle lanes
-    static constexpr size_t bytes_per_col = sizeof(ET) * (45 + 63) + (TAU1L ? 0 : sizeof(NT) * 4 * NHL);
+    static constexpr size_t bytes_per_col = sizeof(double) * 3 + sizeof(ET) * (45 + 63) + (TAU1L ? 0 : sizeof(NT) * 4 * NHL);
     static constexpr size_t tile_bytes = ((bytes_per_col * STRIDE + 15) / 16) * 16;
     static constexpr size_t head_bytes = sizeof(double) * WARPS * (3 * TICK_CHUNK + H3_N_STATS) + 16;
     static constexpr size_t smem_bytes = head_bytes + tile_bytes * WARPS;
@@ -199,8 +222,9 @@ struct TmLayout {
 
 //   HYP   : per-episode hyper-parameter rows (re-read from L2 every tick); TAU1L: tau_lon == 1 (target critic of the cyclic
 //           agent not carried, see agent_update); LANES: episodes per warp (<= 32, as many as the tile allows);
-//   RD    : look-ahead of the RLS shared-memory streams; UF / V: hidden units per TMEM round trip (forward / update)
-template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int RD, int UF, int V, int WARPS_>
+//   RD    : look-ahead of the RLS shared-memory streams; UF / UP / V2: hidden units per group of the collective
+//           agent's forward pass / critic passes / weight update
+template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int RD, int UF, int UP, int V2, int WARPS_>
 __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel(const LoopParams<ET, NT> P) {
     typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, WARPS_> LY;
     constexpr int WARPS = LY::WARPS, STRIDE = LY::STRIDE, BLOCK = WARPS * 32;
@@ -228,8 +252,11 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     CovSym<ET, CovVec> cov;
     WMatD<ET, SmemVec<ET, 63, STRIDE>> Wm;
     LonNetTm<NT, NHL, STRIDE, !TAU1L> lon;
+    SmemVec<double, 3, STRIDE> accv;        // sum r_col, sum r_lon, sum r_lon inside the score window
     {
-        ET* pe = reinterpret_cast<ET*>(tp);
+        double* pd = reinterpret_cast<double*>(tp);
+        accv.p = pd + lc; pd += 3 * STRIDE;
+        ET* pe = reinterpret_cast<ET*>(pd);
         cov.v.p = pe + lc; pe += 45 * STRIDE;
         Wm.v.p = pe + lc; pe += 63 * STRIDE;
         NT* pn = reinterpret_cast<NT*>(pe);
@@ -249,8 +276,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
         }
     }
     ET s[7], refth, prev[9];
-    double acc0, acc1, acc2, t_ep;
-    ET corr_u, pid_corr, trim0, trim1;
+    double t_ep;
 #pragma unroll
     for (int i = 0; i < 7; ++i) s[i] = P.state[i * ld + ec];
     refth = P.ref[ld + ec];
@@ -262,14 +288,13 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     for (int i = 0; i < 7; ++i) prev[i] = P.rls_x[i * ld + ec];
     prev[7] = P.rls_u[ec];
     prev[8] = P.rls_u[ld + ec];
-    acc0 = P.acc[ec];
-    acc1 = P.acc[ld + ec];
-    acc2 = P.acc[2 * ld + ec];
+    // cold per-episode scalars stay out of the register file: the accumulators live in the tile, the trimmed
+    // controls (read-only) are re-read from L2 every tick, the PID / velocity-task integrators are read and written
+    // in place by the ticks that use them (PID collective: ticks < switch_step only)
+    accv[0] = P.acc[ec];
+    accv[1] = P.acc[ld + ec];
+    accv[2] = P.acc[2 * ld + ec];
     t_ep = P.t[ec];
-    corr_u = P.corr_u[ec];
-    pid_corr = P.pid_corr[ec];
-    trim0 = (ET)P.trim[ec];
-    trim1 = (ET)P.trim[ld + ec];
 #pragma unroll
     for (int i = 0; i < 9; ++i)
 #pragma unroll
@@ -283,7 +308,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
 
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
     const bool table_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_TABLE);
-    NT stl[2 * NHL + 3];                    // hl[NHL], fl, sl0, sl1, scratch[NHL] of the cyclic agent
+    NT stl[2 * NHL + 3];                    // hl[NHL], fl, (sl0, sl1: update only), scratch[NHL] of the cyclic agent
 
     // ---- resumable tick loop: leaves whenever a lane terminated, so that its state is stored at once ----
     int j = 0;
@@ -312,6 +337,10 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 for (int i = 0; i < 7; ++i) s[i] = (ET)0;
                 refth = (ET)0;
             }
+            // trimmed controls (read-only rows, L2): issued here, consumed after the forward passes
+            const ET trim1 = (ET)__ldcg(P.trim + ld + ec);
+            ET trim0 = (ET)0;
+            if (phase2) trim0 = (ET)__ldcg(P.trim + ec);
             AgentH<NT> Hcol = P.col_h, Hlon = P.lon_h;
             ET wr_col = P.col_wr, wr_lon = P.lon_wr;
             if constexpr (HYP) {            // read-only rows, L2-resident: re-read per tick instead of pinning 24 registers
@@ -331,8 +360,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                                                                     stl, fl);
                 cyc = trim1 + (ET)a_lon;
                 stl[NHL] = fl;
-                stl[NHL + 1] = sl0;
-                stl[NHL + 2] = sl1;
             }
             if (phase2) {
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
@@ -346,9 +373,9 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             ET scy, ccy;
             Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
             if (!phase2) {
-                ET pc = pid_corr;
+                ET pc = P.pid_corr[ec];
                 colv = pid_collective(K, s, sth, cth, pc);                          // PID.py:16-24
-                pid_corr = pc;
+                if (!dead) P.pid_corr[ec] = pc;
             }
             colv += (ET)sh_exc[2 * jj];
             if (dead) colv = (ET)0;
@@ -364,8 +391,11 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             X[8] = cyc - prev[8];
             prev[7] = colv;                         // model.py:46
             prev[8] = cyc;
-            ET cu = corr_u;
-            if (P.task == H3_TASK_VELOCITY) (void)velocity_ref(K, s[2], cu);        // heli_models.py:155
+            ET cu = (ET)0;
+            if (P.task == H3_TASK_VELOCITY) {
+                cu = P.corr_u[ec];
+                (void)velocity_ref(K, s[2], cu);                                    // heli_models.py:155
+            }
             bool done;
             env_step(K, s, colv, cyc, sth, cth, scy, ccy, done);
             const double t_new = t_ep + P.dt;                                        // heli_models.py:206
@@ -415,9 +445,12 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 transition_matrices<ET, NT>(Wm, P.lon, F, G);
                 const NT n0 = (NT)pick7(s, P.lon.ac_state);
                 const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
+                // the augmented state of (obs, ref) again: prev[] holds the pre-step observation (model.py:45)
+                const NT sl0 = (NT)pick7(prev, P.lon.ac_state);
+                const NT sl1 = (NT)(P.lon.tracked_state == 1 ? prev[1] : pick7(prev, P.lon.tracked_state) - refth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
-                agent_update<NT, NHL, NHL, TAU1L, false>(lon, Hlon, P.lon.final_activation, stl[NHL + 1], stl[NHL + 2],
-                                                         n0, n1, (NT)0, dr, F, G, stl, stl[NHL], scr);
+                agent_update<NT, NHL, NHL, TAU1L, false>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
+                                                         F, G, stl, stl[NHL], scr);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -429,7 +462,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT n0 = (NT)pick7(s, P.col.ac_state);
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
                 __syncwarp();
-                col_update_tm<NT, NHC, V>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G);
+                col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G);
             }
             // -------- bookkeeping and termination (main_3dof.py:189-197): frozen for terminated episodes --------
             if (!dead) {
@@ -438,10 +471,10 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                     row[11 * P.ld_traj] = (ET)r_lon;
                 }
                 t_ep = t_new;
-                if (P.task == H3_TASK_VELOCITY) corr_u = cu;
-                acc0 += r_col;
-                acc1 += r_lon;
-                if (k >= P.win_lo && k < P.win_hi) acc2 += r_lon;
+                if (P.task == H3_TASK_VELOCITY) P.corr_u[ec] = cu;
+                accv[0] += r_col;
+                accv[1] += r_lon;
+                if (k >= P.win_lo && k < P.win_hi) accv[2] += r_lon;
                 refth = nrefth;
                 step = k + 1;
                 const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
@@ -476,8 +509,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
 #pragma unroll
             for (int i = 0; i < 7; ++i) P.state[i * ld + e] = s[i];
             P.ref[ld + e] = refth;
-            P.corr_u[e] = corr_u;
-            P.pid_corr[e] = pid_corr;
 #pragma unroll
             for (int i = 0; i < 7; ++i) P.rls_x[i * ld + e] = prev[i];
             P.rls_u[e] = prev[7];
@@ -487,9 +518,9 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             P.flags[e] = flags;
             P.term_step[e] = term_step;
             P.t[e] = t_ep;
-            P.acc[e] = acc0;
-            P.acc[ld + e] = acc1;
-            P.acc[2 * ld + e] = acc2;
+            P.acc[e] = accv[0];
+            P.acc[ld + e] = accv[1];
+            P.acc[2 * ld + e] = accv[2];
 #pragma unroll
             for (int i = 0; i < 9; ++i)
 #pragma unroll
@@ -518,9 +549,10 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
         v[1] = (valid && flags == 0) ? 1.0 : 0.0;
         v[2] = (valid && (flags & H3_FLAG_DONE)) ? 1.0 : 0.0;
         v[3] = (valid && (flags & H3_FLAG_NAN)) ? 1.0 : 0.0;
-        v[4] = valid ? acc0 : 0.0;
-        v[5] = valid ? acc1 : 0.0;
-        v[6] = valid ? acc2 : 0.0;
+        // (a terminated episode's accumulators are frozen: every update above is guarded by !dead)
+        v[4] = valid ? accv[0] : 0.0;
+        v[5] = valid ? accv[1] : 0.0;
+        v[6] = valid ? accv[2] : 0.0;
         v[7] = valid ? (double)step : 0.0;
         __syncthreads();
         block_reduce_stats<WARPS>(v, sh_red);

@@ -125,8 +125,14 @@ static KernelSel<ET, NT> sel_flags(bool col, int variant) {
 #ifndef H3_TM_WARPS
 #define H3_TM_WARPS 4       // warps per CTA of the tensor-memory kernel (8 / H3_TM_WARPS CTAs per SM)
 #endif
-#ifndef H3_TM_V
-#define H3_TM_V 2           // hidden units per TMEM round trip of the collective agent's update
+#ifndef H3_TM_V2
+#define H3_TM_V2 2          // ... of its weight update (pass 2)
+#endif
+#ifndef H3_TM_RD
+#define H3_TM_RD 1          // look-ahead (groups) of the RLS shared-memory streams in the tensor-memory kernel
+#endif
+#ifndef H3_TM_UP
+#define H3_TM_UP 5          // hidden units of the collective agent whose critic + target tanh chains are interleaved
 #endif
 constexpr size_t SMEM_PER_SM = 233472;          // 228 KB per SM, 1 KB of it reserved per resident CTA
 
@@ -141,7 +147,8 @@ struct TuneTm {
     static constexpr int LANES = fit >= 32 ? 32 : fit - 1;
     static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");
     static constexpr int UF = (NHC % 5 == 0) ? 5 : ((NHC % 4 == 0) ? 4 : ((NHC % 3 == 0) ? 3 : ((NHC % 2 == 0) ? 2 : 1)));
-    static constexpr int V = (NHC % H3_TM_V == 0) ? H3_TM_V : 1;
+    static constexpr int UP = (NHC % H3_TM_UP == 0) ? H3_TM_UP : ((NHC % 4 == 0) ? 4 : ((NHC % 3 == 0) ? 3 : ((NHC % 2 == 0) ? 2 : 1)));
+    static constexpr int V2 = (NHC % H3_TM_V2 == 0) ? H3_TM_V2 : 1;
     typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, H3_TM_WARPS> LY;
 };
 
@@ -149,7 +156,7 @@ template <typename ET, typename NT, int NHL, int NHC, int VAR>
 static KernelSel<ET, NT> sel_tm() {
     typedef TuneTm<ET, NT, NHL, NHC, VAR> T;
     KernelSel<ET, NT> k;
-    k.fn = closed_loop_tm_kernel<ET, NT, NHL, NHC, T::HYP, T::TAU1L, T::LANES, H3_RD_P1, T::UF, T::V, H3_TM_WARPS>;
+    k.fn = closed_loop_tm_kernel<ET, NT, NHL, NHC, T::HYP, T::TAU1L, T::LANES, H3_TM_RD, T::UF, T::UP, T::V2, H3_TM_WARPS>;
     k.block = T::LY::WARPS * 32;
     k.lanes = T::LANES;
     k.warps = T::LY::WARPS;

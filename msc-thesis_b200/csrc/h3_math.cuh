@@ -241,8 +241,9 @@ H3_DEV T clip_nan(T x, T lo, T hi) {
 }
 
 // element `idx` of a 7-vector held in registers (runtime but warp-uniform index)
-template <typename T>
-H3_DEV T pick7(const T (&s)[7], int idx) {
+template <typename T, int N>
+H3_DEV T pick7(const T (&s)[N], int idx) {
+    static_assert(N >= 7, "a state vector (or an array that starts with one)");
     T r = s[0];
 #pragma unroll
     for (int i = 1; i < 7; ++i) r = (idx == i) ? s[i] : r;
