@@ -242,6 +242,27 @@ int h3_math_probe(int32_t fn, const double* x, double* y, double* y2, int64_t n,
  * times it with CUDA events on `stream`. dtype: H3_F64 | H3_F32. */
 int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_out, void* stream);
 
+/* Episode initialisation on the device: everything main_3dof.py does before its tick loop (:58-71, :122), per
+ * episode, from a seed and the episode's GLOBAL index -- Helicopter3DOF.reset(v) incl. the trim (heli_models.py:
+ * 285-328), ref = env.get_ref() (main_3dof.py:62), RecursiveLeastSquares.reset (model.py:79-89), PID integrator 0
+ * (PID.py:8), DHPAgent weights ~ N(0, nn_stdev) with the target critic a copy of the critic (agents.py:19-22,
+ * :42-45, :107), counters and accumulators.  The reference draws its weights from torch's global generator; here
+ * draw (agent a, matrix m, element i) of episode g is Philox4x32-10 with counter (g_lo, g_hi, 4 a + m, i / 2), key =
+ * seed, followed by Box-Muller (exact recipe: oracle/philox_np.py), so a batch is the same set of episodes however it
+ * is cut into shards.  Writes EVERY per-episode row of the batch except the read-only inputs ref_par / *_hyper (the
+ * `const` rows trim and theta_trim ARE written). */
+typedef struct H3Init {
+    uint64_t seed;
+    int64_t episode0;            /* global index of the batch's episode 0 (rank offset of a sharded job) */
+    double v_trim;               /* trim speed, m/s (main_3dof.py:54), unless v_trim_ep */
+    double sigma[4];             /* nn_stdev: col actor, col critic, lon actor, lon critic */
+    double rls_cov0;             /* model.py:85 */
+    const double* v_trim_ep;     /* DEVICE [ld] or NULL */
+    const double* sigma_ep;      /* DEVICE [4][ld] or NULL: per-episode standard deviations (sweeps) */
+    const int64_t* episode_id;   /* DEVICE [ld] or NULL: explicit global indices (overrides episode0 + e) */
+} H3Init;
+int h3_init_episodes(const H3Config* cfg, const H3Batch* b, const H3Init* init, void* stream);
+
 /* Tensor memory (TMEM, 256 KB per SM on sm_100a) used as thread-private storage by the fused kernel: functional
  * probe.  Launches `blocks` CTAs of `warps` (4 or 8) warps; every thread fills its 128 private doubles with
  * (global thread index * 1024 + word), reads them back in the piece sizes the kernel uses (out[0..127][nthreads]),

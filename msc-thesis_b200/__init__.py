@@ -21,9 +21,11 @@ from .excitation import excitation_signal, load_excitation
 from .heli_models import Helicopter3DOF
 from .host_batch import HostBatchPipeline, loop_result_tensors, loop_state_tensors
 from .model import RecursiveLeastSquares
+from . import episodes
+from .episodes import EpisodeRunner
 from . import sweep
 from . import heli6dof
 
 __all__ = ["Helicopter3DOF", "CollectivePID3DOF", "RecursiveLeastSquares", "DHPAgent", "DHPActor", "DHPCritic",
            "ClosedLoop3DOF", "TRAJ_COLUMNS", "sinusoid_ref_table", "excitation_signal", "load_excitation",
-           "shard_range", "allreduce_stats", "H3Error", "lib"]
+           "shard_range", "allreduce_stats", "H3Error", "lib", "EpisodeRunner", "episodes"]

@@ -25,7 +25,7 @@ HYPER_NAMES = ("gamma", "lr_actor", "lr_critic", "tau", "scale", "reward_weight"
 EXPORTS = ("h3_version", "h3_last_error", "h3_env_params_default", "h3_trim", "h3_env_step", "h3_get_ref",
            "h3_pid_collective", "h3_rls_update", "h3_rls_predict", "h3_agent_action", "h3_agent_reward",
            "h3_agent_transition", "h3_agent_update", "h3_closed_loop", "h3_stats_scratch_bytes",
-           "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe")
+           "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe", "h3_init_episodes")
 
 
 class H3EnvParams(C.Structure):
@@ -54,6 +54,12 @@ class H3Batch(C.Structure):
     _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in (
         "state", "t", "ref", "corr_u", "trim", "theta_trim", "ref_par", "pid_corr", "rls_W", "rls_cov", "rls_x",
         "rls_u", "rls_skip", "col_net", "lon_net", "col_hyper", "lon_hyper", "step", "flags", "term_step", "acc")]
+
+
+class H3Init(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("episode0", C.c_int64), ("v_trim", C.c_double), ("sigma", C.c_double * 4),
+                ("rls_cov0", C.c_double), ("v_trim_ep", C.c_void_p), ("sigma_ep", C.c_void_p),
+                ("episode_id", C.c_void_p)]
 
 
 class H3Traj(C.Structure):
@@ -136,9 +142,10 @@ def lib():
     L.h3_fma_peak.argtypes = [i32, i32, vp, dp, vp]
     L.h3_math_probe.argtypes = [i32, vp, vp, vp, i64, vp]
     L.h3_tmem_probe.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.h3_init_episodes.argtypes = [cfgp, batp, C.POINTER(H3Init), vp]
     for name in ("h3_trim", "h3_env_step", "h3_get_ref", "h3_pid_collective", "h3_rls_update", "h3_rls_predict",
                  "h3_agent_action", "h3_agent_reward", "h3_agent_transition", "h3_agent_update", "h3_closed_loop",
-                 "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe"):
+                 "h3_closed_loop_info", "h3_math_probe", "h3_fma_peak", "h3_tmem_probe", "h3_init_episodes"):
         getattr(L, name).restype = C.c_int
     c6, b6 = C.POINTER(H6Config), C.POINTER(H6Batch)
     L.h6_engine_power.argtypes = [dp]

@@ -91,6 +91,8 @@ class DHPAgent:
         self.critic = DHPCritic(v[3 * nh:5 * nh].view(nh, 2, n), v[5 * nh:7 * nh].view(2, nh, n))
         self.target_critic = DHPCritic(v[7 * nh:9 * nh].view(nh, 2, n), v[9 * nh:11 * nh].view(2, nh, n))
         self.networks = [self.actor, self.critic, self.target_critic]
+        self.nn_stdev_actor, self.nn_stdev_critic = nn_stdev_actor, nn_stdev_critic
+        self.hyper_rows_device = None       # optional (6, N) f64 device rows (HYPER_NAMES order): used as they are
         if init == "auto":
             init = "reference" if n == 1 else "batched"
         self._init_weights(init, nn_stdev_actor, nn_stdev_critic, generator)
@@ -118,8 +120,10 @@ class DHPAgent:
             for layer, (o, i), std in shapes:
                 w = torch.randn(o, i, n, generator=generator, dtype=torch.float64) * std
                 layer.weight.copy_(w.to(self.dtype))
+        elif init == "device":
+            return                          # ClosedLoop3DOF.init_episodes draws the weights on the device
         else:
-            raise ValueError("init must be 'auto', 'reference' or 'batched'")
+            raise ValueError("init must be 'auto', 'reference', 'batched' or 'device'")
         self.target_critic.fc1.weight.copy_(self.critic.fc1.weight)      # copy.deepcopy, agents.py:107
         self.target_critic.fc2.weight.copy_(self.critic.fc2.weight)
 
@@ -130,6 +134,8 @@ class DHPAgent:
 
     def _hyper_rows(self):
         """(6, N) f64 per-episode hyper-parameter rows, or None when every value is a scalar."""
+        if self.hyper_rows_device is not None:
+            return self.hyper_rows_device
         vals = self._hyper_values()
         if not any(is_per_episode(v) for v in vals.values()):
             return None

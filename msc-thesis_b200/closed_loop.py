@@ -76,6 +76,62 @@ class ClosedLoop3DOF:
         self._retired = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
 
     # -- state ------------------------------------------------------------------------------------------
+    def init_episodes(self, seed, episode0=0, v_trim=None, sigma=None, episode_id=None, covariance=None):
+        """(Re-)initialise every episode on the device: what main_3dof.py:58-71 does before its loop -- trim and
+        reset of the environment, the first reference, RLS reset, N(0, nn_stdev) network weights with the target
+        critic a copy of the critic -- as ONE kernel (h3_init_episodes).  The draws of an episode depend on `seed`
+        and its GLOBAL index `episode0 + i` (or `episode_id[i]`) only, so a sharded job makes the same episodes as
+        an unsharded one.  v_trim: scalar or (N,) tensor; sigma: None (the agents' nn_stdev) or a (4, N) device
+        tensor [col actor, col critic, lon actor, lon critic]."""
+        env, rls = self.env, self.rls
+        n = self.n
+        ini = L.H3Init()
+        ini.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        ini.episode0 = int(episode0)
+        keep = []
+        if v_trim is None:
+            v_trim = 10.0
+        if torch.is_tensor(v_trim) and v_trim.numel() > 1:
+            vt = v_trim.to(device=self.device, dtype=torch.float64).contiguous()
+            keep.append(vt)
+            ini.v_trim_ep = vt.data_ptr()
+        else:
+            ini.v_trim = float(v_trim)
+        sg = (self.agent_col.nn_stdev_actor, self.agent_col.nn_stdev_critic, self.agent_lon.nn_stdev_actor,
+              self.agent_lon.nn_stdev_critic)
+        if sigma is not None and torch.is_tensor(sigma) and sigma.dim() == 2:
+            sg_t = sigma.to(device=self.device, dtype=torch.float64).contiguous()
+            if tuple(sg_t.shape) != (4, n):
+                raise ValueError("sigma: expected a (4, N) tensor")
+            keep.append(sg_t)
+            ini.sigma_ep = sg_t.data_ptr()
+            sg = (0.0, 0.0, 0.0, 0.0)
+        elif sigma is not None:
+            sg = tuple(float(x) for x in sigma)
+        for i in range(4):
+            ini.sigma[i] = float(sg[i])
+        ini.rls_cov0 = float(rls.covariance if covariance is None else covariance)
+        if episode_id is not None:
+            ids = episode_id.to(device=self.device, dtype=torch.int64).contiguous()
+            keep.append(ids)
+            ini.episode_id = ids.data_ptr()
+        self.n_active = n
+        cfg = self._config(L.REF_KERNEL)
+        b = self._batch(self.agent_col._hyper_rows(), self.agent_lon._hyper_rows())
+        L.check(L.lib().h3_init_episodes(byref(cfg), byref(b), C.byref(ini), L.stream_ptr(self.device)))
+        # host-side bookkeeping of the objects whose tensors were just rewritten
+        theta = env.trimmed_state[4].clone()
+        env.trimmed_state.copy_(env.state)
+        env.trimmed_state[4].copy_(theta)
+        env.t = 0
+        env.uniform_clock = True
+        rls.assume_symmetric = True
+        self.k = 0
+        self.order = torch.arange(n, device=self.device)
+        self._retired.zero_()
+        self._keep_init = keep              # inputs of an asynchronous launch stay alive until the next call
+        return self
+
     def set_heterogeneous(self):
         """Episodes no longer share tick index / clock (e.g. after loading per-episode snapshots): launches use
         each episode's own step counter and evaluate the sinusoid reference in the kernel."""
@@ -176,6 +232,9 @@ class ClosedLoop3DOF:
               env.step_count, env.flags, env.term_step, self.acc, self.order]
         if env.ref_params is not None:
             ts.append(env.ref_params)
+        for ag in (self.agent_col, self.agent_lon):
+            if ag.hyper_rows_device is not None:
+                ts.append(ag.hyper_rows_device)
         return ts
 
     def compact(self):
@@ -255,6 +314,8 @@ class ClosedLoop3DOF:
     def info(self, phase2=True):
         """Occupancy facts of the kernel variant run() would launch (block, smem, blocks/SM, registers)."""
         cfg = self._config(L.REF_TABLE)
+        if self.agent_col._hyper_rows() is not None or self.agent_lon._hyper_rows() is not None:
+            cfg.lon.tau = 0.5           # the query has no batch: any tau != 1 selects the per-episode-hyper variant
         vals = [C.c_int32() for _ in range(5)]
         L.check(L.lib().h3_closed_loop_info(byref(cfg), 1 if phase2 else 0, *[C.byref(v) for v in vals]))
         return dict(zip(("block", "smem_bytes", "blocks_per_sm", "regs", "lanes_per_warp"), (v.value for v in vals)))

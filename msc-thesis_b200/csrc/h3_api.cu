@@ -35,11 +35,9 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + SMALL_BLOCK 
 // ---------------------------------------------------------------------------------------------
 // Helicopter3DOF._trim (heli_models.py:293-328)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMALL_BLOCK) trim_kernel(H3EnvParams E, const double* __restrict__ v, double* trim,
-                                                           double* state, int64_t n, int64_t ld) {
-    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
-    if (e >= n) return;
-    const double vt = v[e];
+// one episode: trimmed [collective, cyclic] and the trimmed state [x z u w theta q lambda_i]
+__device__ __forceinline__ void trim_one(const H3EnvParams& E, double vt, double& collective, double& cyclic,
+                                         double (&st)[7]) {
     const double weight = E.mass * E.g;                                 // :302
     const double drag = 0.5 * E.rho * vt * vt * E.cds;                  // :303
     const double thrust = ::sqrt(drag * drag + weight * weight);        // :304
@@ -67,17 +65,149 @@ __global__ void __launch_bounds__(SMALL_BLOCK) trim_kernel(H3EnvParams E, const 
     const double r0 = -2.0 * mu * mu * drag / weight - 2.0 * mu * l;
     const double r1 = 4.0 / E.blade_solidity * c_t / E.cl_alpha + mu * drag / weight + l;
     const double det = a * d - b * c;
-    const double cyclic = (r0 * d - b * r1) / det;
-    const double collective = (a * r1 - c * r0) / det;
+    cyclic = (r0 * d - b * r1) / det;
+    collective = (a * r1 - c * r0) / det;
+    st[0] = 0.0;
+    st[1] = 0.0;
+    st[2] = vt * cf;
+    st[3] = vt * sf;
+    st[4] = theta_f;
+    st[5] = 0.0;
+    st[6] = l;
+}
+
+__global__ void __launch_bounds__(SMALL_BLOCK) trim_kernel(H3EnvParams E, const double* __restrict__ v, double* trim,
+                                                           double* state, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    double collective, cyclic, st[7];
+    trim_one(E, v[e], collective, cyclic, st);
     trim[e] = collective;
     trim[ld + e] = cyclic;
-    state[e] = 0.0;
-    state[ld + e] = 0.0;
-    state[2 * ld + e] = vt * cf;
-    state[3 * ld + e] = vt * sf;
-    state[4 * ld + e] = theta_f;
-    state[5 * ld + e] = 0.0;
-    state[6 * ld + e] = l;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) state[i * ld + e] = st[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// h3_init_episodes: every per-episode field at loop entry of main_3dof.py, from (seed, global episode index)
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a draw depends on (key, counter) only.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ double uniform53(uint32_t hi, uint32_t lo) {
+    const uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+    return ((double)m + 0.5) * 1.1102230246251565e-16;          // 2^-53
+}
+
+// standard normals (2 j, 2 j + 1) of `stream` for global episode `ep` (Box-Muller)
+__device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t ep, uint32_t stream, uint32_t j, double& z0,
+                                            double& z1) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ep, (uint32_t)(ep >> 32), stream, j),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const double u1 = uniform53(r.x, r.y), u2 = uniform53(r.z, r.w);
+    const double rad = ::sqrt(-2.0 * ::log(u1));
+    double sn, cs;
+    ::sincos(2.0 * 3.14159265358979323846 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// rows [row0, row0 + cnt) of a network block <- sigma * N(0, 1)
+template <typename NT>
+__device__ __forceinline__ void init_matrix(NT* net, int64_t ld, int64_t e, int row0, int cnt, uint64_t seed, uint64_t ep,
+                                            uint32_t stream, double sigma) {
+    for (int j = 0; 2 * j < cnt; ++j) {
+        double z0, z1;
+        normal_pair(seed, ep, stream, (uint32_t)j, z0, z1);
+        net[(int64_t)(row0 + 2 * j) * ld + e] = (NT)(sigma * z0);
+        if (2 * j + 1 < cnt) net[(int64_t)(row0 + 2 * j + 1) * ld + e] = (NT)(sigma * z1);
+    }
+}
+
+template <typename NT>
+__device__ __forceinline__ void init_agent(NT* net, int64_t ld, int64_t e, int nh, uint64_t seed, uint64_t ep, int agent,
+                                           double sig_a, double sig_c) {
+    init_matrix(net, ld, e, 0, 2 * nh, seed, ep, 4 * agent + 0, sig_a);             // actor fc1   agents.py:42-45
+    init_matrix(net, ld, e, 2 * nh, nh, seed, ep, 4 * agent + 1, sig_a);            // actor fc2
+    init_matrix(net, ld, e, 3 * nh, 2 * nh, seed, ep, 4 * agent + 2, sig_c);        // critic fc1  agents.py:19-22
+    init_matrix(net, ld, e, 5 * nh, 2 * nh, seed, ep, 4 * agent + 3, sig_c);        // critic fc2
+    for (int r = 0; r < 4 * nh; ++r)                                                // target = copy  agents.py:107
+        net[(int64_t)(7 * nh + r) * ld + e] = net[(int64_t)(3 * nh + r) * ld + e];
+}
+
+template <typename ET, typename NT>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    init_episodes_kernel(H3EnvParams E, EnvK<ET> K, H3Batch b, H3Init in, int task, double ref_amp, double ref_period,
+                         int nh_col, int nh_lon) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= b.n) return;
+    const int64_t ld = b.ld;
+    const uint64_t ep = in.episode_id != nullptr ? (uint64_t)in.episode_id[e] : (uint64_t)(in.episode0 + e);
+    // Helicopter3DOF.reset (heli_models.py:285-291)
+    double collective, cyclic, st[7];
+    trim_one(E, in.v_trim_ep != nullptr ? in.v_trim_ep[e] : in.v_trim, collective, cyclic, st);
+    double* trim = const_cast<double*>(b.trim);
+    trim[e] = collective;
+    trim[ld + e] = cyclic;
+    const_cast<double*>(b.theta_trim)[e] = st[4];
+    ET* state = (ET*)b.state;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) state[i * ld + e] = (ET)st[i];
+    b.t[e] = 0.0;
+    // ref = env.get_ref() before the loop (main_3dof.py:62; velocity task: integrates corr_u once)
+    ET* ref = (ET*)b.ref;
+    ET cu = (ET)0;
+    if (task == H3_TASK_SINUSOID) {
+        double amp = ref_amp, period = ref_period;
+        if (b.ref_par != nullptr) {
+            amp = b.ref_par[e];
+            period = b.ref_par[ld + e];
+        }
+        ref[e] = (ET)-0.0;
+        ref[ld + e] = (ET)sinusoid_ref(E.dt, amp, period);
+    } else if (task == H3_TASK_VELOCITY) {
+        ref[e] = (ET)0;
+        ref[ld + e] = velocity_ref(K, (ET)st[2], cu);
+    } else {
+        ref[e] = (ET)0;
+        ref[ld + e] = stop_over_point_ref(K, (ET)st[0], (ET)st[2], (ET)st[4]);
+    }
+    ((ET*)b.corr_u)[e] = cu;
+    ((ET*)b.pid_corr)[e] = (ET)0;                                       // PID.py:8
+    // RecursiveLeastSquares.reset (model.py:79-89)
+    ET* W = (ET*)b.rls_W;
+    for (int i = 0; i < 63; ++i) W[(int64_t)i * ld + e] = (ET)0;
+    ET* cov = (ET*)b.rls_cov;
+    for (int i = 0; i < 81; ++i) cov[(int64_t)i * ld + e] = (i % 10 == 0) ? (ET)in.rls_cov0 : (ET)0;
+    for (int i = 0; i < 7; ++i) ((ET*)b.rls_x)[(int64_t)i * ld + e] = (ET)0;
+    ((ET*)b.rls_u)[e] = (ET)0;
+    ((ET*)b.rls_u)[ld + e] = (ET)0;
+    b.rls_skip[e] = 1;
+    // DHPAgent.__init__ (agents.py:104-107)
+    double sg[4] = {in.sigma[0], in.sigma[1], in.sigma[2], in.sigma[3]};
+    if (in.sigma_ep != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sg[i] = in.sigma_ep[(int64_t)i * ld + e];
+    }
+    init_agent((NT*)b.col_net, ld, e, nh_col, in.seed, ep, 0, sg[0], sg[1]);
+    init_agent((NT*)b.lon_net, ld, e, nh_lon, in.seed, ep, 1, sg[2], sg[3]);
+    // bookkeeping (main_3dof.py:122)
+    b.step[e] = 0;
+    b.flags[e] = 0;
+    b.term_step[e] = -1;
+    b.acc[e] = 0.0;
+    b.acc[ld + e] = 0.0;
+    b.acc[2 * ld + e] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,6 +992,48 @@ int h3_fma_peak(int32_t dtype, int32_t iters, void* scratch_out, double* flops_o
         fma_peak_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (float*)scratch_out);
     if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
     return check_launch("fma_peak_kernel");
+}
+
+int h3_init_episodes(const H3Config* cfg, const H3Batch* b, const H3Init* init, void* stream) {
+    if (!cfg || !b || !init) {
+        set_error("h3_init_episodes: null argument");
+        return H3_E_ARG;
+    }
+    if (!b->state || !b->t || !b->ref || !b->corr_u || !b->trim || !b->theta_trim || !b->pid_corr || !b->rls_W ||
+        !b->rls_cov || !b->rls_x || !b->rls_u || !b->rls_skip || !b->col_net || !b->lon_net || !b->step ||
+        !b->flags || !b->term_step || !b->acc || b->ld < b->n) {
+        set_error("h3_init_episodes: H3Batch has a null field or ld < n");
+        return H3_E_ARG;
+    }
+    if (cfg->task < 0 || cfg->task > 2 || !agent_desc_ok(cfg->col) || !agent_desc_ok(cfg->lon) ||
+        !dtype_ok(cfg->env_dtype) || !dtype_ok(cfg->net_dtype)) {
+        set_error("h3_init_episodes: bad configuration");
+        return H3_E_ARG;
+    }
+    if (b->n <= 0) return H3_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = grid_for(b->n);
+    switch (precision_pair(cfg)) {
+        case 0:
+            init_episodes_kernel<double, double><<<grid, SMALL_BLOCK, 0, st>>>(
+                cfg->env, make_envk<double>(*cfg), *b, *init, cfg->task, cfg->ref_amp, cfg->ref_period, cfg->col.n_hidden,
+                cfg->lon.n_hidden);
+            break;
+        case 1:
+            init_episodes_kernel<double, float><<<grid, SMALL_BLOCK, 0, st>>>(
+                cfg->env, make_envk<double>(*cfg), *b, *init, cfg->task, cfg->ref_amp, cfg->ref_period, cfg->col.n_hidden,
+                cfg->lon.n_hidden);
+            break;
+        case 2:
+            init_episodes_kernel<float, float><<<grid, SMALL_BLOCK, 0, st>>>(
+                cfg->env, make_envk<float>(*cfg), *b, *init, cfg->task, cfg->ref_amp, cfg->ref_period, cfg->col.n_hidden,
+                cfg->lon.n_hidden);
+            break;
+        default:
+            set_error("h3_init_episodes: unsupported precision pair");
+            return H3_E_UNSUPPORTED;
+    }
+    return check_launch("init_episodes_kernel");
 }
 
 int h3_tmem_probe(int32_t warps, int32_t blocks, int32_t reps, double* out, int64_t* cycles, void* stream) {

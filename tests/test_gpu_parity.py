@@ -389,25 +389,26 @@ def test_sweep_is_shard_independent(h3):
     """main.py-style sweep: per-setting success counts / scores must not depend on how the expanded
     (setting, seed) list is sharded over ranks."""
     grid = {"tau_target_critic": [0.01, 1.0], "learning_rate_actor": [0.1, 0.4], "nn_stdev": [0.1, 0.2]}
-    keys, settings, setting_of, seed_of = h3.sweep.expand_grid(grid, n_seeds=6)
-    n = len(setting_of)
-    kw = dict(switch_step=60, score_window=(20, 120), ticks_per_launch=40)
-    whole = h3.sweep.build_sweep_loop(keys, settings, setting_of, seed_of, 0, n, **kw)
-    whole.run(120)
-    res = h3.sweep.sweep_results(whole, setting_of, len(settings), 100)
+    kw = dict(grid=grid, n_seeds=6, n_ticks=120, device="cuda", switch_step=60, score_window=(20, 120), ticks_per_launch=40,
+              seed=5)
+    keys, settings, res, whole = h3.sweep.run_sweep(**kw)
+    n = 8 * 6
     parts = []
     for r in range(3):
         lo, hi = h3.shard_range(n, r, 3)
-        lp = h3.sweep.build_sweep_loop(keys, settings, setting_of, seed_of, lo, hi, **kw)
-        lp.run(120)
+        _, _, part, lp = h3.sweep.run_sweep(rank=r, world_size=3, **kw)
         assert torch.equal(lp.env.state, whole.env.state[:, lo:hi])
         assert torch.equal(lp.acc, whole.acc[:, lo:hi])
-        parts.append(h3.sweep.sweep_results(lp, setting_of[lo:hi], len(settings), 100))
+        parts.append(part)
     assert np.array_equal(sum(p["n"] for p in parts), res["n"]) and res["n"].sum() == n
     assert np.array_equal(sum(p["success"] for p in parts), res["success"])
     assert np.all(res["success"] <= res["n"]) and np.isfinite(res["mean_score_of_successes"][res["success"] > 0]).all()
     st = whole.stats()
     assert st["n"] == n and st["n_alive"] == res["success"].sum()
+    # the swept values reach the cyclic agent only (main.py:56-62 sets them on ac_params['lon'])
+    rows = whole.agent_lon.hyper_rows_device.cpu().numpy()
+    assert sorted(set(rows[3])) == [0.01, 1.0] and sorted(set(rows[1])) == [0.1, 0.4]
+    assert set(whole.agent_col.hyper_rows_device.cpu().numpy()[3]) == {0.01}
 
 
 @pytest.mark.parametrize("n", [1, 15, 17, 31, 33, 250])

@@ -322,13 +322,17 @@ def test_launch_plan_splits_at_the_phase_switch():
 
 
 def test_sweep_grid_and_compat_modules():
-    keys, settings, setting_of, seed_of = h3.sweep.expand_grid({"a": [1, 2, 3], "b": [10, 20]}, n_seeds=4)
-    assert keys == ["a", "b"] and settings.shape == (6, 2) and len(setting_of) == 24
-    assert list(settings[1]) == [1, 20] and list(setting_of[:5]) == [0, 0, 0, 0, 1] and list(seed_of[:5]) == [0, 1, 2, 3, 0]
-    # per-episode draws depend on (seed, salt) only, not on the shard they are generated in
-    a = h3.sweep._normal((3, 2), np.arange(10), 5)
-    b = h3.sweep._normal((3, 2), np.arange(4, 10), 5)
-    assert torch.equal(a[..., 4:], b)
+    keys, settings, n_total = h3.sweep.expand_grid({"a": [1, 2, 3], "b": [10, 20]}, n_seeds=4)
+    assert keys == ["a", "b"] and settings.shape == (6, 2) and n_total == 24
+    assert list(settings[1]) == [1, 20]
+    # the parameter block of a shard is a slice of the whole job's block (setting = global index // n_seeds)
+    k2, s2, n2 = h3.sweep.expand_grid({"tau_target_critic": [0.01, 1.0], "nn_stdev": [0.1, 0.2, 0.4]}, n_seeds=5)
+    whole, so = h3.sweep.sweep_params(k2, s2, 5, 0, n2, "cpu")
+    part, so_p = h3.sweep.sweep_params(k2, s2, 5, 7, 19, "cpu")
+    assert torch.equal(part, whole[:, 7:19]) and torch.equal(so_p, so[7:19]) and list(so[:6]) == [0, 0, 0, 0, 0, 1]
+    R = h3.episodes.ROW
+    assert set(whole[R["lon_tau"]].tolist()) == {0.01, 1.0} and set(whole[R["col_tau"]].tolist()) == {0.01}
+    assert set(whole[R["sigma_lon_critic"]].tolist()) == {0.1, 0.2, 0.4} and set(whole[R["sigma_col_actor"]].tolist()) == {0.1}
     # the reference's module names resolve to the batched classes when compat/ is on sys.path
     import importlib
     import sys
