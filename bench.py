@@ -4,15 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE config 3): 1,048,576 episodes PER GPU (weak scaling), each the
-main_3dof.py scenario (trim 10 m/s, sinusoid task, RLS 9x7 gamma=1 cov0=1e4, agents of main_3dof.py:20-46,
-weights ~ N(0, sigma_w)), excitation.npy applied for ticks < 1000.  One bench "step" = ONE fused kernel
-launch that advances every episode by --ticks ticks.  The phase switch (main_3dof.py:127-137: PID
-collective -> collective agent) is placed at the midpoint of the timed region, so the timed steps are half
-phase-1 launches and half phase-2 launches like the reference's 6000 + 6000 ticks; per-phase rates are
-reported next to the whole-region value.  env-steps are COUNTED (sum of per-episode tick counters from the
-kernel's statistics epilogue), so terminated episodes stop counting.
+Workload (BASELINE config 3): 1,048,576 episodes PER GPU (weak scaling), each ONE WHOLE RUN of
+main_3dof.py: trim at 10 m/s, sinusoid task, RLS 9x7 gamma=1 cov0=1e4, agents of main_3dof.py:20-46 with weights
+~ N(0, nn_stdev) drawn on the device from (job seed, global episode index), excitation.npy applied for ticks < 1000,
+12,000 ticks with the PID -> collective-agent switch at tick 6000, episodes that diverge stop at their tick like the
+reference's `break` (main_3dof.py:192-197).  One bench "step" = one such batch of whole episodes: h3_init_episodes,
+then 12 fused launches of 1000 ticks (live episodes are moved to the front between launches), then the all-reduce of
+the statistics vector.  env-steps are COUNTED by the kernels (terminated episodes stop counting).
+
+    value : inputs (per-episode parameters) resident in HBM
+    e2e   : the same step through the public API (EpisodeRunner.run) from pinned HOST buffers -- parameters up,
+            per-episode returns / flags / termination ticks and the statistics down, every step
 """
+
 import argparse
 import importlib
 import json
@@ -40,11 +44,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=1 << 20, help="episodes per GPU")
-    ap.add_argument("--ticks", type=int, default=200, help="ticks per launch (= per bench step)")
+    ap.add_argument("--ticks", type=int, default=12000, help="ticks per episode (= per bench step)")
+    ap.add_argument("--launch-ticks", type=int, default=1000, help="ticks per kernel launch")
+    ap.add_argument("--switch", type=int, default=6000, help="tick at which the collective agent takes over")
+    ap.add_argument("--compact-every", type=int, default=1000, help="move live episodes to the front every K ticks (0: never)")
     ap.add_argument("--precision", default="f64", choices=["f64", "mixed", "f32"])
-    ap.add_argument("--store", type=int, default=0, help="0 default, 1 local arrays, 2 shared-memory tile")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=16384, help="CPU sample: episodes (per host thread for "
@@ -99,6 +105,28 @@ def cpu_numpy_oracle_rate(n, n_ticks):
     return float(S["step"].sum()) / dt, dt
 
 
+def _np_worker(args):
+    n, n_ticks, seed = args
+    from oracle import heli3dof_np as O
+    S, cfg = _cpu_workload(n, n_ticks, seed=seed)
+    O.run(S, cfg, n_ticks, "all64")
+    return float(S["step"].sum())
+
+
+def cpu_numpy_all_cores_rate(n_per_proc, n_ticks):
+    """the NumPy oracle on every host core, one process per core over seeds (what main.py:67-70
+    does with multiprocessing.Pool)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_np_worker, [(32, 4, 0)] * cores)            # start the workers, import numpy
+        t0 = time.perf_counter()
+        steps = pool.map(_np_worker, [(n_per_proc, n_ticks, i) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    return sum(steps) / dt, dt, cores
+
+
 def run_reference_arm(a):
     """--impl reference: the reference's algorithm for this path on the host cores.  The reference is
     pure Python (NumPy + torch-CPU autograd, 400-485 ticks/s per core in the build container)
@@ -123,8 +151,7 @@ def run_reference_arm(a):
         "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config3: 3-DOF closed-loop training (RLS incremental model + IDHP actor-critic "
-                               "online update), bounded CPU sample", "sample": sample},
+        "config": {"workload": WORKLOAD % a.episodes + " -- bounded CPU sample of it", "sample": sample},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -283,6 +310,134 @@ def fma_peak(h3, torch, dtype_code, device):
     return best
 
 
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm: whole episodes
+# ---------------------------------------------------------------------------------------------------------
+class LaunchLog:
+    """Per-launch CUDA events and the kernel's own tick counter after every launch of one bench step."""
+
+    def __init__(self, torch, n_launches, device):
+        self.t0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_launches)]
+        self.t1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_launches)]
+        self.ticks = torch.zeros(n_launches + 1, dtype=torch.float64, device=device)    # cumulative sum_ticks
+        self.first_tick = [0] * n_launches
+
+
+def run_step(runner, seed, episode0, n_ticks, launch_ticks, compact_every, log=None):
+    """One bench step on device-resident parameters: init + n_ticks ticks in launches of launch_ticks."""
+    from msc_thesis_b200.episodes import ROW
+    lp = runner.loop
+    lp.init_episodes(seed, episode0=episode0, v_trim=runner.params[ROW["v_trim"]],
+                     sigma=runner.params[ROW["sigma_col_actor"]:ROW["sigma_lon_critic"] + 1])
+    done = i = 0
+    while done < n_ticks:
+        m = min(launch_ticks, n_ticks - done)
+        if log is not None:
+            log.first_tick[i] = done
+            log.t0[i].record()
+        lp.run(m)
+        if log is not None:
+            log.t1[i].record()
+            log.ticks[i + 1].copy_(lp.stats_dev[7])
+        done += m
+        i += 1
+        if compact_every and done % compact_every == 0 and done < n_ticks:
+            lp.compact()
+    lp.allreduce_stats()                # the only collective of the path: per-batch statistics (NCCL all-reduce)
+    return i
+
+
+def phase_summary(logs, switch, flops):
+    """Per-phase totals over the timed steps of this rank: launch milliseconds and counted env-steps."""
+    out = {}
+    for name, sel in (("phase1", lambda k: k < switch), ("phase2", lambda k: k >= switch)):
+        ms = steps = 0.0
+        nl = 0
+        for lg in logs:
+            tk = lg.ticks.cpu().numpy()
+            for i, k0 in enumerate(lg.first_tick):
+                if sel(k0):
+                    ms += lg.t0[i].elapsed_time(lg.t1[i])
+                    steps += tk[i + 1] - tk[i]
+                    nl += 1
+        out[name] = {"launches": nl, "ms": ms, "env_steps": steps,
+                     "env_steps_per_s": steps / (ms * 1e-3) if ms > 0 else None,
+                     "tflops": steps * flops[name] / (ms * 1e-3) / 1e12 if ms > 0 else None}
+    return out
+
+
+def launch_table(logs):
+    """Per launch index, averaged over the timed steps of this rank: first tick, milliseconds, counted env-steps."""
+    rows = []
+    tks = [lg.ticks.cpu().numpy() for lg in logs]
+    for i, k0 in enumerate(logs[0].first_tick):
+        ms = float(np.mean([lg.t0[i].elapsed_time(lg.t1[i]) for lg in logs]))
+        st = float(np.mean([tk[i + 1] - tk[i] for tk in tks]))
+        rows.append({"first_tick": k0, "ms": round(ms, 3), "env_steps": st, "env_steps_per_s": st / (ms * 1e-3)})
+    return rows
+
+
+def timed_whole_episodes(torch, dist, runner, a, world, rank, device, steps, warmup, params_host=None, results_host=None):
+    """W warm-up + K timed whole-episode steps.  params_host given: the e2e form (EpisodeRunner.run from pinned host
+    buffers).  Returns (total env-steps of the job, max-over-ranks milliseconds, per-step logs, all-reduced statistics)."""
+    n = runner.n
+    nl = (a.ticks + a.launch_ticks - 1) // a.launch_ticks
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def one(i, log):
+        seed = 1000 + i
+        if params_host is None:
+            run_step(runner, seed, rank * n, a.ticks, a.launch_ticks, a.compact_every, log)
+        else:
+            runner.run(params_host, results_host, seed, n_ticks=a.ticks, episode0=rank * n, compact_every=a.compact_every)
+            runner.loop.allreduce_stats()
+
+    for i in range(warmup):
+        one(i, None)
+    barrier()
+    logs = [LaunchLog(torch, nl, device) for _ in range(steps)] if params_host is None else [None] * steps
+    stats_log = torch.zeros(steps, 8, dtype=torch.float64, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        one(warmup + i, logs[i])
+        stats_log[i].copy_(runner.loop.stats_dev)          # all-reduced: whole-job values on every rank
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    st = stats_log.cpu().numpy()
+    assert np.all(st[:, 0] == world * n), "all-reduced episode count %r != %d ranks x %d episodes" % (st[:, 0], world, n)
+    return float(st[:, 7].sum()), float(ms.item()), logs, st
+
+
+def whole_episode_rate(torch, runner, a, device, passes=2, seed0=500):
+    """Device-resident whole-episode env-steps/s of a runner on this rank (extras: other precisions / configs)."""
+    run_step(runner, seed0, 0, a.ticks, a.launch_ticks, a.compact_every)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 0.0
+    e0.record()
+    for i in range(passes):
+        run_step(runner, seed0 + 1 + i, 0, a.ticks, a.launch_ticks, a.compact_every)
+        steps += float(runner.loop.stats_dev[7].item())
+    e1.record()
+    torch.cuda.synchronize(device)
+    st = runner.loop.stats()
+    return steps / (e0.elapsed_time(e1) * 1e-3), st
+
+
+WORKLOAD = ("config3: 3-DOF closed-loop training (RLS incremental model + IDHP actor-critic online update), %d whole "
+            "main_3dof.py episodes per GPU")
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -291,6 +446,7 @@ def main():
     import torch
     import torch.distributed as dist
     import msc_thesis_b200 as h3
+    from msc_thesis_b200 import episodes as EP
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -301,172 +457,200 @@ def main():
     device = torch.device("cuda", local)
     numa_cpus = None
     if world > 1 and os.environ.get("H3_NUMA_BIND", "1") != "0":
-        # one process per GPU: keep this rank (and the pinned host buffers of the e2e leg) on the GPU's NUMA node
         numa_cpus = h3.distributed.bind_to_gpu_numa_node(local)
     if world > 1:
-        if "H3_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+        # NCCL's INFO lines (communicator, rank count, NVLS) are what shows that the collective ran on N ranks: leave
+        # NCCL_DEBUG to the caller; if it is unset, ask for the init lines and send them to stderr (stdout carries the
+        # JSON line, printed last)
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     h3.lib()
 
-    n, T, K, W = a.episodes, a.ticks, a.steps, a.warmup
-    loop = make_workload(h3, torch, n, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
-    # phase switch at the midpoint of the timed region
-    k_switch = (W + K // 2) * T
-    loop.switch_step = k_switch
-    info1, info2 = loop.info(phase2=False), loop.info(phase2=True)
+    n, K, W = a.episodes, a.steps, a.warmup
+    runner = h3.EpisodeRunner(n, device=device, precision=a.precision, per_episode_hyper=False, switch_step=a.switch,
+                              score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
+    params_host = EP.default_params(n, pin=True)
+    runner.params.copy_(params_host)
+    info1, info2 = runner.loop.info(phase2=False), runner.loop.info(phase2=True)
 
-    def barrier():
-        torch.cuda.synchronize(device)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(device)
-
-    for _ in range(W):
-        loop.run(T)
-    barrier()
-    ticks_before = loop.stats()["sum_ticks"]
     sampler = ClockSampler(local) if rank == 0 else None
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    barrier()
-    evs[0].record()
-    for i in range(K):
-        loop.run(T)
-        evs[i + 1].record()
-    loop.allreduce_stats()              # the only collective of the path: per-batch statistics (NCCL)
-    barrier()
+    env_steps, ms_max, logs, st = timed_whole_episodes(torch, dist, runner, a, world, rank, device, K, W)
     clocks = sampler.stop() if sampler is not None else None
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
-    total_ms = evs[0].elapsed_time(evs[K])
-    stats_all = dict(zip(h3._lib.STATS_FIELDS, loop.stats_dev.cpu().tolist()))
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tb = torch.tensor([ticks_before], dtype=torch.float64, device=device)
-        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-        ticks_before = float(tb.item())
-    total_ms_max = float(tmax.item())
-    env_steps = stats_all["sum_ticks"] - ticks_before            # whole job, counted by the kernels
-    value = env_steps / (total_ms_max * 1e-3)
-
-    # per-phase numbers on this rank (per-launch CUDA events)
-    half = K // 2
-    alive_frac = stats_all["n_alive"] / max(stats_all["n"], 1.0)
-    p1_ms = float(np.mean(step_ms[:half])) if half else None
-    p2_ms = float(np.mean(step_ms[half:]))
-    rate1 = n * T / (p1_ms * 1e-3) if half else None
+    value = env_steps / (ms_max * 1e-3)
+    n_launch = sum(len(lg.first_tick) for lg in logs)
 
     out = None
     if rank == 0:
-        # ---- roofline of the dominant (only) kernel: FP64/FP32 pipe; HBM beside it ----
+        flops = {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2}
+        ph = phase_summary(logs, a.switch, flops)
         code = h3._lib.H3_F32 if a.precision == "f32" else h3._lib.H3_F64
         peak = fma_peak(h3, torch, code, device)
-        flops_step = n * T * (FLOP_PHASE1 * half + FLOP_PHASE2 * (K - half)) / K      # nominal per launch
-        exec_frac = env_steps / (world * n * T * K)
-        launch_s = float(np.mean(step_ms)) * 1e-3
-        achieved = flops_step * exec_frac / launch_s
         word = 4 if a.precision == "f32" else 8
-        bytes_launch = 2.0 * STATE_WORDS * word * n
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak, hbm_src = 6650.0, "fallback"
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
-        # DRAM traffic and pipe utilisation of the same kernels from the committed ncu capture (per episode)
         traffic, ncu_note = None, None
         tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tfile) and a.precision == "f64":
             tj = json.load(open(tfile))
-            per_ep = (tj["phase1"]["dram_bytes_per_episode"] * half + tj["phase2"]["dram_bytes_per_episode"] * (K - half)) / K
-            traffic = per_ep * n
-            ncu_note = {"source": tj.get("source"), "fp64_pipe_active_pct": {"phase1": tj["phase1"]["fp64_pipe_active_pct"],
-                                                                             "phase2": tj["phase2"]["fp64_pipe_active_pct"]},
-                        "dram_throughput_pct": {"phase1": tj["phase1"]["dram_throughput_pct"],
-                                                "phase2": tj["phase2"]["dram_throughput_pct"]}}
-        roofline = {"bound": "fp64" if a.precision != "f32" else "fp32", "achieved": achieved / 1e12,
-                    "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            traffic = tj["phase2"]["dram_bytes_per_episode"] * n
+            ncu_note = {"source": tj.get("source"), "kernel": tj["phase2"].get("kernel"),
+                        "fp64_pipe_active_pct": tj["phase2"]["fp64_pipe_active_pct"],
+                        "issue_active_pct": tj["phase2"].get("issue_active_pct"),
+                        "dram_throughput_pct": tj["phase2"]["dram_throughput_pct"],
+                        "phase1_kernel": {k: tj["phase1"][k] for k in ("fp64_pipe_active_pct", "dram_throughput_pct")}}
+        # the dominant kernel: the tensor-memory kernel of the launches in which both agents learn (ticks >= switch)
+        dom = "phase2" if ph["phase2"]["launches"] else "phase1"
+        ach = ph[dom]["tflops"] * 1e12
+        launch_s = ph[dom]["ms"] * 1e-3 / max(ph[dom]["launches"], 1)
+        bytes_launch = 2.0 * STATE_WORDS * word * n
+        total_tf = (ph["phase1"]["env_steps"] * FLOP_PHASE1 + ph["phase2"]["env_steps"] * FLOP_PHASE2) / (
+            (ph["phase1"]["ms"] + ph["phase2"]["ms"]) * 1e-3) / 1e12
+        roofline = {"bound": "fp64" if a.precision != "f32" else "fp32", "achieved": ach / 1e12, "peak": peak / 1e12,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                    "kernel": "closed_loop_tm_kernel (launches with ticks >= switch_step: both agents learn)" if dom == "phase2"
+                              else "closed_loop_kernel (PID collective)",
+                    "avg_launch_ms": launch_s * 1e3, "share_of_kernel_time": ph[dom]["ms"] / (ph["phase1"]["ms"] + ph["phase2"]["ms"]),
                     "ncu": ncu_note,
                     "peak_source": "FMA-chain microbenchmark in this run (h3_fma_peak, 2 flop/FMA)",
                     "flops_per_env_step": {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2,
-                                           "note": "literal reference operator count; transcendental calls "
+                                           "note": "literal reference operator count (SURVEY.md 8d); transcendental calls "
                                                    "(46 / 86 per tick) not folded in"},
+                    "other_kernel": {"kernel": "closed_loop_kernel (ticks < switch_step: PID collective)",
+                                     "achieved": ph["phase1"]["tflops"], "frac": (ph["phase1"]["tflops"] or 0) * 1e12 / peak},
+                    "whole_step": {"achieved": total_tf, "frac": total_tf * 1e12 / peak},
                     "hbm": {"achieved": bytes_launch / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": bytes_launch / launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-                            "bytes_per_env_step": 2.0 * STATE_WORDS * word / T}}
+                            "bytes_per_env_step": 2.0 * STATE_WORDS * word / a.launch_ticks}}
+        stats_last = dict(zip(h3._lib.STATS_FIELDS, st[-1].tolist()))
         out = {
             "metric": "closed-loop env-steps/sec (model+RLS+actor-critic)", "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"f64": "f64", "mixed": "f64 model/RLS + f32 networks", "f32": "f32"}[a.precision],
             "data": "synthetic",
-            "config": {"workload": "config3: 3-DOF closed-loop training (RLS incremental model + IDHP actor-critic "
-                                   "online update), %d episodes per GPU" % n,
-                       "episodes_per_gpu": n, "ticks_per_launch": T, "switch_step": k_switch,
-                       "phase_mix": "%d phase-1 + %d phase-2 launches timed" % (half, K - half),
+            "config": {"workload": WORKLOAD % n, "episodes_per_gpu": n, "ticks_per_episode": a.ticks,
+                       "ticks_per_launch": a.launch_ticks, "switch_step": a.switch, "compact_every": a.compact_every,
+                       "step": "h3_init_episodes + %d fused launches + statistics all-reduce" % (n_launch // max(K, 1)),
                        "excitation": "excitation.npy closed form, ticks < 1000", "nh_lon": 6, "nh_col": 10,
                        "l2": "inputs (%.2f GB of episode state per GPU) larger than L2" % (bytes_launch / 2e9),
                        "kernel_phase1": info1, "kernel_phase2": info2},
-            "phase1_env_steps_per_s_rank0": rate1, "phase2_ms_per_launch_rank0": p2_ms,
-            "phase1_ms_per_launch_rank0": p1_ms, "alive_fraction_end": alive_frac,
-            "env_steps_timed": env_steps, "stats": stats_all,
-            "roofline": roofline, "clocks": clocks, "gpu_launches": K,
+            "phases_rank0": ph, "launches_rank0": launch_table(logs), "alive_fraction_end": stats_last["n_alive"] / max(stats_last["n"], 1.0),
+            "env_steps_timed": env_steps, "stats_last_step_all_ranks": stats_last,
+            "allreduced_n": int(st[-1, 0]), "roofline": roofline, "clocks": clocks,
+            "gpu_launches": n_launch + K,           # fused launches + one init kernel per step (rank 0)
             "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
         }
 
-    # ---- e2e: same metric through the public API from HOST buffers (H2D + launch + D2H every step) ----
-    # The batch lives in pinned host memory as `n_chunks` chunks; h3.HostBatchPipeline streams them through two
-    # device slots on two CUDA streams, so uploads, launches and downloads overlap.
+    # ---- e2e: the same step through the public API from pinned HOST buffers ----
     if not a.no_e2e:
-        del loop
-        torch.cuda.empty_cache()
-        n_chunks = a.e2e_chunks
-        chunk = n // n_chunks
-
-        k_e2e = W * T                       # the host batch is the state after the same untimed warm-up ticks
-
-        def make(nc):
-            lp = make_workload(h3, torch, nc, a.precision, device, seed=1 + rank, store=a.store, ticks=T)
-            lp.switch_step = k_e2e + T // 2
-            return lp
-
-        pipe = h3.HostBatchPipeline(make, chunk, n_slots=2)
-        for _ in range(W):
-            pipe.slots[0].run(T)
-        pipe.k0, pipe.t0 = pipe.slots[0].k, pipe.slots[0].env.t
-        ticks_at_start = float(pipe.slots[0].stats()["sum_ticks"])
-        host_chunks = pipe.host_chunks_from(pipe.slots[0], n_chunks)
-        host_results = pipe.result_buffers(n_chunks)
-        h2d = sum(t.numel() * t.element_size() for ch in host_chunks for t in ch)
-        d2h = sum(t.numel() * t.element_size() for ch in host_results for t in ch)
-        for _ in range(max(1, min(W, 2))):
-            pipe.run(host_chunks, host_results, T)
-        barrier()
-        ke = max(2, min(K, 4))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(ke):
-            pipe.run(host_chunks, host_results, T)
-        e1.record()
-        barrier()
-        # sum_ticks of every chunk minus the ticks the host batch had already run, ke passes
-        steps_e2e = sum(float(r[4][7].item()) - ticks_at_start for r in host_results) * ke
-        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-        se = torch.tensor([steps_e2e], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        results_host = runner.result_buffers(pin=True)
+        ke = max(1, min(K, a.e2e_steps))
+        steps_e2e, ms_e2e, _, st_e = timed_whole_episodes(torch, dist, runner, a, world, rank, device, ke, 1,
+                                                          params_host=params_host, results_host=results_host)
+        torch.cuda.synchronize(device)
+        host_steps = float(results_host[1][2].double().sum().item())     # per-episode tick counters that came back
+        assert host_steps == float(results_host[2][7].item()) or world > 1
         if rank == 0:
-            out["e2e"] = {"value": float(se.item()) / (float(ems.item()) * 1e-3), "unit": "env-steps/s",
-                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-                          "ms_per_step": float(ems.item()) / ke,
-                          "what": "pinned host batch (%d chunks of %d episodes, state after %d warm-up ticks) -> "
-                                  "device, one %d-tick launch per chunk (ticks %d-%d, switch at %d), per-episode "
-                                  "returns/flags/term_step/step + statistics -> host; 2 device slots on 2 streams "
-                                  "(copies overlap launches)"
-                                  % (n_chunks, chunk, k_e2e, T, k_e2e, k_e2e + T, k_e2e + T // 2)}
-        del pipe
+            out["e2e"] = {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s",
+                          "h2d_bytes_per_step": runner.h2d_bytes(n), "d2h_bytes_per_step": runner.d2h_bytes(n), "steps": ke,
+                          "ms_per_step": ms_e2e / ke,
+                          "what": "EpisodeRunner.run: pinned host block of per-episode parameters (19 doubles: trim speed, "
+                                  "reference amplitude / period, 4 nn_stdev, 2 x 6 hyper-parameters) -> device, "
+                                  "h3_init_episodes, %d ticks (switch at %d), per-episode returns / score sum / flags / "
+                                  "term_step / step + the statistics vector -> pinned host; per GPU" % (a.ticks, a.switch)}
+    del runner
+    torch.cuda.empty_cache()
 
-    # ---- extras (rank 0, N == 1): BASELINE config 2, open-loop model step only, 65,536 episodes ----
+    # ---- extras, at every N (every rank takes part; rank 0 reports) ----
+    if not a.no_extras:
+        extras = {}
+        # BASELINE config 4: hyper-parameter / seed sweep, per-episode (tau, nn_stdev, gamma, lr_a, lr_c) on the cyclic agent
+        # from the main.py:107-112 grid (405 settings), 1,048,576 episodes per GPU, per-setting sums all-reduced
+        try:
+            S = h3.sweep
+            keys, settings, _ = S.expand_grid(S.DEFAULT_GRID, 1)
+            n_total = world * n
+            n_seeds = -(-n_total // len(settings))
+            swr = h3.EpisodeRunner(n, device=device, precision=a.precision, per_episode_hyper=True, switch_step=a.switch,
+                                   score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
+            kw = dict(grid=S.DEFAULT_GRID, n_seeds=n_seeds, n_total=n_total, n_ticks=a.ticks, rank=rank, world_size=world,
+                      compact_every=a.compact_every, runner=swr)
+            S.run_sweep(seed=1, **kw)
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, _, res, lp = S.run_sweep(seed=2, **kw)
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms4 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+            st4 = dict(zip(h3._lib.STATS_FIELDS, lp.stats_dev.cpu().tolist()))
+            assert st4["n"] == n_total and res["n"].sum() == n_total
+            best = int(np.nanargmax(res["success"] / np.maximum(res["n"], 1)))
+            rate4 = st4["sum_ticks"] / (float(ms4.item()) * 1e-3)
+            extras["config4_sweep"] = {
+                "episodes": n_total, "episodes_per_gpu": n, "settings": len(settings), "seeds_per_setting": n_seeds,
+                "ticks": a.ticks, "env_steps_per_s": rate4, "ms": float(ms4.item()), "allreduced_n": int(st4["n"]),
+                "kernel_phase2": lp.info(phase2=True), "success_rate_overall": st4["n_alive"] / st4["n"],
+                "best_setting": dict(zip(keys, settings[best].tolist())),
+                "best_setting_success_rate": float(res["success"][best] / max(res["n"][best], 1)),
+                "roofline_frac_whole_run": None,
+                "what": "per-episode hyper-parameter rows (SWEEP kernel variants), device-side init from (seed, global "
+                        "episode index), per-setting success / score sums all-reduced (NCCL)"}
+            del swr, lp
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            extras["config4_sweep"] = {"error": repr(exc)}
+        # BASELINE config 5: long-horizon episodes with randomised trims and reference signals, fp64 vs fp32; a 10,000-tick
+        # window of the 100k-tick episodes, 2,097,152 episodes per GPU (16M across 8)
+        try:
+            n5, ticks5 = 2 * n, 10000
+            c5 = {"episodes_per_gpu": n5, "episodes": world * n5, "ticks_window": ticks5,
+                  "what": "v_trim ~ U(5, 25) m/s, reference amplitude and period ~ U(5, 15) per episode (reference evaluated in "
+                          "the kernel), switch at %d, live episodes compacted every %d ticks" % (a.switch, a.compact_every)}
+            for prec in ("f64", "f32"):
+                r5 = h3.EpisodeRunner(n5, device=device, precision=prec, per_episode_hyper=False, switch_step=a.switch,
+                                      score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
+                g = torch.Generator(device=device).manual_seed(77 + rank)
+                p5 = EP.default_params(1).to(device).expand(-1, n5).clone()
+                p5[EP.ROW["v_trim"]] = 5 + 20 * torch.rand(n5, generator=g, device=device, dtype=torch.float64)
+                p5[EP.ROW["ref_amplitude"]] = 5 + 10 * torch.rand(n5, generator=g, device=device, dtype=torch.float64)
+                p5[EP.ROW["ref_period"]] = 5 + 10 * torch.rand(n5, generator=g, device=device, dtype=torch.float64)
+                r5.params.copy_(p5)
+                r5.loop.env.ref_params = r5.params[EP.ROW["ref_amplitude"]:EP.ROW["ref_period"] + 1]
+                a5 = argparse.Namespace(**{**vars(a), "ticks": ticks5})
+                run_step(r5, 5, rank * n5, 1000, a.launch_ticks, a.compact_every)       # warm-up launch
+                torch.cuda.synchronize(device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run_step(r5, 6, rank * n5, ticks5, a.launch_ticks, a.compact_every)
+                e1.record()
+                torch.cuda.synchronize(device)
+                ms5 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+                if world > 1:
+                    dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+                st5 = dict(zip(h3._lib.STATS_FIELDS, r5.loop.stats_dev.cpu().tolist()))
+                assert st5["n"] == world * n5
+                c5[prec] = {"env_steps_per_s": st5["sum_ticks"] / (float(ms5.item()) * 1e-3), "ms": float(ms5.item()),
+                            "alive_fraction_end": st5["n_alive"] / st5["n"], "allreduced_n": int(st5["n"])}
+                del r5, p5
+                torch.cuda.empty_cache()
+            c5["f32"]["tolerance"] = F32_TOLERANCE
+            extras["config5_long_horizon"] = c5
+        except Exception as exc:
+            extras["config5_long_horizon"] = {"error": repr(exc)}
+        if rank == 0:
+            out["extras"] = extras
+
+    # ---- extras, rank 0 at N == 1 only ----
     if rank == 0 and world == 1 and not a.no_extras:
+        # BASELINE config 2: open-loop model step only, 65,536 episodes
         env2 = h3.Helicopter3DOF(dt=0.01, t_max=120, n_envs=65536, device=device)
         gen = torch.Generator().manual_seed(0)
         env2.reset(v_initial=5 + 20 * torch.rand(65536, generator=gen, dtype=torch.float64))
@@ -478,54 +662,62 @@ def main():
             env2.rollout(1000)
         e1.record()
         torch.cuda.synchronize(device)
-        alive2 = float((env2.flags == 0).double().mean().item())
-        out["extras"] = {"config2_open_loop": {"episodes": 65536, "ticks_per_launch": 1000,
-                                               "env_steps_per_s": 5 * 65536 * 1000 / (e0.elapsed_time(e1) * 1e-3),
-                                               "alive_fraction": alive2}}
+        out["extras"]["config2_open_loop"] = {"episodes": 65536, "ticks_per_launch": 1000,
+                                              "env_steps_per_s": 5 * 65536 * 1000 / (e0.elapsed_time(e1) * 1e-3),
+                                              "alive_fraction": float((env2.flags == 0).double().mean().item())}
         del env2
-        # the other two precision paths of the same kernel template, same workload and phase mix (device-resident)
+        # the other two precision paths of the same kernel templates, same whole-episode workload (device-resident)
         if a.precision == "f64":
             other = {}
             for prec in ("mixed", "f32"):
-                lp = make_workload(h3, torch, n, prec, device, seed=1, store=a.store, ticks=T)
-                lp.switch_step = (W + 2) * T
-                for _ in range(W):
-                    lp.run(T)
-                torch.cuda.synchronize(device)
-                t_before = lp.stats()["sum_ticks"]
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(4):
-                    lp.run(T)
-                e1.record()
-                torch.cuda.synchronize(device)
-                other[prec] = {"env_steps_per_s": (lp.stats()["sum_ticks"] - t_before) / (e0.elapsed_time(e1) * 1e-3),
+                r2 = h3.EpisodeRunner(n, device=device, precision=prec, per_episode_hyper=False, switch_step=a.switch,
+                                      score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
+                r2.params.copy_(params_host)
+                rate, st2 = whole_episode_rate(torch, r2, a, device, passes=1)
+                other[prec] = {"env_steps_per_s": rate, "alive_fraction_end": st2["n_alive"] / st2["n"],
                                "what": {"mixed": "fp64 model/PID/RLS + fp32 networks (the reference's torch-1.4 precision)",
-                                        "f32": "everything fp32"}[prec], "steps": 4}
-                del lp
+                                        "f32": "everything fp32"}[prec]}
+                del r2
+                torch.cuda.empty_cache()
+            other["f32"]["tolerance"] = F32_TOLERANCE
             out["extras"]["other_precisions"] = other
-
         # the 6-DOF widening: train.py's loop, 262,144 episodes, phase 1 and phase 2
         try:
             out["extras"]["six_dof_closed_loop"] = bench_6dof(torch, device, no_cpu=a.no_cpu)
         except Exception as exc:                    # an extra must never take the headline line down with it
             out["extras"]["six_dof_closed_loop"] = {"error": repr(exc)}
 
-    # ---- CPU baseline: the oracle on one host core, bounded sample ----
-    if rank == 0:
-        if not a.no_cpu and world == 1:
-            v, wall = cpu_c_oracle_rate(a.cpu_episodes, a.cpu_ticks, threads=1)
-            v_np, wall_np = cpu_numpy_oracle_rate(max(256, a.cpu_episodes // 8), max(50, a.cpu_ticks // 6))
-            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                   "sample": "%d episodes x %d ticks, compiled C oracle (oracle/heli3dof_ref.c), "
-                                             "1 thread, %.1f s" % (a.cpu_episodes, a.cpu_ticks, wall),
-                                   "host_cores": os.cpu_count(),
-                                   "numpy_oracle_env_steps_per_s": v_np,
-                                   "reference_python_loop_ticks_per_s": "400-485 per core (measured in the build "
-                                                                        "container, BASELINE.md section 2)"}
-        print(json.dumps(out))
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N == 1) ----
+    if rank == 0 and not a.no_cpu and world == 1:
+        v, wall = cpu_c_oracle_rate(a.cpu_episodes, a.cpu_ticks, threads=1)
+        n_np, t_np = max(256, a.cpu_episodes // 2), max(50, a.cpu_ticks // 2)
+        v_np, wall_np = cpu_numpy_oracle_rate(n_np, t_np)
+        v_all, wall_all, cores = cpu_numpy_all_cores_rate(n_np, t_np)
+        out["cpu_baseline"] = {
+            "value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": "%d episodes x %d ticks (switch at the midpoint, excitation on), compiled C oracle "
+                      "(oracle/heli3dof_ref.c), 1 thread, %.1f s" % (a.cpu_episodes, a.cpu_ticks, wall),
+            "host_cores": os.cpu_count(),
+            "numpy_oracle_1_core": {"value": v_np, "unit": "env-steps/s",
+                                    "sample": "%d episodes x %d ticks, oracle/heli3dof_np.py (closed-form batched NumPy, no "
+                                              "autograd), %.1f s" % (n_np, t_np, wall_np)},
+            "numpy_oracle_all_cores": {"value": v_all, "unit": "env-steps/s", "cores": cores,
+                                       "sample": "one process per core (multiprocessing.Pool over seeds, as main.py:67-70), same "
+                                                 "sample per process, %.1f s" % wall_all},
+            "reference_loop": "not measurable on the GPU box: the reference is Python (NumPy + torch autograd) under "
+                              "/root/reference, which does not travel; in the build container its own loop runs 400-485 "
+                              "ticks/s per core (BASELINE.md section 2, not measured in this run)"}
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+# full-episode tolerance of the f32 path (tests/test_gpu_parity.py::test_f32_full_episode_tolerance)
+F32_TOLERANCE = ("relative trajectory RMS error vs the f64 path over the WHOLE episode, 4096 random episodes: up to the phase "
+                 "switch (6000 ticks) median <= 2e-4 and 90 % of the episodes <= 5e-2 on u, theta, q; over all 12,000 ticks "
+                 "median <= 1e-1 -- the closed loop is chaotic after the switch: the reference's own fp32-network mode drifts "
+                 "from its fp64 mode by the same amounts (within 3x)")
 
 
 if __name__ == "__main__":

@@ -15,12 +15,12 @@ from .episodes import DEFAULTS, N_PARAMS, ROW, EpisodeRunner
 
 # main.py:107-112 (taus, nn_stdevs, gammas, lrs_act, lrs_crit) mapped to the 3-DOF magnitudes (config_3dof.json:5-9,
 # main_3dof.py:22-44)
-DEFAULT_GRID = {
+DEFAULT_GRID = {                                        # 3 x 3 x 5 x 3 x 3 = 405 settings, as main.py:107-112
     "tau_target_critic": [0.01, 0.1, 1.0],
-    "nn_stdev": [0.05, 0.1, 0.2, 0.4],
-    "discount_factor": [0.6, 0.7, 0.8, 0.9, 0.95, 0.99],
-    "learning_rate_actor": [0.05, 0.1, 0.2, 0.4],
-    "learning_rate_critic": [0.05, 0.1, 0.2, 0.4],
+    "nn_stdev": [0.05, 0.1, 0.2],
+    "discount_factor": [0.7, 0.8, 0.9, 0.95, 0.99],
+    "learning_rate_actor": [0.1, 0.2, 0.4],             # main.py: (2, 5, 10) for the 6-DOF agents; 3-DOF magnitudes here
+    "learning_rate_critic": [0.1, 0.2, 0.4],
 }
 
 # grid key -> parameter rows of one agent (episodes.PARAM_ROWS without the "col_" / "lon_" prefix)
@@ -84,10 +84,13 @@ def sweep_results(loop, setting_of_shard, n_settings, window_len, group=None):
 
 def run_sweep(grid=None, n_seeds=40, n_ticks=12000, rank=0, world_size=1, out_json=None, seed=0, device=None,
               precision="f64", switch_step=6000, score_window=(5000, 6000), ticks_per_launch=1000, agents=("lon",),
-              compact_every=0, runner=None):
-    """The whole sweep on this rank's shard; returns (keys, settings, per-setting results, loop)."""
+              compact_every=0, runner=None, n_total=None):
+    """The whole sweep on this rank's shard; returns (keys, settings, per-setting results, loop).  n_total (<= settings x
+    n_seeds) truncates the expanded list, e.g. to a fixed number of episodes per GPU: the last setting(s) then get fewer
+    seeds."""
     grid = DEFAULT_GRID if grid is None else grid
-    keys, settings, n_total = expand_grid(grid, n_seeds)
+    keys, settings, n_full = expand_grid(grid, n_seeds)
+    n_total = n_full if n_total is None else min(int(n_total), n_full)
     lo, hi = shard_range(n_total, rank, world_size)
     if runner is None:
         runner = EpisodeRunner(hi - lo, device=device, precision=precision, per_episode_hyper=True,

@@ -327,20 +327,82 @@ def test_full_size_replicated_episodes_agree_bitwise(h3):
 
 
 def test_f32_path_tolerance(h3):
-    """Full-fp32 path (model, PID, RLS and networks in fp32): trajectory RMS error against the reference's
-    mixed-precision run over the first 1000 ticks of the main_3dof.py scenario.  Stated tolerance: relative
-    RMS error <= 2e-2 on u, theta, q (RLS with cov0 = 1e4 in fp32 is the limiting factor)."""
+    """Full-fp32 path (model, PID, RLS and networks in fp32) against the reference's own mixed-precision run of the
+    main_3dof.py scenario (seed 2, fixture seed2_ref32): relative trajectory RMS error on u, theta, q <= 2e-2 over the
+    first 1000 ticks, <= 1e-1 over the whole run up to the reference's termination tick (5090)."""
     g = H.load("seed2_ref32.npz")
     snap = H.snaps_from(g, "snap_")[0]
     S = O.state_from_snapshots([snap], "ref32")
     S["theta_trim"][:] = snap["state"][4]
     loop = H.make_loop(S, O.default_config(), "f32", env_dtype=torch.float32, ticks_per_launch=500)
-    traj = loop.run(1000, record=1).cpu().double().numpy()[:, :, 0]
-    assert (traj[:, 12] > 0).all()
-    for col in (2, 4, 5):
-        ref = g["state"][:1000, col]
-        rms = np.sqrt(np.mean((traj[:, col] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
-        assert rms <= 2e-2, (col, rms)
+    n_ref = int(g["state"].shape[0])
+    traj = loop.run(min(n_ref, 5000), record=1).cpu().double().numpy()[:, :, 0]
+    assert (traj[:1000, 12] > 0).all()
+    for hz, tol in ((1000, 2e-2), (min(n_ref, 5000), 1e-1)):
+        alive = traj[:hz, 12] > 0
+        for col in (2, 4, 5):
+            ref = g["state"][:hz, col][alive]
+            rms = np.sqrt(np.mean((traj[:hz, col][alive] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+            assert rms <= tol, (hz, col, rms)
+
+
+def _runner(h3, precision, R, seed, chunk):
+    run = h3.EpisodeRunner(R, device="cuda", precision=precision, per_episode_hyper=False, ticks_per_launch=chunk)
+    run.params.copy_(h3.episodes.default_params(R))
+    Rw = h3.episodes.ROW
+    run.loop.init_episodes(seed, v_trim=run.params[Rw["v_trim"]], sigma=run.params[Rw["sigma_col_actor"]:Rw["sigma_lon_critic"] + 1])
+    return run
+
+
+def test_f32_full_episode_tolerance(h3):
+    """The f32 path over the WHOLE episode (12,000 ticks, switch at 6000, excitation < 1000) on 4096 random episodes
+    (device-side init: the same N(0, nn_stdev) draws in every precision), against the f64 path.  The closed loop is
+    chaotic once the collective agent learns: the reference's own two precision modes (fp32 networks vs all fp64)
+    separate to O(1) on some seeds and the seed-2 run even terminates at a different tick (5090 vs 10892), so the
+    tolerance is a statement about the distribution over episodes, per state, and is tied to the drift of the
+    mixed-precision path (the reference's original precision) measured in the same run.
+
+    Stated tolerance (relative trajectory RMS error on u, theta, q over the ticks both runs executed, episodes alive
+    over the whole horizon in both):
+        ticks [0, 6000)   : median <= 2e-4, 90 % of the episodes <= 5e-2
+        ticks [0, 12000)  : median <= 1e-1 (u, theta), <= 2.5e-1 (q)
+        median(f32) <= 4 x median(mixed) + 1e-6 at both horizons; >= 75 % of the episodes end on the f64 run's tick."""
+    R, seed, chunk, ticks = 4096, 31, 1000, 12000
+    cols = {"u": 2, "theta": 4, "q": 5}
+    runs = {p: _runner(h3, p, R, seed, chunk) for p in ("f64", "mixed", "f32")}
+    acc = {p: {"num": torch.zeros(3, R, dtype=torch.float64, device="cuda"), "den": torch.zeros(3, R, dtype=torch.float64, device="cuda"),
+               "full": torch.ones(R, dtype=torch.bool, device="cuda")} for p in ("mixed", "f32")}
+    stats = {"mixed": {}, "f32": {}}
+    ci = torch.tensor(list(cols.values()), device="cuda")
+    for c in range(ticks // chunk):
+        rec = {p: r.loop.run(chunk, record=R).double() for p, r in runs.items()}
+        a = rec["f64"]
+        for p in ("mixed", "f32"):
+            b = rec[p]
+            both = (a[:, 12] > 0) & (b[:, 12] > 0)                                  # (chunk, R)
+            d = (a[:, ci] - b[:, ci]) ** 2 * both[:, None, :]
+            acc[p]["num"] += d.sum(0)
+            acc[p]["den"] += (a[:, ci] ** 2 * both[:, None, :]).sum(0)
+            acc[p]["full"] &= both.all(0)
+        if (c + 1) * chunk in (6000, 12000):
+            hz = (c + 1) * chunk
+            for p in ("mixed", "f32"):
+                full = acc[p]["full"]
+                assert int(full.sum()) >= R // 8
+                rel = torch.sqrt(acc[p]["num"][:, full] / acc[p]["den"][:, full]).cpu().numpy()
+                for i, name in enumerate(cols):
+                    stats[p][(hz, name)] = (float(np.median(rel[i])), float(np.quantile(rel[i], 0.9)))
+    t64 = runs["f64"].loop.env.term_step
+    for p in ("mixed", "f32"):
+        stats[p]["same_term"] = float((runs[p].loop.env.term_step == t64).double().mean().item())
+    print("f32 / mixed full-episode drift (median, p90):", stats)
+    f, m = stats["f32"], stats["mixed"]
+    assert f["same_term"] >= 0.75, f["same_term"]
+    for name in cols:
+        assert f[(6000, name)][0] <= 2e-4 and f[(6000, name)][1] <= 5e-2, (name, f[(6000, name)])
+        assert f[(12000, name)][0] <= (2.5e-1 if name == "q" else 1e-1), (name, f[(12000, name)])
+        for hz in (6000, 12000):
+            assert f[(hz, name)][0] <= 4 * m[(hz, name)][0] + 1e-6, (hz, name, f[(hz, name)], m[(hz, name)])
 
 
 # ------------------------------------------------------------------------------------------------------
