@@ -323,6 +323,9 @@ class LaunchLog:
         self.first_tick = [0] * n_launches
 
 
+SORT_KEY = staticmethod(lambda lp: lp.heat).__func__      # per-episode sort key for compact(): the branch pattern; None: no sorting
+
+
 def run_step(runner, seed, episode0, n_ticks, launch_ticks, compact_every, log=None):
     """One bench step on device-resident parameters: init + n_ticks ticks in launches of launch_ticks."""
     from msc_thesis_b200.episodes import ROW
@@ -342,7 +345,7 @@ def run_step(runner, seed, episode0, n_ticks, launch_ticks, compact_every, log=N
         done += m
         i += 1
         if compact_every and done % compact_every == 0 and done < n_ticks:
-            lp.compact()
+            lp.compact(sort_key=SORT_KEY(lp) if SORT_KEY is not None else None)
     lp.allreduce_stats()                # the only collective of the path: per-batch statistics (NCCL all-reduce)
     return i
 

@@ -53,7 +53,7 @@ class H3Config(C.Structure):
 class H3Batch(C.Structure):
     _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in (
         "state", "t", "ref", "corr_u", "trim", "theta_trim", "ref_par", "pid_corr", "rls_W", "rls_cov", "rls_x",
-        "rls_u", "rls_skip", "col_net", "lon_net", "col_hyper", "lon_hyper", "step", "flags", "term_step", "acc")]
+        "rls_u", "rls_skip", "col_net", "lon_net", "col_hyper", "lon_hyper", "step", "flags", "term_step", "acc", "heat")]
 
 
 class H3Init(C.Structure):

@@ -63,6 +63,7 @@ class ClosedLoop3DOF:
             ref = env.get_ref()
         self.ref2 = ref[[1, 4]].to(env.dtype).contiguous() if ref.shape[0] == 7 else ref.to(env.dtype).contiguous()
         self.acc = torch.zeros(3, n, dtype=torch.float64, device=self.device)
+        self.heat = torch.zeros(n, dtype=torch.int32, device=self.device)   # branch pattern of the last tick (sort key)
         self.stats_dev = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
         nbytes = int(L.lib().h3_stats_scratch_bytes(n))
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
@@ -145,7 +146,7 @@ class ClosedLoop3DOF:
                            pid_corr=self.pid.hdot_corr, rls_W=rls._W, rls_cov=rls._cov, rls_x=rls.x, rls_u=rls.u,
                            rls_skip=rls._skip, col_net=self.agent_col.net, lon_net=self.agent_lon.net,
                            col_hyper=col_hyper, lon_hyper=lon_hyper, step=env.step_count, flags=env.flags,
-                           term_step=env.term_step, acc=self.acc)
+                           term_step=env.term_step, acc=self.acc, heat=self.heat)
 
     def _config(self, ref_mode):
         return build_config(env=self.env, pid=self.pid, rls=self.rls, col=self.agent_col, lon=self.agent_lon,
@@ -229,7 +230,7 @@ class ClosedLoop3DOF:
         env, rls = self.env, self.rls
         ts = [env.state, env.t_ep, self.ref2, env.corr_u, env.trimmed_controls, env.trimmed_state, self.pid.hdot_corr,
               rls._W, rls._cov, rls.x, rls.u, rls._skip, rls.X, self.agent_col.net, self.agent_lon.net,
-              env.step_count, env.flags, env.term_step, self.acc, self.order]
+              env.step_count, env.flags, env.term_step, self.acc, self.order, self.heat]
         if env.ref_params is not None:
             ts.append(env.ref_params)
         for ag in (self.agent_col, self.agent_lon):
@@ -237,18 +238,27 @@ class ClosedLoop3DOF:
                 ts.append(ag.hyper_rows_device)
         return ts
 
-    def compact(self):
-        """Move the live episodes to the front (stable order) so that launches only cover them: terminated
-        episodes otherwise keep occupying lanes of their warp.  Returns the number of live episodes.  Per-episode
-        tensors of all five objects are permuted IN PLACE; `self.order` maps columns to original episode indices
-        (`self.original_order(t)` undoes the permutation for reporting).  Per-episode hyper-parameter tensors held
-        by the agents are permuted as well."""
+    def compact(self, sort_key=None):
+        """Move the live episodes to the front so that launches only cover them: terminated episodes otherwise keep
+        occupying lanes of their warp.  Returns the number of live episodes.  Per-episode tensors of all five objects
+        are permuted IN PLACE; `self.order` maps columns to original episode indices (`self.original_order(t)` undoes
+        the permutation for reporting).  Per-episode hyper-parameter tensors held by the agents are permuted as well.
+
+        sort_key: optional (n_active,) tensor; the live episodes are additionally ordered by it (ascending).  Episodes
+        are independent, so any order gives the same per-episode results bit for bit; grouping episodes that take the
+        same data-dependent branches (tanh / sincos range) into the same warps removes the divergence between them."""
         na = self.n_active
         alive = self.env.flags[:na] == 0
         n_alive = int(alive.sum().item())
-        if n_alive == na:
+        if n_alive == na and sort_key is None:
             return na
-        perm = torch.cat([torch.nonzero(alive).reshape(-1), torch.nonzero(~alive).reshape(-1)])
+        if sort_key is None:
+            perm = torch.cat([torch.nonzero(alive).reshape(-1), torch.nonzero(~alive).reshape(-1)])
+        else:
+            key = sort_key[:na].to(torch.float64)
+            key = torch.where(alive, torch.nan_to_num(key, nan=1e300, posinf=1e300, neginf=-1e300),
+                              torch.full_like(key, float("inf")))
+            perm = torch.argsort(key, stable=True)
         for t in self._episode_tensors():
             head = t[..., :na]
             head.copy_(head.index_select(-1, perm))

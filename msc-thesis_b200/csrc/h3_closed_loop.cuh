@@ -22,6 +22,9 @@ namespace h3 {
 // PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
+// bits of H3Batch.heat: which data-dependent slow branches an episode took in its last executed tick
+enum { H3_HEAT_LON = 1, H3_HEAT_COL = 2, H3_HEAT_TRIG = 4 };
+
 #ifndef H3_PAIR_SPLIT_W
 #define H3_PAIR_SPLIT_W 1     // PAIR mode: split the columns of the RLS weight matrix between the two lanes
 #endif
@@ -35,7 +38,7 @@ struct LoopParams {
     ET *state, *ref, *corr_u, *pid_corr, *rls_W, *rls_cov, *rls_x, *rls_u;
     double *t, *acc;
     const double *trim, *theta_trim, *ref_par, *col_hyper, *lon_hyper;
-    int32_t *rls_skip, *step, *flags, *term_step;
+    int32_t *rls_skip, *step, *flags, *term_step, *heat;
     NT *col_net, *lon_net;
     const double* ref_table;
     const double* excitation;
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     if (PAIR) __syncwarp();                 // the partner lane reads what the lead lane staged
 
     const bool lockstep = P.step0 >= 0;
+    int heat = 0;
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
     const bool table_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_TABLE);
 
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         for (int jj = 0; jj < cn; ++jj) {
             const unsigned amask = PAIR ? __ballot_sync(0xffffffffu, flags == 0) : 0xffffffffu;
             if (flags != 0) continue;       // terminated (or idle) lane: frozen (both lanes of a pair agree)
+            heat = 0;
             const int k = lockstep ? (P.step0 + c0 + jj) : step;
             const bool phase2 = COL && (k >= P.switch_step);                    // main_3dof.py:127-137
             AgentH<NT> Hcol = P.col_h, Hlon = P.lon_h;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
                 const NT a_lon = actor_forward<NT, NHLh, UL, PAIR>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
-                                                                    stl, fl, amask);
+                                                                    stl, fl, amask, &heat, H3_HEAT_LON);
                 cyc = misce[3] + (ET)a_lon;
                 stl[NHLh] = fl;
                 stl[NHLh + 1] = sl0;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
                 const NT a_col = actor_forward<NT, NHCh, UC, PAIR>(col, sc0, sc1, Hcol.scale, P.col.final_activation,
-                                                                    stc, fc, amask);
+                                                                    stc, fc, amask, &heat, H3_HEAT_COL);
                 colv = misce[2] + (ET)a_col;
                 stc[NHCh] = fc;
                 stc[NHCh + 1] = sc0;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             cyc += exc1;
             // sin/cos of theta (model + PID) and of the cyclic pitch (model) in one interleaved evaluation
             ET scy, ccy;
-            Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
+            if (!Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy)) heat |= H3_HEAT_TRIG;
             if (!phase2) {
                 ET pc = misce[1];
                 colv = pid_collective(K, s, sth, cth, pc);                      // PID.py:16-24
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 SubVec<decltype(stl), NT> scr{stl, NHLh + 3};
                 agent_update<NT, NHLh, UL, TAU1L, PAIR>(lon, Hlon, P.lon.final_activation, stl[NHLh + 1],
                                                         stl[NHLh + 2], n0, n1, (NT)0, dr, F, G, stl, stl[NHLh], scr,
-                                                        amask);
+                                                        amask, &heat, H3_HEAT_LON);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 SubVec<decltype(stc), NT> scr{stc, NHCh + 3};
                 agent_update<NT, NHCh, UC, false, PAIR>(col, Hcol, P.col.final_activation, stc[NHCh + 1],
                                                         stc[NHCh + 2], n0, n1, (NT)0, dr, F, G, stc, stc[NHCh], scr,
-                                                        amask);
+                                                        amask, &heat, H3_HEAT_COL);
             }
             if (rec) {
                 row[10 * P.ld_traj] = (ET)r_col;
@@ -496,6 +501,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         P.step[e] = step;
         P.flags[e] = flags;
         P.term_step[e] = term_step;
+        if (P.heat != nullptr) P.heat[e] = heat;
         acc0 = miscd[0];
         acc1 = miscd[1];
         acc2 = miscd[2];

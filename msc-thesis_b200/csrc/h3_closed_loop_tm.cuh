@@ -56,7 +56,7 @@ struct ColTm {
 // DHPActor.forward of the collective agent (agents.py:59-63): weights from TMEM, h_a and (f, s0, s1) back to it.
 //   UF: hidden units per group (their tanh chains are interleaved)
 template <typename NT, int NH, int UF>
-H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
+H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act, int& heat) {
     typedef Math<NT> M;
     typedef ColTm<NH> L;
     static_assert(NH % UF == 0, "group width must divide the hidden width");
@@ -70,7 +70,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
         NT pre[UF], hk[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) pre[u] = b[u][0] * s0 + b[u][1] * s1;
-        M::template tanh_vec<UF>(pre, hk);
+        if (!M::template tanh_vec<UF>(pre, hk)) heat |= H3_HEAT_COL;
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
@@ -97,7 +97,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
 //   UP: hidden units per group of passes T and A (their tanh chains are interleaved); V2: units per group of pass C.
 template <typename NT, int NH, int UP, int V2>
 H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n1, NT dr0, NT dr, const NT (&F)[2][2],
-                          const NT (&G)[2]) {
+                          const NT (&G)[2], int& heat) {
     typedef Math<NT> M;
     typedef ColTm<NH> L;
     static_assert(NH % UP == 0 && NH % V2 == 0, "chunk widths must divide the hidden width");
@@ -117,7 +117,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
         NT pre[UP], ht[UP];
 #pragma unroll
         for (int u = 0; u < UP; ++u) pre[u] = b[u][0] * n0 + b[u][1] * n1;
-        M::template tanh_vec<UP>(pre, ht);
+        if (!M::template tanh_vec<UP>(pre, ht)) heat |= H3_HEAT_COL;
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
@@ -142,7 +142,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
 #pragma unroll
             for (int u = 0; u < UP; ++u) pre[u] = c1[u][0] * s0 + c1[u][1] * s1;
         }
-        M::template tanh_vec<UP>(pre, hc);
+        if (!M::template tanh_vec<UP>(pre, hc)) heat |= H3_HEAT_COL;
         __syncwarp();
         TmemBuf<NT, 6> b[UP];               // c2(0,k) c2(1,k) a1(k,0) a1(k,1) a2(k) h_a(k)
 #pragma unroll
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
 
     // ---- resumable tick loop: leaves whenever a lane terminated, so that its state is stored at once ----
     int j = 0;
+    int heat = 0;                           // which data-dependent slow branches the episode took in its last tick
     bool just_died = false, finished = false;
     do {
         bool flush = false;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             }
             const bool dead = flags != 0;
             if (__all_sync(FULL, dead)) continue;       // every episode of this warp has terminated
+            heat = 0;
             const int k = P.step0 + j;
             const bool phase2 = k >= P.switch_step;                                 // main_3dof.py:127-137
             if (dead) {                     // frozen episode: run on harmless values, commit nothing
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
                 const NT a_lon = actor_forward<NT, NHL, NHL, false>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
-                                                                    stl, fl);
+                                                                    stl, fl, FULL, &heat, H3_HEAT_LON);
                 cyc = trim1 + (ET)a_lon;
                 stl[NHL] = fl;
             }
@@ -365,13 +367,13 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
                 __syncwarp();
-                const NT a_col = col_forward_tm<NT, NHC, UF>(tm, sc0, sc1, Hcol.scale, P.col.final_activation);
+                const NT a_col = col_forward_tm<NT, NHC, UF>(tm, sc0, sc1, Hcol.scale, P.col.final_activation, heat);
                 colv = trim0 + (ET)a_col;
             }
             cyc += (ET)sh_exc[2 * jj + 1];                                          // main_3dof.py:139-140
             if (dead) cyc = (ET)0;
             ET scy, ccy;
-            Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
+            if (!Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy)) heat |= H3_HEAT_TRIG;
             if (!phase2) {
                 ET pc = P.pid_corr[ec];
                 colv = pid_collective(K, s, sth, cth, pc);                          // PID.py:16-24
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? prev[1] : pick7(prev, P.lon.tracked_state) - refth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
                 agent_update<NT, NHL, NHL, TAU1L, false>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
-                                                         F, G, stl, stl[NHL], scr);
+                                                         F, G, stl, stl[NHL], scr, FULL, &heat, H3_HEAT_LON);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT n0 = (NT)pick7(s, P.col.ac_state);
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
                 __syncwarp();
-                col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G);
+                col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G, heat);
             }
             // -------- bookkeeping and termination (main_3dof.py:189-197): frozen for terminated episodes --------
             if (!dead) {
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             P.step[e] = step;
             P.flags[e] = flags;
             P.term_step[e] = term_step;
+            if (P.heat != nullptr) P.heat[e] = heat;
             P.t[e] = t_ep;
             P.acc[e] = accv[0];
             P.acc[ld + e] = accv[1];

@@ -245,6 +245,7 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     P.step = b.step;
     P.flags = b.flags;
     P.term_step = b.term_step;
+    P.heat = b.heat;
     P.col_net = (NT*)b.col_net;
     P.lon_net = (NT*)b.lon_net;
     P.ref_table = ref_table;

@@ -161,8 +161,10 @@ struct Math<double> {
     static H3_DEV double tanh_(double x) { return tanh_f64(x); }
     // U independent arguments at once; the polynomial loops run coefficient-major so that consecutive DFMAs
     // belong to different elements (a single warp per scheduler then covers the DFMA latency by itself).
+    // Returns whether the short (polynomial) branch was taken: the kernels keep that per episode as a sort key, so
+    // that episodes taking the same branches can be grouped into the same warps (ClosedLoop3DOF.compact).
     template <int U>
-    static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
+    static H3_DEV bool tanh_vec(const double (&x)[U], double (&y)[U]) {
         bool all_small = true;
 #pragma unroll
         for (int u = 0; u < U; ++u) all_small = all_small && (::fabs(x[u]) < 0.55);
@@ -183,10 +185,12 @@ struct Math<double> {
             // at most H3_TANH_G elements in flight: each carries ~6 live doubles through the pipeline below
             tanh_any_group<0, U>(x, y);
         }
+        return all_small;
     }
     // sin/cos of two independent angles (theta and the cyclic pitch): four interleaved polynomial chains
-    static H3_DEV void sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
-        if (::fabs(a) <= 0.78539816339744828 && ::fabs(b) <= 0.78539816339744828) {
+    static H3_DEV bool sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
+        const bool poly = ::fabs(a) <= 0.78539816339744828 && ::fabs(b) <= 0.78539816339744828;
+        if (poly) {
             const double za = a * a, zb = b * b;
             double psa = H3_SIN_C[7], pca = H3_COS_C[7], psb = H3_SIN_C[7], pcb = H3_COS_C[7];
 #pragma unroll
@@ -207,6 +211,7 @@ struct Math<double> {
             sincos_f64(a, sa, ca);
             sincos_f64(b, sb, cb);
         }
+        return poly;
     }
     static H3_DEV double exp_(double x) { return ::exp(x); }
     static H3_DEV double sqrt_(double x) { return ::sqrt(x); }
@@ -219,13 +224,15 @@ template <>
 struct Math<float> {
     static H3_DEV float tanh_(float x) { return ::tanhf(x); }
     template <int U>
-    static H3_DEV void tanh_vec(const float (&x)[U], float (&y)[U]) {
+    static H3_DEV bool tanh_vec(const float (&x)[U], float (&y)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
+        return true;
     }
-    static H3_DEV void sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
+    static H3_DEV bool sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
         ::sincosf(a, sa, ca);
         ::sincosf(b, sb, cb);
+        return true;
     }
     static H3_DEV float exp_(float x) { return ::expf(x); }
     static H3_DEV float sqrt_(float x) { return ::sqrtf(x); }

@@ -316,7 +316,8 @@ H3_DEV T pair_sum(T x, unsigned mask) {
 // DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
 //   NH = hidden units handled by THIS lane (all of them, or half in PAIR mode).
 template <typename NT, int NH, int U, bool PAIR = false, typename Net, typename HVec>
-H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f, unsigned mask = 0xffffffffu) {
+H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f, unsigned mask = 0xffffffffu,
+                        int* heat = nullptr, int heat_bit = 0) {
     typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     NT y = (NT)0;
@@ -328,7 +329,8 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
             const int k = (U == NH) ? u : k0 + u;
             pre[u] = net.a1(k, 0) * s0 + net.a1(k, 1) * s1;
         }
-        M::template tanh_vec<U>(pre, hk);
+        const bool cool = M::template tanh_vec<U>(pre, hk);
+        if (heat != nullptr && !cool) *heat |= heat_bit;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int k = (U == NH) ? u : k0 + u;
@@ -353,7 +355,7 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
 template <typename NT, int NH, int U, bool TAU1, bool PAIR = false, typename Net, typename HVec, typename SVec>
 H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
                          const NT (&F)[2][2], const NT (&G)[2], HVec& h_a, NT f, SVec& scr,
-                         unsigned mask = 0xffffffffu) {
+                         unsigned mask = 0xffffffffu, int* heat = nullptr, int heat_bit = 0) {
     typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     // action.backward() (:174): delta = da/dy, p_k = da/d(pre-activation of hidden k)
@@ -380,7 +382,8 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
             for (int u = 0; u < U; ++u) { act[u] = aa[u]; act[U + u] = ab[u]; }
         }
 #else
-        M::template tanh_vec<2 * U>(pre, act);
+        const bool cool = M::template tanh_vec<2 * U>(pre, act);
+        if (heat != nullptr && !cool) *heat |= heat_bit;
 #endif
 #pragma unroll
         for (int u = 0; u < U; ++u) {

@@ -91,10 +91,12 @@ class EpisodeRunner:
                 torch.empty(3, self.n, dtype=torch.int32, pin_memory=pin),
                 torch.empty(L.N_STATS, dtype=torch.float64, pin_memory=pin))
 
-    def run(self, params_host, results_host, seed, n_ticks=12000, episode0=0, compact_every=0):
+    def run(self, params_host, results_host, seed, n_ticks=12000, episode0=0, compact_every=0, sort=True):
         """One job: parameters up (H2D), init, n_ticks ticks, results down (D2H) -- all enqueued on the current
         stream; synchronise before reading results_host.  compact_every = K > 0 moves the live episodes to the front
-        every K ticks (ClosedLoop3DOF.compact(); it synchronises), so terminated episodes stop occupying lanes."""
+        every K ticks (ClosedLoop3DOF.compact(); it synchronises), so terminated episodes stop occupying lanes; with
+        `sort` they are also ordered by the branch pattern of their last tick (H3Batch.heat), which takes the
+        divergence between calm and agitated episodes out of the warps.  Results do not depend on either."""
         lp = self.loop
         self.params.copy_(params_host, non_blocking=True)
         lp.init_episodes(seed, episode0=episode0, v_trim=self.params[ROW["v_trim"]],
@@ -106,7 +108,7 @@ class EpisodeRunner:
                 lp.run(m)
                 done += m
                 if done < n_ticks:
-                    lp.compact()
+                    lp.compact(sort_key=lp.heat if sort else None)
         else:
             lp.run(n_ticks)
         out_f, out_i, out_s = results_host

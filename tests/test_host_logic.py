@@ -37,20 +37,21 @@ def test_ctypes_structs_match_the_header(tmp_path):
 #include <stddef.h>
 #include "heli3dof.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\\n", sizeof(H3EnvParams), sizeof(H3AgentHyper), sizeof(H3Config), sizeof(H3Batch), sizeof(H3Traj));
+  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(H3EnvParams), sizeof(H3AgentHyper), sizeof(H3Config), sizeof(H3Batch), sizeof(H3Traj), sizeof(H3Init));
   printf("%zu %zu %zu %zu %zu\\n", offsetof(H3Config, env_dtype), offsetof(H3Config, rls_gamma), offsetof(H3Config, switch_step), offsetof(H3Config, col), offsetof(H3Config, lon));
-  printf("%zu %zu %zu %zu\\n", offsetof(H3Batch, state), offsetof(H3Batch, rls_skip), offsetof(H3Batch, step), offsetof(H3Batch, acc));
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(H3Batch, state), offsetof(H3Batch, rls_skip), offsetof(H3Batch, step), offsetof(H3Batch, acc), offsetof(H3Batch, heat), offsetof(H3Init, sigma), offsetof(H3Init, episode_id));
   return 0;
 }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     lines = subprocess.check_output([str(exe)]).decode().split("\n")
     sizes = [int(x) for x in lines[0].split()]
-    assert sizes == [ctypes.sizeof(c) for c in (L.H3EnvParams, L.H3AgentHyper, L.H3Config, L.H3Batch, L.H3Traj)]
+    assert sizes == [ctypes.sizeof(c) for c in (L.H3EnvParams, L.H3AgentHyper, L.H3Config, L.H3Batch, L.H3Traj, L.H3Init)]
     offs = [int(x) for x in lines[1].split()]
     assert offs == [getattr(L.H3Config, k).offset for k in ("env_dtype", "rls_gamma", "switch_step", "col", "lon")]
     offs = [int(x) for x in lines[2].split()]
-    assert offs == [getattr(L.H3Batch, k).offset for k in ("state", "rls_skip", "step", "acc")]
+    assert offs == [getattr(L.H3Batch, k).offset for k in ("state", "rls_skip", "step", "acc", "heat")] + [
+        L.H3Init.sigma.offset, L.H3Init.episode_id.offset]
 
 
 def test_6dof_exports_and_struct_layout(tmp_path):
