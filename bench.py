@@ -446,6 +446,13 @@ def main():
     if a.impl == "reference":
         run_reference_arm(a)
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ:
+        # NCCL's INFO lines (communicator, rank count, NVLS) are what shows that the collective ran on N ranks: leave
+        # NCCL_DEBUG to the caller; if it is unset, ask for the init lines -- before torch (and with it NCCL) is loaded --
+        # and send them to stderr (stdout carries the JSON line, printed last)
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import msc_thesis_b200 as h3
@@ -462,13 +469,6 @@ def main():
     if world > 1 and os.environ.get("H3_NUMA_BIND", "1") != "0":
         numa_cpus = h3.distributed.bind_to_gpu_numa_node(local)
     if world > 1:
-        # NCCL's INFO lines (communicator, rank count, NVLS) are what shows that the collective ran on N ranks: leave
-        # NCCL_DEBUG to the caller; if it is unset, ask for the init lines and send them to stderr (stdout carries the
-        # JSON line, printed last)
-        if "NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     h3.lib()
 

@@ -31,9 +31,6 @@ def sinusoid_ref_table(t0, dt, n_ticks, amp=10.0, period=10.0):
     return out, t
 
 
-_TABLE_CACHE = {}
-
-
 class ClosedLoop3DOF:
     def __init__(self, env, pid, rls, agent_col, agent_lon, excitation=None, switch_step=6000,
                  score_window=(0, 0), ticks_per_launch=1000, store_policy=0, ref=None):
@@ -153,6 +150,36 @@ class ClosedLoop3DOF:
                             switch_step=self.switch_step, ref_mode=ref_mode, window=self.score_window,
                             store_policy=self.store_policy)
 
+    def _reference_table(self, n_ticks, min_horizon=16384):
+        """Device-resident sinusoid reference for the lockstep clock, built ONCE for a whole horizon (the table is a
+        function of the tick index only) and re-used by every launch: run() then issues no host -> device copy.
+        Entry i belongs to tick k0 + i; `t[i]` is env.t before that tick, accumulated like heli_models.py:206.  The
+        table is rebuilt when the clock does not continue it (reset, a different dt / amplitude / period)."""
+        env = self.env
+        key = (float(env.dt), float(env.ref_amplitude), float(env.ref_period), str(self.device))
+        tab = getattr(self, "_tab", None)
+        k, need = self.k, self.k + n_ticks
+        ok = (tab is not None and tab["key"] == key and tab["k0"] <= k and need <= tab["k0"] + len(tab["host"])
+              and float(tab["t"][k - tab["k0"]]) == float(env.t))
+        if not ok:
+            if tab is not None and tab["key"] == key and tab["k0"] <= k <= tab["k0"] + len(tab["host"]) and \
+                    float(tab["t"][k - tab["k0"]]) == float(env.t):
+                k0, t0 = tab["k0"], float(tab["t"][0])          # same clock: extend the horizon
+            else:
+                k0, t0 = k, float(env.t)
+            n = max(need - k0, min_horizon)
+            host, _ = sinusoid_ref_table(t0, env.dt, n, env.ref_amplitude, env.ref_period)
+            t = np.empty(n + 1)
+            acc = t0
+            for i in range(n + 1):
+                t[i] = acc
+                acc = acc + env.dt
+            pinned = torch.from_numpy(host).pin_memory()
+            tab = {"key": key, "k0": k0, "host": host, "t": t, "pinned": pinned,
+                   "dev": pinned.to(self.device, non_blocking=True)}
+            self._tab = tab
+        return tab["dev"], tab["t"]
+
     def plan(self, n_ticks):
         """Launch plan [(first tick, ticks)] : split at the phase switch so that phase-1 launches never load
         the collective agent's networks, and at ticks_per_launch."""
@@ -188,19 +215,16 @@ class ClosedLoop3DOF:
         stream = L.stream_ptr(self.device)
         lib = L.lib()
         plan = self.plan(n_ticks)
+        tab_dev, tab_t = (None, None)
+        if table_mode:
+            tab_dev, tab_t = self._reference_table(n_ticks)
         for j0, m in plan:
             table = None
             if table_mode:
-                # the table only depends on the clock: reuse the device copy across launches / chunks / slots
-                key = (float(env.t), float(env.dt), m, float(env.ref_amplitude), float(env.ref_period), str(self.device))
-                hit = _TABLE_CACHE.get(key)
-                if hit is None:
-                    tab, t_end = sinusoid_ref_table(env.t, env.dt, m, env.ref_amplitude, env.ref_period)
-                    hit = (torch.as_tensor(tab).to(self.device, non_blocking=False), t_end)
-                    if len(_TABLE_CACHE) > 256:
-                        _TABLE_CACHE.clear()
-                    _TABLE_CACHE[key] = hit
-                table, t_end = hit
+                # a slice of the device-resident table of the whole horizon: no host -> device copy, no sync
+                off = self._tab["k0"]
+                table = tab_dev[self.k + j0 - off:self.k + j0 - off + m]
+                t_end = float(tab_t[self.k + j0 - off + m])
             else:
                 t_end = env.t
                 for _ in range(m):
@@ -225,6 +249,53 @@ class ClosedLoop3DOF:
         if self.k is not None:
             self.k += n_ticks
         return traj
+
+    def run_logged(self, n_ticks, every=10, episodes=1, as_reference=False):
+        """run() with BOTH logs of main_3dof.py: the per-tick rows (:164-175, returned like run(record=episodes)) and the
+        network / incremental-model history that the script appends after the ticks 0, every, 2 every, ... (:178-186):
+        for each agent the six weight matrices (actor, critic, target critic; input and output layer, raveled in
+        torch's (out, in) order) and F, G from get_transition_matrices.  Returns (traj, weight_stats) with
+        weight_stats = {'t': (n_ticks,), 'col': {'nn': {'a': {'i': (T, 2 nh, R), 'o': (T, nh, R)}, 'c': ..., 'tc': ...},
+        'rls': {'F': (T, 4, R), 'G': (T, 2, R)}}, 'lon': {...}} as CPU tensors (R = episodes, T = logged ticks).
+        as_reference: main_3dof.py:181 walks `agent_col.networks` for BOTH agents, so its 'lon' entries hold the
+        collective agent's weights; True reproduces that, False (default) logs each agent's own networks.
+        The history is taken between launches (no extra kernel): launches are cut at the logged ticks."""
+        n_ticks, every, R = int(n_ticks), int(every), int(episodes)
+        k_start = self.k if self.k is not None else 0
+        t_start = float(self.env.t)
+        agents = {"col": self.agent_col, "lon": self.agent_lon}
+        hist = {a: {"nn": {n: {"i": [], "o": []} for n in ("a", "c", "tc")}, "rls": {"F": [], "G": []}} for a in agents}
+        parts, done = [], 0
+
+        def snapshot():
+            for name, ag in agents.items():
+                src = self.agent_col if as_reference else ag
+                for key, net in zip(("a", "c", "tc"), src.networks):
+                    hist[name]["nn"][key]["i"].append(net.fc1.weight[..., :R].reshape(-1, R).clone())
+                    hist[name]["nn"][key]["o"].append(net.fc2.weight[..., :R].reshape(-1, R).clone())
+                F, G = ag.get_transition_matrices(self.rls)
+                hist[name]["rls"]["F"].append(F[..., :R].reshape(4, R).clone())
+                hist[name]["rls"]["G"].append(G[..., :R].reshape(2, R).clone())
+
+        while done < n_ticks:
+            k = k_start + done
+            m = 1 if k % every == 0 else min(every - k % every, n_ticks - done)     # stop right after a logged tick
+            parts.append(self.run(m, record=R, want_stats=(done + m == n_ticks)))
+            if k % every == 0:
+                snapshot()
+            done += m
+        traj = torch.cat(parts) if parts else None
+        t = np.empty(n_ticks)
+        acc = t_start
+        for i in range(n_ticks):                    # env.t after every tick, accumulated like heli_models.py:206
+            acc = acc + self.env.dt
+            t[i] = acc
+        out = {"t": torch.as_tensor(t)}
+        for a in agents:
+            out[a] = {"nn": {n: {l: torch.stack(v).cpu() for l, v in d.items()} for n, d in hist[a]["nn"].items()},
+                      "rls": {k2: torch.stack(v).cpu() for k2, v in hist[a]["rls"].items()}}
+        self._t_at_record_start = t_start
+        return traj, out
 
     def _episode_tensors(self):
         env, rls = self.env, self.rls

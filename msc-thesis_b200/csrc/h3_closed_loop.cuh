@@ -25,10 +25,6 @@ enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 // bits of H3Batch.heat: which data-dependent slow branches an episode took in its last executed tick
 enum { H3_HEAT_LON = 1, H3_HEAT_COL = 2, H3_HEAT_TRIG = 4 };
 
-#ifndef H3_PAIR_SPLIT_W
-#define H3_PAIR_SPLIT_W 1     // PAIR mode: split the columns of the RLS weight matrix between the two lanes
-#endif
-
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
 template <typename ET, typename NT>
@@ -156,26 +152,15 @@ struct LoopLayout {
 //   UL/UC : hidden units per chunk in the cyclic / collective agent's loops (see h3_tick.cuh); a chunked
 //           agent (U < NH) needs its networks and stash in shared memory
 //   RD    : look-ahead depth (groups) of the RLS shared-memory streams
-//   PAIR  : two lanes (l, l ^ 16) per episode: the model step, PID and RLS are computed by both (identical
-//           values), every hidden layer is split in halves between them (h3_tick.cuh: pair_sum).  The
-//           shared-memory tile is per EPISODE, so a warp holds LANES <= 16 episodes and twice as many warps
-//           are resident for the same tile bytes: with one episode per lane the collective-agent launches
-//           could keep only one warp per scheduler, every latency exposed; PAIR gives two, each with half
-//           the agent work on its critical path.  Both halves of a 64-bit shared-memory access are separate
-//           wavefronts anyway, so the 16-lane rows cost no extra bank conflicts.
 //   MINB  : minimum resident CTAs per SM the register allocation has to allow
 template <typename ET, typename NT, int NHL, int NHC, bool COL, bool SYM, bool HYP, bool TAU1L, int PLACE, int LANES,
-          int WARPS, int UL, int UC, int RD, bool PAIR, int MINB>
+          int WARPS, int UL, int UC, int RD, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const LoopParams<ET, NT> P) {
-    constexpr int NHLh = PAIR ? NHL / 2 : NHL, NHCh = PAIR ? NHC / 2 : NHC;     // hidden units of this lane
-    static_assert(UL == NHLh || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
-    static_assert(UC == NHCh || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");
-    static_assert(!PAIR || ((PLACE & (P_STASHL | P_STASHC | P_LON)) == 0 && UL == NHLh &&
-                            UC == NHCh && NHL % 2 == 0 && NHC % 2 == 0 && LANES <= 16),
-                  "PAIR mode: per-lane groups live in registers, hidden widths even, <= 16 episodes per warp");
+    static_assert(UL == NHL || ((PLACE & P_LON) && (PLACE & P_STASHL)), "chunked cyclic agent must live in smem");
+    static_assert(UC == NHC || (PLACE & P_STASHC), "chunked collective agent needs its stash in smem");
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, LANES> LY;
     constexpr int NCOV = LY::NCOV, NNC = LY::NNC;
-    constexpr int NNL = (PLACE & P_LON) ? LY::NNL : (TAU1L ? 7 : 11) * NHLh;    // register copy: this lane's units
+    constexpr int NNL = LY::NNL;
     constexpr int BLOCK = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sh_ref = reinterpret_cast<double*>(smem_raw);               // [TICK_CHUNK]
@@ -183,9 +168,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     double* sh_red = sh_exc + 2 * TICK_CHUNK;                           // [WARPS][H3_N_STATS]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = PAIR ? (lane >> 4) : 0;            // which half of every hidden layer this lane owns
-    const int sub = PAIR ? (lane & 15) : lane;          // episode slot inside the warp
-    const bool lead = half == 0;                        // the lane that loads / stores the shared episode state
+    const int sub = lane;                               // episode slot inside the warp
     const int64_t e = ((int64_t)blockIdx.x * WARPS + warp) * LANES + sub;
     const bool valid = (sub < LANES) && (e < P.n);
     const int64_t ld = P.ld;
@@ -198,15 +181,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     typedef SmemVec<ET, NCOV, LANES> CovVec;
     typename std::conditional<SYM, CovSym<ET, CovVec>, CovFull<ET, CovVec>>::type cov;
     WMatD<ET, SmemVec<ET, 63, LANES>> Wm;
-    NetAcc<NT, NHC, SmemVec<NT, NNC, LANES>, PAIR> col;
-    NetAcc<NT, (PLACE & P_LON) ? NHL : NHLh, Group<NT, NNL, LANES, (PLACE & P_LON) != 0>, PAIR && (PLACE & P_LON)> lon;
-    col.koff_ = half * NHCh;
-    lon.koff_ = half * NHLh;
+    NetAcc<NT, NHC, SmemVec<NT, NNC, LANES>> col;
+    NetAcc<NT, NHL, Group<NT, NNL, LANES, (PLACE & P_LON) != 0>> lon;
     Group<ET, 9, LANES, (PLACE & P_PREV) != 0> prev;             // x_prev[7], u_prev[2]   model.py:45-46
     Group<double, 4, LANES, (PLACE & P_MISC) != 0> miscd;        // acc0, acc1, acc2, t
     Group<ET, 4, LANES, (PLACE & P_MISC) != 0> misce;            // corr_u, pid_corr, trim0, trim1
-    Group<NT, 2 * NHLh + 3, LANES, (PLACE & P_STASHL) != 0> stl; // hl[NHL], fl, sl0, sl1, scratch[NHL]
-    Group<NT, 2 * NHCh + 3, LANES, (PLACE & P_STASHC) != 0> stc; // hc[NHC], fc, sc0, sc1, scratch[NHC]
+    Group<NT, 2 * NHL + 3, LANES, (PLACE & P_STASHL) != 0> stl; // hl[NHL], fl, sl0, sl1, scratch[NHL]
+    Group<NT, 2 * NHC + 3, LANES, (PLACE & P_STASHC) != 0> stc; // hc[NHC], fc, sc0, sc1, scratch[NHC]
     SmemVec<NT, 10, LANES> hypn;                                 // HYP: gamma, lr_a, lr_c, tau, scale x (col, lon)
     SmemVec<ET, 2, LANES> hype;                                  // HYP: reward weights (col, lon)
     {
@@ -259,7 +240,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         misce[2] = (ET)P.trim[ec];
         misce[3] = (ET)P.trim[ld + ec];
     }
-    if (valid && lead) {
+    if (valid) {
         if constexpr (HYP) {
             double wc, wl;
             const AgentH<NT> hc_ = load_hyper<NT>(P.col, P.col_hyper, ld, ec, wc);
@@ -283,15 +264,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         if (COL) col.v.load(P.col_net + ec, ld);
     }
     if constexpr ((PLACE & P_LON) != 0) {
-        if (valid && lead) lon.v.load(P.lon_net + ec, ld);              // TAU1L: rows [0, 7 nh) only
-    } else if constexpr (PAIR) {
-#pragma unroll
-        for (int r = 0; r < NNL; ++r)                                   // this lane's hidden units only
-            lon.v[r] = P.lon_net[(int64_t)net_row_global<NHL, NHLh>(r, half * NHLh) * ld + ec];
+        if (valid) lon.v.load(P.lon_net + ec, ld);                      // TAU1L: rows [0, 7 nh) only
     } else {
         lon.v.load(P.lon_net + ec, ld);
     }
-    if (PAIR) __syncwarp();                 // the partner lane reads what the lead lane staged
 
     const bool lockstep = P.step0 >= 0;
     int heat = 0;
@@ -313,8 +289,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             __syncthreads();
         }
         for (int jj = 0; jj < cn; ++jj) {
-            const unsigned amask = PAIR ? __ballot_sync(0xffffffffu, flags == 0) : 0xffffffffu;
-            if (flags != 0) continue;       // terminated (or idle) lane: frozen (both lanes of a pair agree)
+            constexpr unsigned amask = 0xffffffffu;
+            if (flags != 0) continue;       // terminated (or idle) lane: frozen
             heat = 0;
             const int k = lockstep ? (P.step0 + c0 + jj) : step;
             const bool phase2 = COL && (k >= P.switch_step);                    // main_3dof.py:127-137
@@ -333,23 +309,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 NT fl;
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
-                const NT a_lon = actor_forward<NT, NHLh, UL, PAIR>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
-                                                                    stl, fl, amask, &heat, H3_HEAT_LON);
+                const NT a_lon = actor_forward<NT, NHL, UL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, stl, fl,
+                                                            amask, &heat, H3_HEAT_LON);
                 cyc = misce[3] + (ET)a_lon;
-                stl[NHLh] = fl;
-                stl[NHLh + 1] = sl0;
-                stl[NHLh + 2] = sl1;
+                stl[NHL] = fl;
+                stl[NHL + 1] = sl0;
+                stl[NHL + 2] = sl1;
             }
             if (phase2) {
                 NT fc;
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
-                const NT a_col = actor_forward<NT, NHCh, UC, PAIR>(col, sc0, sc1, Hcol.scale, P.col.final_activation,
-                                                                    stc, fc, amask, &heat, H3_HEAT_COL);
+                const NT a_col = actor_forward<NT, NHC, UC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, stc, fc,
+                                                            amask, &heat, H3_HEAT_COL);
                 colv = misce[2] + (ET)a_col;
-                stc[NHCh] = fc;
-                stc[NHCh + 1] = sc0;
-                stc[NHCh + 2] = sc1;
+                stc[NHC] = fc;
+                stc[NHC + 1] = sc0;
+                stc[NHC + 2] = sc1;
             }
             ET exc0 = (ET)0, exc1 = (ET)0;                                      // main_3dof.py:139-140
             if (lockstep) {
@@ -405,7 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             }
             if (P.task == H3_TASK_VELOCITY) misce[0] = cu;
             // -------- log row (main_3dof.py:164-175): pre-step obs and ref, applied actions; rewards below ----
-            const bool rec = P.traj != nullptr && e < P.n_traj && lead;
+            const bool rec = P.traj != nullptr && e < P.n_traj;
             ET* row = rec ? P.traj + ((int64_t)(c0 + jj) * H3_TRAJ_ROWS) * P.ld_traj + e : nullptr;
             if (rec) {
 #pragma unroll
@@ -422,8 +398,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             } else {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) Y[i] = s[i] - Y[i];                 // model.py:43
-                rls_update<ET, RD, PAIR && H3_PAIR_SPLIT_W>(K, Wm, cov, X, Y, half);
-                if (PAIR) __syncwarp(amask);            // F, G below read columns owned by the partner lane
+                rls_update<ET, RD>(K, Wm, cov, X, Y);
             }
             // -------- cyclic agent (main_3dof.py:148-151) --------
             double r_lon = 0.0, r_col = 0.0;
@@ -435,10 +410,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 transition_matrices<ET, NT>(Wm, P.lon, F, G);
                 const NT n0 = (NT)pick7(s, P.lon.ac_state);
                 const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
-                SubVec<decltype(stl), NT> scr{stl, NHLh + 3};
-                agent_update<NT, NHLh, UL, TAU1L, PAIR>(lon, Hlon, P.lon.final_activation, stl[NHLh + 1],
-                                                        stl[NHLh + 2], n0, n1, (NT)0, dr, F, G, stl, stl[NHLh], scr,
-                                                        amask, &heat, H3_HEAT_LON);
+                SubVec<decltype(stl), NT> scr{stl, NHL + 3};
+                agent_update<NT, NHL, UL, TAU1L>(lon, Hlon, P.lon.final_activation, stl[NHL + 1], stl[NHL + 2], n0, n1,
+                                                 (NT)0, dr, F, G, stl, stl[NHL], scr, amask, &heat, H3_HEAT_LON);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -449,10 +423,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 transition_matrices<ET, NT>(Wm, P.col, F, G);
                 const NT n0 = (NT)pick7(s, P.col.ac_state);
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
-                SubVec<decltype(stc), NT> scr{stc, NHCh + 3};
-                agent_update<NT, NHCh, UC, false, PAIR>(col, Hcol, P.col.final_activation, stc[NHCh + 1],
-                                                        stc[NHCh + 2], n0, n1, (NT)0, dr, F, G, stc, stc[NHCh], scr,
-                                                        amask, &heat, H3_HEAT_COL);
+                SubVec<decltype(stc), NT> scr{stc, NHC + 3};
+                agent_update<NT, NHC, UC, false>(col, Hcol, P.col.final_activation, stc[NHC + 1], stc[NHC + 2], n0, n1,
+                                                 (NT)0, dr, F, G, stc, stc[NHC], scr, amask, &heat, H3_HEAT_COL);
             }
             if (rec) {
                 row[10 * P.ld_traj] = (ET)r_col;
@@ -474,20 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
 
     // ---- exit store ----
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    if (PAIR) __syncwarp();                 // the lead lane stores what both lanes of the pair updated
-    if (valid && !lead) {                   // PAIR: the partner stores its own half of the cyclic agent
-        if constexpr (PAIR && (PLACE & P_LON) == 0) {
-#pragma unroll
-            for (int r = 0; r < NNL; ++r)
-                P.lon_net[(int64_t)net_row_global<NHL, NHLh>(r, half * NHLh) * ld + e] = lon.v[r];
-            if (TAU1L) {
-#pragma unroll
-                for (int r = 3 * NHLh; r < 7 * NHLh; ++r)
-                    P.lon_net[(int64_t)net_row_global<NHL, NHLh>(r + 4 * NHLh, half * NHLh) * ld + e] = lon.v[r];
-            }
-        }
-    }
-    if (valid && lead) {
+    if (valid) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) P.state[i * ld + e] = s[i];
         P.ref[ld + e] = refth;
@@ -524,21 +484,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         }
 #pragma unroll
         for (int i = 0; i < 63; ++i) P.rls_W[i * ld + e] = Wm.v[i];
-        if constexpr (PAIR && (PLACE & P_LON) == 0) {
+        lon.v.store(P.lon_net + e, ld);
+        if (TAU1L) {                // target critic == critic (agents.py:196 with tau = 1)
 #pragma unroll
-            for (int r = 0; r < NNL; ++r)
-                P.lon_net[(int64_t)net_row_global<NHL, NHLh>(r, 0) * ld + e] = lon.v[r];
-            if (TAU1L) {
-#pragma unroll
-                for (int r = 3 * NHLh; r < 7 * NHLh; ++r)
-                    P.lon_net[(int64_t)net_row_global<NHL, NHLh>(r + 4 * NHLh, 0) * ld + e] = lon.v[r];
-            }
-        } else {
-            lon.v.store(P.lon_net + e, ld);
-            if (TAU1L) {            // target critic == critic (agents.py:196 with tau = 1)
-#pragma unroll
-                for (int i = 0; i < 4 * NHL; ++i) P.lon_net[(int64_t)(7 * NHL + i) * ld + e] = lon.v[3 * NHL + i];
-            }
+            for (int i = 0; i < 4 * NHL; ++i) P.lon_net[(int64_t)(7 * NHL + i) * ld + e] = lon.v[3 * NHL + i];
         }
         if (COL) col.v.store(P.col_net + e, ld);
     }
@@ -546,7 +495,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     // ---- statistics epilogue: block partials -> last block sums them in a fixed order ----
     if (P.stats != nullptr) {
         double v[H3_N_STATS];
-        const bool cnt = valid && lead;
+        const bool cnt = valid;
         v[0] = cnt ? 1.0 : 0.0;
         v[1] = (cnt && flags == 0) ? 1.0 : 0.0;
         v[2] = (cnt && (flags & H3_FLAG_DONE)) ? 1.0 : 0.0;

@@ -3,9 +3,9 @@
 // TENSOR MEMORY (h3_tmem.cuh).
 //
 // Why: in these launches an episode carries 2.3-2.7 KB of fp64 state.  Registers (256 KB per SM) and shared
-// memory (227 KB) together hold 128 episodes per SM -- one warp per scheduler with a lane per episode, or the
-// two-lanes-per-episode PAIR scheme of h3_closed_loop.cuh that buys a second warp per scheduler by executing the
-// model step, PID and covariance update twice.  An sm_100a SM has a third on-chip store: 256 KB of tensor
+// memory (227 KB) together hold 128 episodes per SM -- one warp per scheduler with a lane per episode (round 1 bought
+// a second warp per scheduler with two lanes per episode, at the price of executing the model step, PID and
+// covariance update twice: 145 warp-instructions per env-step against 97 here).  An sm_100a SM has a third on-chip store: 256 KB of tensor
 // memory, 128 lanes x 512 columns x 32 bit, and its 32x32b access shape is exactly "N private columns per
 // thread".  With the collective agent's 11 nh weights (+ the hidden activations kept from the forward pass) in
 // TMEM, the RLS matrices in shared memory and the cyclic agent in registers, 8 warps x 32 episodes are resident
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 NT fl;
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
-                const NT a_lon = actor_forward<NT, NHL, NHL, false>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
+                const NT a_lon = actor_forward<NT, NHL, NHL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
                                                                     stl, fl, FULL, &heat, H3_HEAT_LON);
                 cyc = trim1 + (ET)a_lon;
                 stl[NHL] = fl;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             } else {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) Y[i] = s[i] - Y[i];                     // model.py:43
-                rls_update<ET, RD, false>(K, Wm, cov, X, Y, 0);
+                rls_update<ET, RD>(K, Wm, cov, X, Y);
             }
             // -------- cyclic agent (main_3dof.py:148-151) --------
             double r_lon = 0.0, r_col = 0.0;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl0 = (NT)pick7(prev, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? prev[1] : pick7(prev, P.lon.tracked_state) - refth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
-                agent_update<NT, NHL, NHL, TAU1L, false>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
+                agent_update<NT, NHL, NHL, TAU1L>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
                                                          F, G, stl, stl[NHL], scr, FULL, &heat, H3_HEAT_LON);
             }
             // -------- collective agent (main_3dof.py:156-159) --------

@@ -37,26 +37,13 @@ enum { VAR_FAST = 0, VAR_SWEEP = 1, VAR_GENERAL = 2 };
 constexpr size_t SMEM_PER_BLOCK_MAX = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 // On-chip placement per variant.  Phase-1 launches (COL == false) keep everything
-// but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM); launches with the
-// collective agent run one 4-warp CTA per SM with as many episodes per warp as the tile allows.
+// but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM).  Launches with the collective agent
+// go to the tensor-memory kernel (below) when they are lockstep and the covariance is symmetric; the rest
+// (heterogeneous batches, the literal non-symmetric update) run one 4-warp CTA per SM with as many episodes per
+// warp as the shared-memory tile allows.
 // ---- tuning knobs (compile-time; defaults are the measured best) ----
 #ifndef H3_SWEEP_P1_REGS
 #define H3_SWEEP_P1_REGS 1
-#endif
-#ifndef H3_PAIR_ALL
-#define H3_PAIR_ALL 0       // tuning: PAIR also for the SWEEP / GENERAL variants
-#endif
-#ifndef H3_P1_PAIR
-#define H3_P1_PAIR 0        // tuning: two lanes per episode in phase-1 launches as well
-#endif
-#ifndef H3_P1_MINB
-#define H3_P1_MINB 1
-#endif
-#ifndef H3_P1_WARPS
-#define H3_P1_WARPS 8
-#endif
-#ifndef H3_P2_WARPS
-#define H3_P2_WARPS 8    // PAIR launches: warps per CTA (8 / H3_P2_WARPS CTAs per SM)
 #endif
 #ifndef H3_RD_P1
 #define H3_RD_P1 1
@@ -70,24 +57,17 @@ struct Tune {
     static constexpr bool SYM = VAR != VAR_GENERAL, HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
     // the full cyclic agent (11 nh words) goes to the tile in collective-agent launches of the SWEEP / GENERAL
     // variants; phase-1 launches keep it in registers (7 instead of 4 warps per SM)
-    static constexpr bool lon_smem = !TAU1L && !(H3_PAIR_ALL && COL) && (COL || !H3_SWEEP_P1_REGS);
-#ifndef H3_NO_PAIR
-    // collective-agent launches of the fast variant: two lanes per episode (see closed_loop_kernel, PAIR)
-    static constexpr bool PAIR = (COL || H3_P1_PAIR) && (VAR == VAR_FAST || H3_PAIR_ALL) && NHL % 2 == 0 && NHC % 2 == 0;
-#else
-    static constexpr bool PAIR = false;
-#endif
-    static constexpr int MINB = (!COL && PAIR) ? H3_P1_MINB : ((COL && PAIR) ? 8 / H3_P2_WARPS : 1);
-    static constexpr int PLACE = PAIR ? 0 : ((COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0));
-    static constexpr int UL = PAIR ? NHL / 2 : (lon_smem ? NHL / 2 : NHL);
-    static constexpr int UC = PAIR ? NHC / 2 : (COL ? NHC / 2 : NHC);
-    static constexpr int WARPS = PAIR ? (COL ? H3_P2_WARPS : H3_P1_WARPS) : (COL ? 4 : 1);
+    static constexpr bool lon_smem = !TAU1L && (COL || !H3_SWEEP_P1_REGS);
+    static constexpr int MINB = 1;
+    static constexpr int PLACE = (COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0);
+    static constexpr int UL = lon_smem ? NHL / 2 : NHL;
+    static constexpr int UC = COL ? NHC / 2 : NHC;
+    static constexpr int WARPS = COL ? 4 : 1;
     static constexpr int RD = COL ? H3_RD_P2 : H3_RD_P1;    // RLS stream look-ahead (groups)
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
     static constexpr size_t room = (SMEM_PER_BLOCK_MAX / MINB - 1024 * (MINB - 1) - L32::head_bytes(WARPS)) / WARPS - 16;
     static constexpr int fit = (int)(room / L32::bytes_per_lane);
-    static constexpr int cap = PAIR ? 16 : 32;
-    static constexpr int LANES = fit >= cap ? cap : fit;
+    static constexpr int LANES = fit >= 32 ? 32 : fit;
     static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");
 };
 
@@ -97,7 +77,7 @@ static KernelSel<ET, NT> sel_kernel() {
     typedef LoopLayout<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES> LY;
     KernelSel<ET, NT> k;
     k.fn = closed_loop_kernel<ET, NT, NHL, NHC, COL, T::SYM, T::HYP, T::TAU1L, T::PLACE, T::LANES, T::WARPS, T::UL,
-                              T::UC, T::RD, T::PAIR, T::MINB>;
+                              T::UC, T::RD, T::MINB>;
     k.block = T::WARPS * 32;
     k.lanes = T::LANES;
     k.warps = T::WARPS;
@@ -296,12 +276,6 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
             return H3_E_CUDA;
         }
     }
-#ifdef H3_WIDE_IMPL
-    if constexpr (std::is_same<ET, double>::value && std::is_same<NT, double>::value) {
-        // launches in which both agents learn, main_3dof.py configuration: the 16-warps-per-32-episodes kernel
-        if (col && wide_eligible(cfg, b, step0, n_ticks, ref_table, traj)) return launch_wide(P, stream);
-    }
-#endif
     k.fn<<<(unsigned)grid, k.block, k.smem, stream>>>(P);
     err = cudaGetLastError();
     if (err != cudaSuccess) {

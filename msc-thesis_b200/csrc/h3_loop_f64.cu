@@ -1,7 +1,5 @@
 // Instantiates the fused closed-loop kernel for env type double, network type double.
 #define H3_LOOP_IMPL
-#define H3_WIDE_IMPL
-#include "h3_wide.cuh"
 #include "h3_launch.cuh"
 
 namespace h3 {

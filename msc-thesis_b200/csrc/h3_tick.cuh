@@ -164,11 +164,8 @@ H3_DEV void stream_groups(Load load, Body body) {
     }
 }
 
-//   PAIR: the two lanes of an episode split the 7 output columns of W (lane half h owns columns
-//   [4h, 4h + NC), NC = 4 or 3): the prediction error and the weight update of a column need nothing from
-//   the other columns, so no exchange is required; the covariance part is computed by both lanes.
-template <typename T, int DEPTH, bool PAIR = false, typename WAcc, typename CAcc>
-H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7], int half = 0) {
+template <typename T, int DEPTH, typename WAcc, typename CAcc>
+H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], const T (&Y)[7]) {
     constexpr bool F = WAcc::kFence;
     // gain first: it needs the covariance only (model.py:53-55)
     T covX[9], Xcov[9];
@@ -182,25 +179,18 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
     // then ONE pass over W, column by column: the prediction error of output j (model.py:49-50) and the update of
     // column j (:58) need nothing from the other columns, so each weight is loaded once, not twice.
-    //   PAIR: lane half h owns columns [4h, 4h + 4) (the 4th slot of half 1 re-does column 6 and is not stored).
-    constexpr int NC = PAIR ? 4 : 7;
-    stream_groups<T, NC, 9, DEPTH, F>(
-        [&](int jl, T (&w)[9]) {
-            const int j = PAIR ? ((jl == 3) ? (half ? 6 : 3) : 4 * half + jl) : jl;
+    stream_groups<T, 7, 9, DEPTH, F>(
+        [&](int j, T (&w)[9]) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) w[i] = Wm.dyn(i, j);
         },
-        [&](int jl, T (&w)[9]) {
-            const int j = PAIR ? ((jl == 3) ? (half ? 6 : 3) : 4 * half + jl) : jl;
-            const T yj = PAIR ? (half ? Y[jl < 3 ? 4 + jl : 6] : Y[jl]) : Y[jl];
+        [&](int j, T (&w)[9]) {
             // two partial sums keep the 9-long dependent chain short
-            const T ea = ((yj - X[0] * w[0]) - X[2] * w[2]) - X[4] * w[4] - X[6] * w[6] - X[8] * w[8];
+            const T ea = ((Y[j] - X[0] * w[0]) - X[2] * w[2]) - X[4] * w[4] - X[6] * w[6] - X[8] * w[8];
             const T eb = ((X[1] * w[1] + X[3] * w[3]) + X[5] * w[5]) + X[7] * w[7];
             const T err = ea - eb;
-            if (!PAIR || jl < 3 || !half) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) Wm.ref(i, j) = w[i] + g[i] * err;
-            }
+            for (int i = 0; i < 9; ++i) Wm.ref(i, j) = w[i] + g[i] * err;
         });
     Cv.template downdate<DEPTH>(g, Xcov, K.rls_inv_gamma);              // :59
 }
@@ -304,18 +294,8 @@ struct AgentH {             // hyper-parameters in network precision
     NT gamma, lr_a, lr_c, tau, scale;
 };
 
-// PAIR mode: two lanes (l, l ^ 16) of a warp share one episode and split every hidden layer in halves;
-// sums over hidden units are completed with one butterfly exchange.  a + b == b + a bit for bit, so
-// both lanes of a pair hold identical values afterwards.
-template <bool PAIR, typename T>
-H3_DEV T pair_sum(T x, unsigned mask) {
-    if (PAIR) x += __shfl_xor_sync(mask, x, 16);
-    return x;
-}
-
 // DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
-//   NH = hidden units handled by THIS lane (all of them, or half in PAIR mode).
-template <typename NT, int NH, int U, bool PAIR = false, typename Net, typename HVec>
+template <typename NT, int NH, int U, typename Net, typename HVec>
 H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f, unsigned mask = 0xffffffffu,
                         int* heat = nullptr, int heat_bit = 0) {
     typedef Math<NT> M;
@@ -338,7 +318,6 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
             y += net.a2(k) * hk[u];
         }
     }
-    y = pair_sum<PAIR>(y, mask);
     f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
     return scale * f;
 }
@@ -352,7 +331,7 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
 //   TAU1: tau_target_critic == 1 for every episode of the launch -> the target critic IS the critic after
 //   every update (agents.py:196: 1*p + 0*t), so its rows are neither kept on chip nor updated; lambda_t2
 //   is evaluated with the critic's (pre-update) weights, which are the target's.
-template <typename NT, int NH, int U, bool TAU1, bool PAIR = false, typename Net, typename HVec, typename SVec>
+template <typename NT, int NH, int U, bool TAU1, typename Net, typename HVec, typename SVec>
 H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
                          const NT (&F)[2][2], const NT (&G)[2], HVec& h_a, NT f, SVec& scr,
                          unsigned mask = 0xffffffffu, int* heat = nullptr, int heat_bit = 0) {
@@ -404,12 +383,6 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
             da_ds[0] += net.a1(k, 0) * pk;
             da_ds[1] += net.a1(k, 1) * pk;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        lam1[j] = pair_sum<PAIR>(lam1[j], mask);
-        lam2[j] = pair_sum<PAIR>(lam2[j], mask);
-        da_ds[j] = pair_sum<PAIR>(da_ds[j], mask);
     }
     // target = dr_ds + gamma * lambda_t2 ; error_critic = lambda_t1 - target (F + G da_ds)  (:178-179)
     const NT tg0 = dr0 + H.gamma * lam2[0];     // dr_ds[0] is 0 in get_reward (agents.py:124)
@@ -518,28 +491,15 @@ struct WMat {               // RLS weights (9,7) row-major
     H3_DEV T& ref(int i, int j) { return v[i * 7 + j]; }
 };
 
-template <typename NT, int NH, typename Vec, bool OFFS = false>
+template <typename NT, int NH, typename Vec>
 struct NetAcc {             // rows of the `[11*nh][ld]` network block (include/heli3dof.h)
     Vec v;
-    int koff_ = 0;          // OFFS: first hidden unit of this lane inside the storage (PAIR mode: 0 or NH / 2)
-    H3_DEV int ko() const { return OFFS ? koff_ : 0; }
-    H3_DEV NT& a1(int k, int i) { return v[2 * (k + ko()) + i]; }
-    H3_DEV NT& a2(int k) { return v[2 * NH + k + ko()]; }
-    H3_DEV NT& c1(int k, int i) { return v[3 * NH + 2 * (k + ko()) + i]; }
-    H3_DEV NT& c2(int j, int k) { return v[5 * NH + j * NH + k + ko()]; }
-    H3_DEV NT& t1(int k, int i) { return v[7 * NH + 2 * (k + ko()) + i]; }
-    H3_DEV NT& t2(int j, int k) { return v[9 * NH + j * NH + k + ko()]; }
+    H3_DEV NT& a1(int k, int i) { return v[2 * k + i]; }
+    H3_DEV NT& a2(int k) { return v[2 * NH + k]; }
+    H3_DEV NT& c1(int k, int i) { return v[3 * NH + 2 * k + i]; }
+    H3_DEV NT& c2(int j, int k) { return v[5 * NH + j * NH + k]; }
+    H3_DEV NT& t1(int k, int i) { return v[7 * NH + 2 * k + i]; }
+    H3_DEV NT& t2(int j, int k) { return v[9 * NH + j * NH + k]; }
 };
-
-// Row of the full `[11*NH]` block that holds local row r of a half-width (NHh units, first unit koff) copy
-template <int NH, int NHh>
-H3_DEV int net_row_global(int r, int koff) {
-    if (r < 2 * NHh) return r + 2 * koff;                                   // actor fc1
-    if (r < 3 * NHh) return 2 * NH + (r - 2 * NHh) + koff;                  // actor fc2
-    if (r < 5 * NHh) return 3 * NH + (r - 3 * NHh) + 2 * koff;              // critic fc1
-    if (r < 7 * NHh) return 5 * NH + ((r - 5 * NHh) / NHh) * NH + (r - 5 * NHh) % NHh + koff;   // critic fc2
-    if (r < 9 * NHh) return 7 * NH + (r - 7 * NHh) + 2 * koff;              // target fc1
-    return 9 * NH + ((r - 9 * NHh) / NHh) * NH + (r - 9 * NHh) % NHh + koff;                    // target fc2
-}
 
 }  // namespace h3

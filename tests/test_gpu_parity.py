@@ -579,27 +579,6 @@ def test_compaction_changes_nothing_but_the_order(h3):
         assert abs(sp[k] - sc[k]) <= 1e-9 * abs(sp[k])
 
 
-def test_wide_kernel_option_matches_the_default_kernel(h3, monkeypatch):
-    """csrc/h3_wide.cuh (16 warps per 32 episodes; opt-in with H3_WIDE=1, slower than the default kernel): same
-    results as the one-thread-per-episode kernel on launches where both agents learn."""
-    import bench
-    outs = []
-    for wide in ("0", "1"):
-        monkeypatch.setenv("H3_WIDE", wide)
-        loop = bench.make_workload(h3, torch, 777, "f64", torch.device("cuda", 0), seed=5, store=0, ticks=40)
-        loop.switch_step = 40
-        loop.run(40)
-        loop.run(80)
-        outs.append((loop.env.state.clone(), loop.rls.W.clone(), loop.rls.cov.clone(), loop.agent_col.net.clone(),
-                     loop.agent_lon.net.clone(), loop.env.flags.clone(), loop.stats()))
-    for a, b in zip(outs[0][:5], outs[1][:5]):
-        scale = a.abs().max().item()
-        assert (a - b).abs().max().item() <= 1e-9 * scale
-    assert torch.equal(outs[0][5], outs[1][5])
-    assert outs[0][6]["sum_ticks"] == outs[1][6]["sum_ticks"] and outs[0][6]["n_alive"] == outs[1][6]["n_alive"]
-    assert abs(outs[0][6]["sum_r_lon"] - outs[1][6]["sum_r_lon"]) <= 1e-9 * abs(outs[0][6]["sum_r_lon"])
-
-
 def test_host_batch_pipeline_compact_and_full_formats_agree(h3):
     """HostBatchPipeline (the e2e path): a host-resident batch streamed chunk by chunk gives the results of running the
     same episodes device-resident, with the compact host format (covariance upper triangle, no tau = 1 target critic)
@@ -634,3 +613,66 @@ def test_host_batch_pipeline_compact_and_full_formats_agree(h3):
                     assert (got - w).abs().max().item() <= 1e-9 * max(w.abs().max().item(), 1e-30)
                 else:
                     assert torch.equal(got, w)
+
+
+def test_lockstep_run_issues_no_synchronising_call(h3):
+    """The reference table of the lockstep clock is built once for the whole horizon and lives on the device: after the
+    first run() a lockstep launch sequence (phase switch, statistics, several launches) contains no host <-> device copy
+    and no synchronisation -- checked with torch's sync debug mode, which raises on any synchronising CUDA call."""
+    run = h3.EpisodeRunner(4096, device="cuda", per_episode_hyper=False, switch_step=150, ticks_per_launch=100)
+    run.params.copy_(h3.episodes.default_params(4096))
+    Rw = h3.episodes.ROW
+    kw = dict(v_trim=run.params[Rw["v_trim"]], sigma=run.params[Rw["sigma_col_actor"]:Rw["sigma_lon_critic"] + 1])
+    run.loop.init_episodes(1, **kw)
+    run.loop.run(300)                           # builds the table (one asynchronous upload from pinned memory)
+    want = run.loop.env.state.clone()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        run.loop.init_episodes(1, **kw)
+        run.loop.run(300)
+        run.loop.run(500)                       # continues the same clock: still inside the table
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert run.loop.launches >= 2 * 4 + 5 and run.loop.k == 800
+    run.loop.init_episodes(1, **kw)
+    run.loop.run(300)
+    assert torch.equal(run.loop.env.state, want)
+
+
+def test_run_logged_weight_history(h3):
+    """main_3dof.py:178-186: the weight / F, G history after the ticks 0, 10, 20, ... next to the per-tick rows --
+    cutting the launches at the logged ticks changes nothing, the entries have the script's shapes and values."""
+    n, R, ticks = 64, 3, 95
+    def fresh():
+        lp = h3.episodes.make_loop(n, torch.device("cuda"), switch_step=40, ticks_per_launch=1000)
+        P = h3.episodes.default_params(n).cuda()
+        lp.init_episodes(3, v_trim=P[h3.episodes.ROW["v_trim"]], sigma=P[3:7])
+        return lp
+    plain = fresh()
+    want = plain.run(ticks, record=R)
+    lg = fresh()
+    traj, ws = lg.run_logged(ticks, every=10, episodes=R)
+    assert torch.equal(traj, want) and torch.equal(lg.env.state, plain.env.state)
+    assert torch.equal(lg.agent_col.net, plain.agent_col.net) and torch.equal(lg.rls._W, plain.rls._W)
+    T = 10                                                      # ticks 0, 10, ..., 90
+    assert ws["t"].shape == (ticks,) and abs(float(ws["t"][-1]) - 0.95) < 1e-12
+    assert ws["col"]["nn"]["a"]["i"].shape == (T, 20, R) and ws["col"]["nn"]["tc"]["o"].shape == (T, 20, R)
+    assert ws["lon"]["nn"]["c"]["i"].shape == (T, 12, R) and ws["lon"]["nn"]["a"]["o"].shape == (T, 6, R)
+    assert ws["lon"]["rls"]["F"].shape == (T, 4, R) and ws["col"]["rls"]["G"].shape == (T, 2, R)
+    # entry j = state after tick 10 j: compare with a plain run stopped there
+    chk = fresh()
+    chk.run(1)
+    assert torch.equal(ws["lon"]["nn"]["a"]["i"][0], chk.agent_lon.actor.fc1.weight[..., :R].reshape(-1, R).cpu())
+    F, G = chk.agent_lon.get_transition_matrices(chk.rls)
+    assert torch.equal(ws["lon"]["rls"]["F"][0], F[..., :R].reshape(4, R).cpu())
+    chk.run(50)
+    assert torch.equal(ws["col"]["nn"]["c"]["o"][5], chk.agent_col.critic.fc2.weight[..., :R].reshape(-1, R).cpu())
+    Fc, Gc = chk.agent_col.get_transition_matrices(chk.rls)
+    assert torch.equal(ws["col"]["rls"]["G"][5], Gc[..., :R].reshape(2, R).cpu())
+    # main_3dof.py:181 walks agent_col.networks for both agents: as_reference reproduces that
+    _, wr = fresh().run_logged(11, every=10, episodes=R, as_reference=True)
+    assert torch.equal(wr["lon"]["nn"]["a"]["i"], wr["col"]["nn"]["a"]["i"]) and wr["lon"]["nn"]["a"]["i"].shape == (2, 20, R)
+    df = lg.to_dataframe(traj, 1)
+    assert len(df) == ticks and abs(df["t"].iloc[0] - 0.01) < 1e-15
