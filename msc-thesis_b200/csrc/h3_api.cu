@@ -496,6 +496,50 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     }
 }
 
+// any other width: runtime-width versions on global memory (h3_closed_loop_rt.cuh)
+template <typename ET, typename NT>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_action_rt_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
+                           const ET* __restrict__ ref, NT* out, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    double w_r;
+    const AgentH<NT> H = load_hyper<NT>(h, hyper, ld, e, w_r);
+    RtNet<NT> N{net + e, ld, h.n_hidden};
+    const int ri = (h.tracked_state == 1) ? 0 : 1;
+    const NT s0 = (NT)state[h.ac_state * ld + e];
+    const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
+    NT f;
+    out[e] = actor_forward_rt(N, s0, s1, H.scale, h.final_activation, f);
+}
+
+template <typename ET, typename NT>
+__global__ void __launch_bounds__(SMALL_BLOCK)
+    agent_update_rt_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
+                           const ET* __restrict__ next_state, const ET* __restrict__ ref,
+                           const ET* __restrict__ next_ref, const NT* __restrict__ dr_ds, const NT* __restrict__ Fm,
+                           const NT* __restrict__ Gm, int64_t n, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
+    if (e >= n) return;
+    double w_r;
+    const AgentH<NT> H = load_hyper<NT>(h, hyper, ld, e, w_r);
+    RtNet<NT> N{net + e, ld, h.n_hidden};
+    const int ri = (h.tracked_state == 1) ? 0 : 1;
+    const int ia = h.ac_state, it = h.tracked_state;
+    const NT s0 = (NT)state[ia * ld + e];
+    const NT s1 = (NT)(state[it * ld + e] - ref[ri * ld + e]);
+    const NT n0 = (NT)next_state[ia * ld + e];
+    const NT n1 = (NT)(next_state[it * ld + e] - next_ref[ri * ld + e]);
+    NT F[2][2], G[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) F[i][j] = Fm[(i * 2 + j) * ld + e];
+        G[i] = Gm[i * ld + e];
+    }
+    agent_update_rt(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G);
+}
+
 struct AgentArgs {
     const void *state, *next_state, *ref, *next_ref, *dr_ds, *F, *G;
     void* out;
@@ -522,8 +566,18 @@ static int dispatch_agent(bool update, const H3AgentHyper& h, const double* hype
         H3_AGENT_CASE(12)
         H3_AGENT_CASE(16)
         default:
-            set_error("agent kernels are compiled for n_hidden in {4,6,8,10,12,16}, got %d", h.n_hidden);
-            return H3_E_UNSUPPORTED;
+            if (h.n_hidden < 1) {
+                set_error("agent kernels: n_hidden must be positive, got %d", h.n_hidden);
+                return H3_E_ARG;
+            }
+            if (update)
+                agent_update_rt_kernel<ET, NT><<<grid_for(n), SMALL_BLOCK, 0, st>>>(
+                    h, hyper, (NT*)net, (const ET*)a.state, (const ET*)a.next_state, (const ET*)a.ref,
+                    (const ET*)a.next_ref, (const NT*)a.dr_ds, (const NT*)a.F, (const NT*)a.G, n, ld);
+            else
+                agent_action_rt_kernel<ET, NT><<<grid_for(n), SMALL_BLOCK, 0, st>>>(
+                    h, hyper, (NT*)net, (const ET*)a.state, (const ET*)a.ref, (NT*)a.out, n, ld);
+            break;
     }
 #undef H3_AGENT_CASE
     return check_launch(update ? "agent_update_kernel" : "agent_action_kernel");

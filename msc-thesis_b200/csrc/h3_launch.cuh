@@ -5,6 +5,7 @@
 
 #include "h3_closed_loop.cuh"
 #include "h3_closed_loop_tm.cuh"
+#include "h3_closed_loop_rt.cuh"
 
 namespace h3 {
 
@@ -171,11 +172,22 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     else if (nhl == 8 && nhc == 8) k = sel_flags<ET, NT, 8, 8>(col, variant, tm);
 #endif
     else {
-        set_error("h3_closed_loop: hidden widths (lon %d, col %d) not compiled in (have 6/10, 8/8)", nhl, nhc);
-        return H3_E_UNSUPPORTED;
+        // any other width: the runtime-width kernel (h3_closed_loop_rt.cuh), everything in global memory
+        if (nhl < 1 || nhc < 1) {
+            set_error("h3_closed_loop: hidden widths must be positive (lon %d, col %d)", nhl, nhc);
+            return H3_E_ARG;
+        }
+        k.fn = nullptr;
+        k.block = RT_BLOCK;
+        k.lanes = 32;
+        k.warps = RT_BLOCK / 32;
+        k.smem = 0;
     }
-    cudaError_t err = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
-    if (err == cudaSuccess)         // every variant is sized to fill the SM's shared memory with co-resident CTAs
+    const bool rt = k.fn == nullptr;
+    void (*rt_fn)(const LoopParams<ET, NT>, int, int) = closed_loop_rt_kernel<ET, NT>;
+    cudaError_t err = cudaSuccess;
+    if (!rt) err = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
+    if (!rt && err == cudaSuccess)  // every variant is sized to fill the SM's shared memory with co-resident CTAs
         err = cudaFuncSetAttribute(k.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(smem=%zu): %s", k.smem, cudaGetErrorString(err));
@@ -183,13 +195,14 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     }
     if (info_only != nullptr) {
         cudaFuncAttributes fa;
-        err = cudaFuncGetAttributes(&fa, k.fn);
+        err = rt ? cudaFuncGetAttributes(&fa, rt_fn) : cudaFuncGetAttributes(&fa, k.fn);
         if (err != cudaSuccess) {
             set_error("cudaFuncGetAttributes: %s", cudaGetErrorString(err));
             return H3_E_CUDA;
         }
         int nb = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.fn, k.block, k.smem);
+        err = rt ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_fn, k.block, k.smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k.fn, k.block, k.smem);
         if (err != cudaSuccess) {
             set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor: %s", cudaGetErrorString(err));
             return H3_E_CUDA;
@@ -276,7 +289,10 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
             return H3_E_CUDA;
         }
     }
-    k.fn<<<(unsigned)grid, k.block, k.smem, stream>>>(P);
+    if (rt)
+        rt_fn<<<(unsigned)grid, k.block, 0, stream>>>(P, nhl, nhc);
+    else
+        k.fn<<<(unsigned)grid, k.block, k.smem, stream>>>(P);
     err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error("closed_loop_kernel launch (grid %lld, block %d, smem %zu): %s", (long long)grid, k.block, k.smem,

@@ -676,3 +676,30 @@ def test_run_logged_weight_history(h3):
     assert torch.equal(wr["lon"]["nn"]["a"]["i"], wr["col"]["nn"]["a"]["i"]) and wr["lon"]["nn"]["a"]["i"].shape == (2, 20, R)
     df = lg.to_dataframe(traj, 1)
     assert len(df) == ticks and abs(df["t"].iloc[0] - 0.01) < 1e-15
+
+
+@pytest.mark.parametrize("nh_lon,nh_col", [(5, 7), (3, 16), (12, 1)])
+def test_arbitrary_hidden_widths_vs_oracle(h3, nh_lon, nh_col):
+    """agents.py:74-78 takes any hidden width; widths the fused kernels are not compiled for run on the runtime-width
+    kernel (csrc/h3_closed_loop_rt.cuh) and the runtime-width agent kernels of the object API."""
+    n = 200
+    cfg = O.default_config()
+    cfg["switch_step"], cfg["excitation"] = 25, H.excitation()
+    cfg["agents"]["lon"]["nh"], cfg["agents"]["col"]["nh"] = nh_lon, nh_col
+    S = O.init_state(n, v_initial=np.linspace(6, 24, n), cfg=cfg, seed=12)
+    loop = H.make_loop(_clone_state(S), cfg, ticks_per_launch=20)
+    assert loop.info(True)["block"] == 128
+    loop.run(60)
+    O.run(S, cfg, 60, "all64")
+    H.compare_states(H.loop_state(loop), S, 1e-8, what="runtime-width kernel")
+    st = loop.stats()
+    assert st["n"] == n and st["sum_ticks"] == float(S["step"].sum())
+    # object API on the same widths: one more tick, statement by statement (main_3dof.py:131-161)
+    env, rls, col, lon = loop.env, loop.rls, loop.agent_col, loop.agent_lon
+    ref = torch.full((7, n), float("nan"), dtype=torch.float64, device="cuda")
+    ref[1], ref[4] = loop.ref2[0], loop.ref2[1]
+    obs = env.state.clone()
+    act = torch.stack([env.trimmed_controls[0] + col.get_action(obs, ref), env.trimmed_controls[1] + lon.get_action(obs, ref)])
+    act = act + torch.as_tensor(H.excitation()[60, :2], device="cuda").reshape(2, 1)       # main_3dof.py:139-140
+    loop.run(1)
+    assert torch.allclose(rls.u, act, rtol=1e-10, atol=1e-13)       # the fused tick applied the same actions
