@@ -93,6 +93,9 @@ class DHPAgent:
         self.networks = [self.actor, self.critic, self.target_critic]
         self.nn_stdev_actor, self.nn_stdev_critic = nn_stdev_actor, nn_stdev_critic
         self.hyper_rows_device = None       # optional (6, N) f64 device rows (HYPER_NAMES order): used as they are
+        # whether target critic == critic is KNOWN (True after construction, agents.py:107; None after a load: the fused
+        # kernel's tau = 1 shortcut does not carry the target critic, so ClosedLoop3DOF checks once before relying on it)
+        self.target_synced = True
         if init == "auto":
             init = "reference" if n == 1 else "batched"
         self._init_weights(init, nn_stdev_actor, nn_stdev_critic, generator)
@@ -245,3 +248,4 @@ class DHPAgent:
         self.actor.load_state_dict(checkpoint["actor_state_dict"])
         self.critic.load_state_dict(checkpoint["critic_state_dict"])
         self.target_critic.load_state_dict(checkpoint["target_critic_state_dict"])
+        self.target_synced = None

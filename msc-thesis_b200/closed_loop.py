@@ -124,6 +124,8 @@ class ClosedLoop3DOF:
         env.t = 0
         env.uniform_clock = True
         rls.assume_symmetric = True
+        rls._sym_dirty = False
+        self.agent_col.target_synced = self.agent_lon.target_synced = True
         self.k = 0
         self.order = torch.arange(n, device=self.device)
         self._retired.zero_()
@@ -149,6 +151,30 @@ class ClosedLoop3DOF:
         return build_config(env=self.env, pid=self.pid, rls=self.rls, col=self.agent_col, lon=self.agent_lon,
                             switch_step=self.switch_step, ref_mode=ref_mode, window=self.score_window,
                             store_policy=self.store_policy)
+
+    def _check_shortcuts(self):
+        """The fused kernels take two shortcuts that rest on invariants of the reference's own updates: the upper
+        triangle of the covariance stands for the whole matrix (model.py:59 preserves symmetry), and with tau = 1 the
+        cyclic agent's target critic is the critic (agents.py:196) and is not carried.  Both hold by construction; they
+        are re-verified here (one synchronising comparison) only after something that can break them: a literal
+        RecursiveLeastSquares.update() call, or a checkpoint load."""
+        rls, lon = self.rls, self.agent_lon
+        if rls.assume_symmetric and getattr(rls, "_sym_dirty", False):
+            c = rls.cov
+            rls.assume_symmetric = bool(torch.equal(c, c.transpose(0, 1)))
+            rls._sym_dirty = False
+        tau = lon.tau_target_critic
+        if lon.target_synced is not True and not torch.is_tensor(tau) and float(tau) == 1.0 and lon.hyper_rows_device is None:
+            nh = lon.n_hidden
+            lon.target_synced = bool(torch.equal(lon.net[7 * nh:], lon.net[3 * nh:7 * nh]))
+
+    def _uniform_rows(self, agent):
+        """(6, N) hyper-parameter rows holding the agent's scalar values (forces the per-episode-hyper kernel variant)."""
+        vals = agent._hyper_values()
+        rows = torch.empty(L.HYPER_ROWS, self.n, dtype=torch.float64, device=self.device)
+        for i, k in enumerate(L.HYPER_NAMES):
+            rows[i] = float(vals[k]) if not torch.is_tensor(vals[k]) else vals[k].to(self.device, torch.float64)
+        return rows
 
     def _reference_table(self, n_ticks, min_horizon=16384):
         """Device-resident sinusoid reference for the lockstep clock, built ONCE for a whole horizon (the table is a
@@ -205,8 +231,11 @@ class ClosedLoop3DOF:
         lockstep = self.k is not None and env.uniform_clock
         per_ep_ref = env.ref_params is not None
         table_mode = lockstep and env.task == "sinusoid" and not per_ep_ref
+        self._check_shortcuts()
         cfg = self._config(L.REF_TABLE if table_mode else L.REF_KERNEL)
         col_hyper, lon_hyper = self.agent_col._hyper_rows(), self.agent_lon._hyper_rows()
+        if lon_hyper is None and self.agent_lon.target_synced is False:
+            lon_hyper = self._uniform_rows(self.agent_lon)      # carries the target critic explicitly (no tau = 1 shortcut)
         b = self._batch(col_hyper, lon_hyper)
         traj = None
         self._t_at_record_start = env.t

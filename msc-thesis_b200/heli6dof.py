@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from ._config import as_rows, as_vec, byref, fill_agent, resolve_device, scalar
+from ._config import as_rows, as_vec, byref, fill_agent, is_per_episode, resolve_device, scalar
 from .agents import DHPAgent
 
 NS, NA, NR, NH = L.H6_N_STATE, L.H6_N_ACTION, L.H6_N_REG, L.H6_N_HIDDEN
@@ -395,20 +395,38 @@ class RecursiveLeastSquares6:
         self.x.copy_(d["x"].to(self.x)); self.u.copy_(d["u"].to(self.u)); self._skip.copy_(d["skip"].to(self._skip))
         self.assume_symmetric = bool(torch.equal(self.cov, self.cov.transpose(0, 1)))
 
+    # -- pickling: model.py:94-96 pickles the estimator (train.py:238: rls.pkl), train.py:70-72 unpickles and uses it --
+    def __getstate__(self):
+        from .model import reference_state
+        return reference_state(self)
+
+    def __setstate__(self, state):
+        from .model import restore_state
+        restore_state(self, state)
+
     def save(self, path):
-        """model.py:94-96 pickles the estimator (train.py:238: rls.pkl); here the CPU state dict is pickled."""
         import pickle
         with open(path, 'wb') as f:
-            pickle.dump(self.state_dict(), f)
+            pickle.dump(self, f)
 
     @classmethod
     def load(cls, path, **kwargs):
+        """Reads the estimator pickled by save(), the state-dict format of earlier versions, or a pickled object / dict
+        with the reference's attributes (saved_models/*/rls.pkl when `model` resolves to this package via compat/)."""
         import pickle
+        from .model import restore_state
         with open(path, 'rb') as f:
             d = pickle.load(f)
-        obj = cls(state_size=d["state_size"], action_size=d["action_size"], gamma=d["gamma"], covariance=d["covariance"],
-                  constant=d["constant"], n_envs=d["W"].shape[-1], **kwargs)
-        obj.load_state_dict(d)
+        if isinstance(d, cls):
+            obj = d
+        else:
+            obj = cls.__new__(cls)
+            restore_state(obj, d if isinstance(d, dict) else dict(vars(d)))
+        if kwargs.get("device") is not None:
+            dev = torch.device(kwargs["device"])
+            obj.device = dev
+            for k in ("_W", "_cov", "x", "u", "_skip", "X"):
+                setattr(obj, k, getattr(obj, k).to(dev))
         return obj
 
 
@@ -557,6 +575,12 @@ class ClosedLoop6DOF:
         cfg.win_lo, cfg.win_hi = self.score_window
         cfg.target_synced = self._target_synced()
         for h, agent in ((cfg.col, self.agent_col), (cfg.lon, self.agent_lon)):
+            # gamma, tau, scale and the reward weight are launch-uniform in the 6-DOF kernels (only the learning rates
+            # are per episode, self.lr): a per-episode tensor here would silently run as 0
+            for name, v in agent._hyper_values().items():
+                if name not in ("lr_actor", "lr_critic") and is_per_episode(v):
+                    raise NotImplementedError("6-DOF loop: per-episode %s is not supported (launch-uniform in the kernels); "
+                                              "group the episodes by %s as mp_train does" % (name, name))
             fill_agent(h, agent)
             h.scale = float(scalar(agent.actor.scale))
         return cfg
@@ -849,7 +873,8 @@ def mp_train(settings, num_seeds=100, excitation=None, device=None, rank=0, worl
     (main.py:60-65).  tau and gamma are launch-uniform in the kernels, so the settings are grouped by (tau, gamma) and
     each group runs as one batch of len(group) * num_seeds episodes (sharded over `world` ranks); learning rates and the
     initial weights are per episode.  Returns {setting: {'success': [...], 'average_rms': [...]}} like the JSON files of
-    main.py:85-89 (written to json_dir if given; with world > 1 every rank holds its shard's entries only)."""
+    main.py:85-89 (written to json_dir by rank 0 if given; with world > 1 the ranks' entries are gathered first, so every
+    setting's lists are complete)."""
     import itertools
     import json
     import os
@@ -888,7 +913,25 @@ def mp_train(settings, num_seeds=100, excitation=None, device=None, rank=0, worl
                 results[str(tuple(st))] = {"success": [int(v) for v in ok[m]],
                                            "average_rms": [float(sc) if o else 0.0 for o, sc in zip(ok[m], score[m])]}
         del loop
-    if json_dir is not None:
+    if world > 1:
+        # a setting's seeds can straddle two ranks (contiguous shards): gather every rank's entries and merge them in rank
+        # order, so that each setting's lists are complete and in seed order on every rank (main.py:85-89 writes ONE
+        # complete JSON per setting)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() == world:
+            parts = [None] * world
+            dist.all_gather_object(parts, results)
+            merged = {}
+            for part in parts:
+                for k, v in part.items():
+                    m = merged.setdefault(k, {"success": [], "average_rms": []})
+                    m["success"] += v["success"]
+                    m["average_rms"] += v["average_rms"]
+            results = merged
+        elif json_dir is not None:
+            raise RuntimeError("mp_train(world > 1, json_dir=...) needs an initialised torch.distributed group of that size to "
+                               "assemble complete per-setting files")
+    if json_dir is not None and rank == 0:
         os.makedirs(json_dir, exist_ok=True)
         for k, v in results.items():
             with open(os.path.join(json_dir, k + ".json"), "w") as f:

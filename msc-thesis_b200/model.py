@@ -86,6 +86,7 @@ class RecursiveLeastSquares:
         self._cov.zero_()
         self._cov[:: k + 1] = self.covariance
         self.assume_symmetric = True
+        self._sym_dirty = False
 
     def _batch(self):
         return build_batch(self.n_envs, rls_W=self._W, rls_cov=self._cov, rls_x=self.x, rls_u=self.u,
@@ -103,6 +104,9 @@ class RecursiveLeastSquares:
         cfg = build_config(rls=self, env_dtype=dt)
         b = self._batch()
         L.check(L.lib().h3_rls_update(byref(cfg), byref(b), L.ptr(s), L.ptr(a), L.ptr(s2), L.stream_ptr(dev)))
+        # the literal update computes cov.X and X^T.cov separately (model.py:53-54): (a d) b != (b d) a in floating
+        # point, so bit-symmetry is not guaranteed any more -- the fused loop re-checks before it keeps a triangle
+        self._sym_dirty = True
 
     def predict(self, state, action):
         """model.py:61-69 -> (7, N)"""
@@ -138,17 +142,85 @@ class RecursiveLeastSquares:
         self.u.copy_(d["u"].to(self.u))
         self._skip.copy_(d["skip"].to(self._skip))
 
+    # -- pickling: model.py:94-96 pickles the ESTIMATOR, train.py:70-72 unpickles rls.pkl and uses it as is --------
+    def __getstate__(self):
+        """Plain-data state (CPU): what pickle stores.  With n_envs == 1 the arrays have the reference's shapes
+        (W (9,7), cov (9,9), x (7,1), u (2,1), X (9,1)) under the reference's attribute names."""
+        return reference_state(self)
+
+    def __setstate__(self, state):
+        """Accepts both this package's pickles and the attribute dict of a reference estimator (numpy arrays without an
+        episode axis, e.g. an rls.pkl written by the reference when `model` resolves to this class via compat/)."""
+        restore_state(self, state)
+
     def save(self, path):
-        """model.py:94-96 pickles the object; here the (CPU) state dict is pickled."""
+        """model.py:94-96: the estimator object is pickled."""
         with open(path, 'wb') as f:
-            pickle.dump(self.state_dict(), f)
+            pickle.dump(self, f)
 
     @classmethod
     def load(cls, path, **kwargs):
+        """Reads a pickle written by save() (the estimator), by the previous format of this package (a state dict), or
+        any pickled object / dict that carries the reference's attributes W, cov, x, u, skip_update."""
         with open(path, 'rb') as f:
             d = pickle.load(f)
-        n = d["W"].shape[-1]
-        obj = cls(state_size=d["state_size"], action_size=d["action_size"], gamma=d["gamma"],
-                  covariance=d["covariance"], constant=d["constant"], n_envs=n, dtype=d["W"].dtype, **kwargs)
-        obj.load_state_dict(d)
+        if isinstance(d, cls):
+            obj = d
+        else:
+            obj = cls.__new__(cls)
+            restore_state(obj, d if isinstance(d, dict) else dict(vars(d)))
+        if kwargs.get("device") is not None:
+            obj.to(kwargs["device"])
         return obj
+
+    def to(self, device):
+        self.device = resolve_device(device)
+        for k in ("_W", "_cov", "x", "u", "_skip", "X"):
+            setattr(self, k, getattr(self, k).to(self.device))
+        return self
+
+
+def reference_state(rls):
+    """Attribute dict of an estimator in the reference's vocabulary (numpy arrays; the episode axis is dropped when
+    n_envs == 1)."""
+    def arr(t):
+        a = t.detach().cpu().numpy()
+        return a[..., 0] if rls.n_envs == 1 else a
+    x, u, X = arr(rls.x), arr(rls.u), arr(rls.X)
+    if rls.n_envs == 1:
+        x, u, X = x.reshape(-1, 1), u.reshape(-1, 1), X.reshape(-1, 1)
+    return {"state_size": rls.state_size, "action_size": rls.action_size, "gamma": rls.gamma,
+            "covariance": rls.covariance, "constant": rls.constant, "nb_vars": rls.nb_vars,
+            "nb_coefficients": rls.nb_coefficients, "W": arr(rls.W), "cov": arr(rls.cov), "x": x, "u": u, "X": X,
+            "skip_update": (bool(rls._skip[0].item()) if rls.n_envs == 1 else rls._skip.cpu().numpy().astype(bool)),
+            "n_envs": rls.n_envs, "dtype": str(getattr(rls, "dtype", torch.float64)).replace("torch.", ""),
+            "assume_symmetric": bool(rls.assume_symmetric)}
+
+
+def restore_state(rls, d):
+    """Inverse of reference_state; also reads the state-dict format of earlier versions ('skip', tensors)."""
+    import numpy as np
+    def ten(v):
+        return v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))
+    W = ten(d["W"])
+    n = W.shape[2] if W.dim() == 3 else 1
+    rls.state_size, rls.action_size = int(d["state_size"]), int(d["action_size"])
+    rls.gamma, rls.covariance, rls.constant = d["gamma"], d["covariance"], d.get("constant", False)
+    rls.nb_vars = rls.state_size + rls.action_size
+    rls.nb_coefficients = rls.nb_vars + (1 if rls.constant else 0)
+    rls.n_envs = n
+    rls.device = torch.device("cpu")
+    dt = d.get("dtype")
+    rls.dtype = getattr(torch, dt) if isinstance(dt, str) else (W.dtype if W.dtype in (torch.float32, torch.float64) else torch.float64)
+    k, ns, na = rls.nb_coefficients, rls.state_size, rls.action_size
+    rls._W = W.to(rls.dtype).reshape(k * ns, n).contiguous() if W.dim() == 3 else W.to(rls.dtype).reshape(k * ns, 1).contiguous()
+    cov = ten(d["cov"]).to(rls.dtype)
+    rls._cov = cov.reshape(k * k, n).contiguous()
+    rls.x = ten(d["x"]).to(rls.dtype).reshape(ns, n).contiguous()
+    rls.u = ten(d["u"]).to(rls.dtype).reshape(na, n).contiguous()
+    rls.X = ten(d["X"]).to(rls.dtype).reshape(k, n).contiguous() if "X" in d else torch.ones(k, n, dtype=rls.dtype)
+    skip = d["skip_update"] if "skip_update" in d else d["skip"]
+    rls._skip = ten(skip).reshape(-1).to(torch.int32).expand(n).contiguous()
+    c3 = rls._cov.view(k, k, n)
+    rls.assume_symmetric = bool(torch.equal(c3, c3.transpose(0, 1)))
+    rls._sym_dirty = False

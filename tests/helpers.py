@@ -136,6 +136,7 @@ def make_loop(S, cfg, mode="all64", device="cuda", heterogeneous=False, env_dtyp
                 else:
                     ag.actor.scale = tv
         ag.net.copy_(net_block(S, name, hp["nh"], ndt))
+        ag.target_synced = None         # weights written behind the agent's back: like after a load()
         agents[name] = ag
     exc = cfg.get("excitation")
     ref = torch.as_tensor(S["ref"]).to(device, edt).contiguous()

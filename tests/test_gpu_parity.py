@@ -703,3 +703,32 @@ def test_arbitrary_hidden_widths_vs_oracle(h3, nh_lon, nh_col):
     act = act + torch.as_tensor(H.excitation()[60, :2], device="cuda").reshape(2, 1)       # main_3dof.py:139-140
     loop.run(1)
     assert torch.allclose(rls.u, act, rtol=1e-10, atol=1e-13)       # the fused tick applied the same actions
+
+
+def test_shortcuts_are_verified_after_a_load_or_a_literal_update(h3, tmp_path):
+    """tau = 1 shortcut: a checkpoint whose target critic differs from its critic (agents.py:205-209 loads all three
+    networks) must run with the stored target, like the reference.  Symmetric-covariance shortcut: after a literal
+    RecursiveLeastSquares.update() the covariance is re-checked before the kernel keeps only a triangle."""
+    n = 96
+    cfg = O.default_config()
+    cfg["switch_step"] = 10
+    S = O.init_state(n, v_initial=12.0, cfg=cfg, seed=4)
+    rng = np.random.default_rng(0)
+    S["lon_t_w1"] = S["lon_t_w1"] + 0.05 * rng.standard_normal(S["lon_t_w1"].shape)       # target != critic, tau_lon = 1
+    S["lon_t_w2"] = S["lon_t_w2"] + 0.05 * rng.standard_normal(S["lon_t_w2"].shape)
+    loop = H.make_loop(_clone_state(S), cfg, ticks_per_launch=8)
+    loop.agent_lon.save(str(tmp_path / "lon.pt"))
+    loop.agent_lon.load(str(tmp_path / "lon.pt"))
+    assert loop.agent_lon.target_synced is None
+    loop.run(30)
+    assert loop.agent_lon.target_synced is False
+    O.run(S, cfg, 30, "all64")
+    H.compare_states(H.loop_state(loop), S, 1e-8, what="stored target critic with tau = 1")
+    # literal update -> dirty -> re-checked
+    rls = loop.rls
+    assert rls.assume_symmetric
+    obs = loop.env.state.clone()
+    rls.update(obs, torch.zeros(2, n, dtype=torch.float64, device="cuda"), obs * 1.001)
+    assert rls._sym_dirty
+    loop.run(1)
+    assert not rls._sym_dirty

@@ -285,6 +285,34 @@ def test_checkpoints_round_trip(tmp_path):
     assert not back.assume_symmetric                                # non-symmetric input -> general kernel
     with pytest.raises(NotImplementedError):
         h3.RecursiveLeastSquares(state_size=15, action_size=2, constant=False, device="cpu")
+    # model.py:94-96 / train.py:70-72: the estimator OBJECT is pickled and unpickled, and a reference estimator's
+    # attribute dict (numpy arrays without an episode axis) is understood
+    import pickle
+    single = h3.RecursiveLeastSquares(state_size=7, action_size=2, gamma=1, covariance=10 ** 4, constant=False, device="cpu")
+    single.W = torch.arange(63, dtype=torch.float64).reshape(9, 7)
+    single.save(str(tmp_path / "one.pkl"))
+    with open(str(tmp_path / "one.pkl"), "rb") as f:
+        obj = pickle.load(f)                                        # what train.py:70-72 does
+    assert isinstance(obj, h3.RecursiveLeastSquares) and torch.equal(obj.W, single.W) and obj.skip_update
+    st = single.__getstate__()
+    assert st["W"].shape == (9, 7) and st["cov"].shape == (9, 9) and st["x"].shape == (7, 1) and st["skip_update"] is True
+
+    class RefLike:                                                  # the attributes a reference estimator pickles
+        pass
+    ref = RefLike()
+    ref.state_size, ref.action_size, ref.gamma, ref.covariance, ref.constant = 7, 2, 1, 10 ** 4, False
+    ref.nb_vars = ref.nb_coefficients = 9
+    ref.W, ref.cov = np.arange(63.0).reshape(9, 7), np.eye(9) * 3.0
+    ref.x, ref.u, ref.X, ref.skip_update = np.ones((7, 1)), np.zeros((2, 1)), np.ones((9, 1)), False
+    with open(str(tmp_path / "ref.pkl"), "wb") as f:
+        pickle.dump(vars(ref), f)
+    got = h3.RecursiveLeastSquares.load(str(tmp_path / "ref.pkl"))
+    assert got.n_envs == 1 and torch.equal(got.W[..., 0], torch.as_tensor(ref.W)) and not got.skip_update
+    assert float(got.cov[4, 4, 0]) == 3.0 and got.assume_symmetric and torch.equal(got.x, torch.ones(7, 1, dtype=torch.float64))
+    r6 = h3.heli6dof.RecursiveLeastSquares6(state_size=15, action_size=2, gamma=1, covariance=1e8, constant=False, n_envs=2, device="cpu")
+    r6.save(str(tmp_path / "r6.pkl"))
+    b6 = h3.heli6dof.RecursiveLeastSquares6.load(str(tmp_path / "r6.pkl"))
+    assert torch.equal(b6.W, r6.W) and torch.equal(b6.cov, r6.cov) and b6.n_envs == 2
 
 
 def test_config_parsing_and_loud_failure_without_gpu(tmp_path):
