@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
                 const NT a_col = actor_forward<NT, NHC, UC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, stc, fc,
-                                                            amask, &heat, H3_HEAT_COL);
+                                                            amask, &heat, H3_HEAT_COL, true);
                 colv = misce[2] + (ET)a_col;
                 stc[NHC] = fc;
                 stc[NHC + 1] = sc0;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
                 SubVec<decltype(stc), NT> scr{stc, NHC + 3};
                 agent_update<NT, NHC, UC, false>(col, Hcol, P.col.final_activation, stc[NHC + 1], stc[NHC + 2], n0, n1,
-                                                 (NT)0, dr, F, G, stc, stc[NHC], scr, amask, &heat, H3_HEAT_COL);
+                                                 (NT)0, dr, F, G, stc, stc[NHC], scr, amask, &heat, H3_HEAT_COL, true);
             }
             if (rec) {
                 row[10 * P.ld_traj] = (ET)r_col;

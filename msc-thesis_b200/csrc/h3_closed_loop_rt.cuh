@@ -32,12 +32,17 @@ struct RtNet {              // rows of the `[11*nh][ld]` network block (include/
     H3_DEV NT& t2(int j, int k) { return at(9 * nh + j * nh + k); }
 };
 
+template <typename NT>
+H3_DEV NT tanh_rt(NT x, bool wide) {        // hidden-layer tanh: full-range formula for the collective agent (wide)
+    return wide ? Math<NT>::tanh_wide_(x) : Math<NT>::tanh_(x);
+}
+
 // DHPActor.forward (agents.py:59-63)
 template <typename NT>
-H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& f) {
+H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& f, bool wide) {
     typedef Math<NT> M;
     NT y = (NT)0;
-    for (int k = 0; k < net.nh; ++k) y += net.a2(k) * M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
+    for (int k = 0; k < net.nh; ++k) y += net.a2(k) * tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1, wide);
     f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
     return scale * f;
 }
@@ -47,20 +52,19 @@ H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& 
 // unit's rows are written only after they were read).
 template <typename NT>
 H3_DEV void agent_update_rt(RtNet<NT>& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
-                            const NT (&F)[2][2], const NT (&G)[2]) {
-    typedef Math<NT> M;
+                            const NT (&F)[2][2], const NT (&G)[2], bool wide) {
     NT f;
-    (void)actor_forward_rt(net, s0, s1, H.scale, act, f);
+    (void)actor_forward_rt(net, s0, s1, H.scale, act, f, wide);
     const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);
     NT lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
     for (int k = 0; k < net.nh; ++k) {
-        const NT hc = M::tanh_(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
-        const NT ht = M::tanh_(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
+        const NT hc = tanh_rt(net.c1(k, 0) * s0 + net.c1(k, 1) * s1, wide);
+        const NT ht = tanh_rt(net.t1(k, 0) * n0 + net.t1(k, 1) * n1, wide);
         lam1[0] += net.c2(0, k) * hc;
         lam1[1] += net.c2(1, k) * hc;
         lam2[0] += net.t2(0, k) * ht;
         lam2[1] += net.t2(1, k) * ht;
-        const NT ha = M::tanh_(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
+        const NT ha = tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1, wide);
         const NT pk = delta * net.a2(k) * ((NT)1 - ha * ha);
         da_ds[0] += net.a1(k, 0) * pk;
         da_ds[1] += net.a1(k, 1) * pk;
@@ -76,8 +80,8 @@ H3_DEV void agent_update_rt(RtNet<NT>& net, const AgentH<NT>& H, int act, NT s0,
     for (int k = 0; k < net.nh; ++k) {
         const NT a10 = net.a1(k, 0), a11 = net.a1(k, 1), a2k = net.a2(k);
         const NT c10 = net.c1(k, 0), c11 = net.c1(k, 1), c20 = net.c2(0, k), c21 = net.c2(1, k);
-        const NT ha = M::tanh_(a10 * s0 + a11 * s1);
-        const NT hc = M::tanh_(c10 * s0 + c11 * s1);
+        const NT ha = tanh_rt(a10 * s0 + a11 * s1, wide);
+        const NT hc = tanh_rt(c10 * s0 + c11 * s1, wide);
         const NT pk = delta * a2k * ((NT)1 - ha * ha);
         const NT back = (c20 * e_c[0] + c21 * e_c[1]) * ((NT)1 - hc * hc);
         net.a1(k, 0) = a10 + ka * (pk * s0);
@@ -149,11 +153,11 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
         const NT sl0 = (NT)pick7(s, P.lon.ac_state);
         const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
         NT fdummy;
-        ET cyc = trim1 + (ET)actor_forward_rt(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, fdummy);
+        ET cyc = trim1 + (ET)actor_forward_rt(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, fdummy, false);
         const NT sc0 = (NT)pick7(s, P.col.ac_state);
         const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
         ET colv = (ET)0;
-        if (phase2) colv = trim0 + (ET)actor_forward_rt(col, sc0, sc1, Hcol.scale, P.col.final_activation, fdummy);
+        if (phase2) colv = trim0 + (ET)actor_forward_rt(col, sc0, sc1, Hcol.scale, P.col.final_activation, fdummy, true);
         ET exc0 = (ET)0, exc1 = (ET)0;                                          // main_3dof.py:139-140
         if (P.excitation != nullptr && k < P.exc_len) {
             exc0 = (ET)P.excitation[2 * k];
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
             transition_matrices<ET, NT>(Wm, P.lon, F, G);
             const NT n0 = (NT)pick7(s, P.lon.ac_state);
             const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
-            agent_update_rt(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr, F, G);
+            agent_update_rt(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr, F, G, false);
         }
         if (phase2) {
             const ET e_tr = P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
             transition_matrices<ET, NT>(Wm, P.col, F, G);
             const NT n0 = (NT)pick7(s, P.col.ac_state);
             const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
-            agent_update_rt(col, Hcol, P.col.final_activation, sc0, sc1, n0, n1, (NT)0, dr, F, G);
+            agent_update_rt(col, Hcol, P.col.final_activation, sc0, sc1, n0, n1, (NT)0, dr, F, G, true);
         }
         if (rec) {
             row[10 * P.ld_traj] = (ET)r_col;

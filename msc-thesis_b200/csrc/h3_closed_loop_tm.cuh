@@ -70,7 +70,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act, int& heat
         NT pre[UF], hk[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) pre[u] = b[u][0] * s0 + b[u][1] * s1;
-        if (!M::template tanh_vec<UF>(pre, hk)) heat |= H3_HEAT_COL;
+        if (!M::template tanh_vec<UF>(pre, hk, true)) heat |= H3_HEAT_COL;
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
@@ -117,7 +117,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
         NT pre[UP], ht[UP];
 #pragma unroll
         for (int u = 0; u < UP; ++u) pre[u] = b[u][0] * n0 + b[u][1] * n1;
-        if (!M::template tanh_vec<UP>(pre, ht)) heat |= H3_HEAT_COL;
+        if (!M::template tanh_vec<UP>(pre, ht, true)) heat |= H3_HEAT_COL;
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
@@ -142,7 +142,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
 #pragma unroll
             for (int u = 0; u < UP; ++u) pre[u] = c1[u][0] * s0 + c1[u][1] * s1;
         }
-        if (!M::template tanh_vec<UP>(pre, hc)) heat |= H3_HEAT_COL;
+        if (!M::template tanh_vec<UP>(pre, hc, true)) heat |= H3_HEAT_COL;
         __syncwarp();
         TmemBuf<NT, 6> b[UP];               // c2(0,k) c2(1,k) a1(k,0) a1(k,1) a2(k) h_a(k)
 #pragma unroll

@@ -159,12 +159,20 @@ struct Math;
 template <>
 struct Math<double> {
     static H3_DEV double tanh_(double x) { return tanh_f64(x); }
+    static H3_DEV double tanh_wide_(double x) { return tanh_any(x); }
     // U independent arguments at once; the polynomial loops run coefficient-major so that consecutive DFMAs
     // belong to different elements (a single warp per scheduler then covers the DFMA latency by itself).
     // Returns whether the short (polynomial) branch was taken: the kernels keep that per episode as a sort key, so
     // that episodes taking the same branches can be grouped into the same warps (ClosedLoop3DOF.compact).
+    // wide: every element takes the full-range formula (no test, no divergence): for the collective agent, whose
+    // inputs are a speed in m/s and an altitude error in m -- its pre-activations leave the polynomial's range as soon
+    // as the episode is under way, and a warp in which only SOME lanes have left it pays for both branches.
     template <int U>
-    static H3_DEV bool tanh_vec(const double (&x)[U], double (&y)[U]) {
+    static H3_DEV bool tanh_vec(const double (&x)[U], double (&y)[U], bool wide = false) {
+        if (wide) {
+            tanh_any_group<0, U>(x, y);
+            return false;
+        }
         bool all_small = true;
 #pragma unroll
         for (int u = 0; u < U; ++u) all_small = all_small && (::fabs(x[u]) < 0.55);
@@ -223,8 +231,9 @@ struct Math<double> {
 template <>
 struct Math<float> {
     static H3_DEV float tanh_(float x) { return ::tanhf(x); }
+    static H3_DEV float tanh_wide_(float x) { return ::tanhf(x); }
     template <int U>
-    static H3_DEV bool tanh_vec(const float (&x)[U], float (&y)[U]) {
+    static H3_DEV bool tanh_vec(const float (&x)[U], float (&y)[U], bool = false) {
 #pragma unroll
         for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
         return true;

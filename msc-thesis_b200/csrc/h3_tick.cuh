@@ -265,6 +265,9 @@ struct CovSym {             // upper triangle only (45 elements): cov == cov^T i
     }
     template <int DEPTH>
     H3_DEV void downdate(const T (&g)[9], const T (&Xcov)[9], T inv_gamma) {
+        // forgetting factor 1 (main_3dof.py:49): x * 1 == x bit for bit, so the multiplication is left out (launch-
+        // uniform branch; 45 of the tick's FP64 instructions)
+        const bool unit = inv_gamma == (T)1;
         stream_groups<T, 5, 9, DEPTH, Vec::kFence>(
             [&](int gr, T (&c)[9]) {
 #pragma unroll
@@ -274,7 +277,8 @@ struct CovSym {             // upper triangle only (45 elements): cov == cov^T i
 #pragma unroll
                 for (int e = 0; e < 9; ++e) {
                     const int i = gi(gr, e), j = gj(gr, e);
-                    v[idx(i, j)] = (c[e] - g[i] * Xcov[j]) * inv_gamma;
+                    const T d = c[e] - g[i] * Xcov[j];
+                    v[idx(i, j)] = unit ? d : d * inv_gamma;
                 }
             });
     }
@@ -296,8 +300,10 @@ struct AgentH {             // hyper-parameters in network precision
 
 // DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
 template <typename NT, int NH, int U, typename Net, typename HVec>
+//   wide: the hidden layer uses the full-range tanh without testing the arguments (collective agent, see
+//   Math<double>::tanh_vec); the choice is a property of the agent, the same in every kernel.
 H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f, unsigned mask = 0xffffffffu,
-                        int* heat = nullptr, int heat_bit = 0) {
+                        int* heat = nullptr, int heat_bit = 0, bool wide = false) {
     typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     NT y = (NT)0;
@@ -309,7 +315,7 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
             const int k = (U == NH) ? u : k0 + u;
             pre[u] = net.a1(k, 0) * s0 + net.a1(k, 1) * s1;
         }
-        const bool cool = M::template tanh_vec<U>(pre, hk);
+        const bool cool = M::template tanh_vec<U>(pre, hk, wide);
         if (heat != nullptr && !cool) *heat |= heat_bit;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -334,7 +340,7 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
 template <typename NT, int NH, int U, bool TAU1, typename Net, typename HVec, typename SVec>
 H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
                          const NT (&F)[2][2], const NT (&G)[2], HVec& h_a, NT f, SVec& scr,
-                         unsigned mask = 0xffffffffu, int* heat = nullptr, int heat_bit = 0) {
+                         unsigned mask = 0xffffffffu, int* heat = nullptr, int heat_bit = 0, bool wide = false) {
     typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     // action.backward() (:174): delta = da/dy, p_k = da/d(pre-activation of hidden k)
@@ -355,13 +361,13 @@ H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, N
             NT pa[U], aa[U], pb[U], ab[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { pa[u] = pre[u]; pb[u] = pre[U + u]; }
-            M::template tanh_vec<U>(pa, aa);
-            M::template tanh_vec<U>(pb, ab);
+            M::template tanh_vec<U>(pa, aa, wide);
+            M::template tanh_vec<U>(pb, ab, wide);
 #pragma unroll
             for (int u = 0; u < U; ++u) { act[u] = aa[u]; act[U + u] = ab[u]; }
         }
 #else
-        const bool cool = M::template tanh_vec<2 * U>(pre, act);
+        const bool cool = M::template tanh_vec<2 * U>(pre, act, wide);
         if (heat != nullptr && !cool) *heat |= heat_bit;
 #endif
 #pragma unroll
