@@ -323,7 +323,7 @@ class LaunchLog:
         self.first_tick = [0] * n_launches
 
 
-SORT_KEY = staticmethod(lambda lp: lp.heat).__func__      # per-episode sort key for compact(): the branch pattern; None: no sorting
+SORT_KEY = staticmethod(lambda lp: lp.sort_key()).__func__     # per-episode sort key for compact(); None: no sorting
 
 
 def run_step(runner, seed, episode0, n_ticks, launch_ticks, compact_every, log=None):

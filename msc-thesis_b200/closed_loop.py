@@ -385,6 +385,17 @@ class ClosedLoop3DOF:
         self.n_active = n_alive
         return n_alive
 
+    def sort_key(self):
+        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branches of the
+        next launch.  While the PID flies the collective (ticks < switch_step) the slow branches belong to episodes
+        whose pitch loop is becoming agitated -- |theta - theta_ref| and |q| predict that well ahead of time, better
+        than the branches of the last tick; afterwards the branch pattern of the last tick (H3Batch.heat) is used.
+        (Measured over whole episodes, 262,144 episodes: PID launches 174 -> 158 ms, later launches 236 -> 231 ms.)"""
+        if self.k is not None and self.k < self.switch_step:
+            st = self.env.state
+            return (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
+        return self.heat
+
     def original_order(self, t):
         """Per-episode tensor `t` (episode axis last) re-ordered to the original episode indices."""
         out = torch.empty_like(t)

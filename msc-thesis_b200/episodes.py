@@ -95,8 +95,8 @@ class EpisodeRunner:
         """One job: parameters up (H2D), init, n_ticks ticks, results down (D2H) -- all enqueued on the current
         stream; synchronise before reading results_host.  compact_every = K > 0 moves the live episodes to the front
         every K ticks (ClosedLoop3DOF.compact(); it synchronises), so terminated episodes stop occupying lanes; with
-        `sort` they are also ordered by the branch pattern of their last tick (H3Batch.heat), which takes the
-        divergence between calm and agitated episodes out of the warps.  Results do not depend on either."""
+        `sort` they are also ordered by ClosedLoop3DOF.sort_key(), which takes the divergence between calm and
+        agitated episodes out of the warps.  Results do not depend on either."""
         lp = self.loop
         self.params.copy_(params_host, non_blocking=True)
         lp.init_episodes(seed, episode0=episode0, v_trim=self.params[ROW["v_trim"]],
@@ -108,7 +108,7 @@ class EpisodeRunner:
                 lp.run(m)
                 done += m
                 if done < n_ticks:
-                    lp.compact(sort_key=lp.heat if sort else None)
+                    lp.compact(sort_key=lp.sort_key() if sort else None)
         else:
             lp.run(n_ticks)
         out_f, out_i, out_s = results_host

@@ -106,7 +106,7 @@ def run_sweep(grid=None, n_seeds=40, n_ticks=12000, rank=0, world_size=1, out_js
         loop.run(m)
         done += m
         if compact_every and done < n_ticks:
-            loop.compact()
+            loop.compact(sort_key=loop.sort_key())
     loop.allreduce_stats()
     res = sweep_results(loop, setting_of, len(settings), score_window[1] - score_window[0])
     if out_json and rank == 0:

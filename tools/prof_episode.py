@@ -26,6 +26,10 @@ if a.sort == "none":
     bench.SORT_KEY = None
 elif a.sort == "z":
     bench.SORT_KEY = lambda lp: lp.env.state[1].abs()
+elif a.sort == "th":
+    bench.SORT_KEY = lambda lp: (lp.env.state[4] - lp.ref2[1]).abs() + 0.1 * lp.env.state[5].abs()
+elif a.sort == "heat_th":
+    bench.SORT_KEY = lambda lp: lp.heat.double() + (lambda x: x / (1 + x))((lp.env.state[4] - lp.ref2[1]).abs() + 0.1 * lp.env.state[5].abs())
 elif a.sort == "zt":
     bench.SORT_KEY = lambda lp: lp.env.state[1].abs() + 20 * (lp.env.state[4] - lp.ref2[1]).abs()
 n = a.episodes
