@@ -59,26 +59,30 @@ def sweep_params(keys, settings, n_seeds, lo, hi, device, agents=("lon",)):
     return p, setting_of
 
 
-def sweep_results(loop, setting_of_shard, n_settings, window_len, group=None):
-    """Per-setting (n, successes, mean score) like main.py:71-79: success = the episode reached the end alive,
-    score = sqrt(-sum r_lon[window] / len(window)) (train.py:256).  Sums are all-reduced over the ranks.  Episodes that
-    did not survive are excluded BEFORE summing: a diverged episode's accumulator is NaN or -inf, and NaN * 0 is NaN."""
+def setting_sums(alive, score, setting_of_shard, n_settings, group=None):
+    """(3, n_settings) sums {episodes, successes, score of the successes} of this rank's shard, all-reduced over the
+    ranks (NCCL for CUDA tensors, gloo for CPU tensors).  Episodes that did not survive are excluded BEFORE summing: a
+    diverged episode's accumulator is NaN or -inf, and NaN * 0 is NaN."""
     import torch.distributed as dist
-    dev = loop.device
-    flags, acc = loop.env.flags, loop.acc
-    if loop.n_active < loop.n:
-        flags, acc = loop.original_order(flags), loop.original_order(acc)
-    alive = flags == 0
-    score = torch.sqrt(torch.clamp(-acc[2], min=0.0) / max(window_len, 1))
     score = torch.where(alive, score, torch.zeros_like(score))
-    idx = torch.as_tensor(setting_of_shard, device=dev, dtype=torch.int64)
-    sums = torch.zeros(3, n_settings, dtype=torch.float64, device=dev)
+    idx = torch.as_tensor(setting_of_shard, device=score.device, dtype=torch.int64)
+    sums = torch.zeros(3, n_settings, dtype=torch.float64, device=score.device)
     sums[0].index_add_(0, idx, torch.ones_like(score))
     sums[1].index_add_(0, idx, alive.double())
     sums[2].index_add_(0, idx, score)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    n, ok, sc = sums.cpu().numpy()
+    return sums
+
+
+def sweep_results(loop, setting_of_shard, n_settings, window_len, group=None):
+    """Per-setting (n, successes, mean score) like main.py:71-79: success = the episode reached the end alive,
+    score = sqrt(-sum r_lon[window] / len(window)) (train.py:256)."""
+    flags, acc = loop.env.flags, loop.acc
+    if loop.n_active < loop.n:
+        flags, acc = loop.original_order(flags), loop.original_order(acc)
+    score = torch.sqrt(torch.clamp(-acc[2], min=0.0) / max(window_len, 1))
+    n, ok, sc = setting_sums(flags == 0, score, setting_of_shard, n_settings, group).cpu().numpy()
     return {"n": n, "success": ok, "mean_score_of_successes": np.where(ok > 0, sc / np.maximum(ok, 1), np.nan)}
 
 

@@ -1,5 +1,6 @@
 """CPU, world_size 2, gloo: the N>1 path of the closed loop is "shard the episodes, all-reduce the per-batch
-statistics" (DESIGN.md section 6).  Each rank builds the statistics vector of ITS shard (with the oracle standing
+statistics" (DESIGN.md section 6); a sweep additionally all-reduces per-setting sums over shards whose parameter blocks
+are slices of the whole job's block.  Each rank builds the statistics vector of ITS shard (with the oracle standing
 in for the kernel epilogue, same field order), all-reduces it through the package's helper, and the result
 must equal the single-process statistics of the whole batch -- independent of the partition."""
 import os
@@ -62,3 +63,45 @@ def test_sharded_statistics_allreduce_matches_single_process(tmp_path):
     assert torch.allclose(got[4:7], want[4:7], rtol=1e-12, atol=0)
     d = h3.distributed.summarize(got)
     assert d["n"] == N_TOTAL and 0.0 <= d["success_rate"] <= 1.0
+
+
+def _sweep_outcome(g):
+    """Per-episode outcome as a function of the GLOBAL episode index (stands in for the kernels' results)."""
+    alive = (g % 3) != 0
+    score = torch.sqrt(1.0 + g.double())
+    score = torch.where((g % 7) == 0, torch.full_like(score, float("nan")), score)     # a diverged accumulator
+    return alive & ((g % 7) != 0), score
+
+
+def _sweep_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import msc_thesis_b200 as h3
+    S = h3.sweep
+    keys, settings, n_total = S.expand_grid({"tau_target_critic": [0.01, 1.0], "nn_stdev": [0.1, 0.2, 0.4]}, 7)
+    lo, hi = h3.shard_range(n_total, rank, world)
+    params, setting_of = S.sweep_params(keys, settings, 7, lo, hi, "cpu")
+    alive, score = _sweep_outcome(torch.arange(lo, hi))
+    sums = S.setting_sums(alive, score, setting_of, len(settings))
+    if rank == 0:
+        torch.save({"sums": sums, "params": params, "lo": lo, "hi": hi}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_sums_allreduce_matches_single_process(tmp_path):
+    import msc_thesis_b200 as h3
+    S = h3.sweep
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "sweep.pt")
+    mp.spawn(_sweep_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    keys, settings, n_total = S.expand_grid({"tau_target_critic": [0.01, 1.0], "nn_stdev": [0.1, 0.2, 0.4]}, 7)
+    whole, setting_of = S.sweep_params(keys, settings, 7, 0, n_total, "cpu")
+    alive, score = _sweep_outcome(torch.arange(n_total))
+    want = S.setting_sums(alive, score, setting_of, len(settings))
+    assert torch.equal(got["sums"][:2], want[:2]) and torch.allclose(got["sums"][2], want[2], rtol=1e-13, atol=0)
+    assert torch.isfinite(got["sums"]).all() and float(got["sums"][0].sum()) == n_total
+    assert torch.equal(got["params"], whole[:, got["lo"]:got["hi"]])
