@@ -446,10 +446,10 @@ def main():
     if a.impl == "reference":
         run_reference_arm(a)
         return
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ:
-        # NCCL's INFO lines (communicator, rank count, NVLS) are what shows that the collective ran on N ranks: leave
-        # NCCL_DEBUG to the caller; if it is unset, ask for the init lines -- before torch (and with it NCCL) is loaded --
-        # and send them to stderr (stdout carries the JSON line, printed last)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        # NCCL's INFO lines (communicator, rank count, NVLS) are what shows that the collective ran on N ranks.  The image
+        # ships NCCL_DEBUG=VERSION; unless the caller already asked for INFO, ask for the init lines here -- before torch
+        # (and with it NCCL) is loaded -- and send them to stderr: stdout carries the ONE JSON line.
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
