@@ -386,15 +386,16 @@ class ClosedLoop3DOF:
         return n_alive
 
     def sort_key(self):
-        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branches of the
-        next launch.  While the PID flies the collective (ticks < switch_step) the slow branches belong to episodes
-        whose pitch loop is becoming agitated -- |theta - theta_ref| and |q| predict that well ahead of time, better
-        than the branches of the last tick; afterwards the branch pattern of the last tick (H3Batch.heat) is used.
-        (Measured over whole episodes, 262,144 episodes: PID launches 174 -> 158 ms, later launches 236 -> 231 ms.)"""
-        if self.k is not None and self.k < self.switch_step:
-            st = self.env.state
-            return (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
-        return self.heat
+        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branches in the
+        next launch: the number of ticks of the last launch in which the episode left the short tanh branch (cyclic
+        agent) or the short sin / cos branch (H3Batch.heat) -- the reference signal is periodic, so an episode's duty
+        cycle on the slow branches is what persists from launch to launch --, with the current pitch-loop agitation
+        |theta - theta_ref| + 0.1 |q| as the tie-break (and as the whole key before the first launch has counted)."""
+        st = self.env.state
+        agitation = (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
+        h = self.heat
+        counts = ((h & 1023) + 2 * ((h >> 20) & 1023)).double()
+        return counts + agitation / (1.0 + agitation)
 
     def original_order(self, t):
         """Per-episode tensor `t` (episode axis last) re-ordered to the original episode indices."""

@@ -22,8 +22,10 @@ namespace h3 {
 // PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
-// bits of H3Batch.heat: which data-dependent slow branches an episode took in its last executed tick
+// H3Batch.heat: per slow data-dependent branch, in how many ticks of the launch the episode took it (three 10-bit
+// counters: bits 0-9 cyclic agent's tanh beyond the polynomial range, 10-19 collective agent's, 20-29 sin / cos beyond pi/4)
 enum { H3_HEAT_LON = 1, H3_HEAT_COL = 2, H3_HEAT_TRIG = 4 };
+H3_DEV int heat_counts(int bits) { return (bits & 1) + ((bits & 2) << 9) + ((bits & 4) << 18); }
 
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     }
 
     const bool lockstep = P.step0 >= 0;
-    int heat = 0;
+    int heat = 0, heat_acc = 0;
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
     const bool table_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_TABLE);
 
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             // -------- next step / termination (main_3dof.py:189-197) --------
             refth = nrefth;
             step = k + 1;
+            heat_acc += heat_counts(heat);
             const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
             if (nf) {
                 flags = nf;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         P.step[e] = step;
         P.flags[e] = flags;
         P.term_step[e] = term_step;
-        if (P.heat != nullptr) P.heat[e] = heat;
+        if (P.heat != nullptr) P.heat[e] = heat_acc;
         acc0 = miscd[0];
         acc1 = miscd[1];
         acc2 = miscd[2];

@@ -56,7 +56,7 @@ struct ColTm {
 // DHPActor.forward of the collective agent (agents.py:59-63): weights from TMEM, h_a and (f, s0, s1) back to it.
 //   UF: hidden units per group (their tanh chains are interleaved)
 template <typename NT, int NH, int UF>
-H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act, int& heat) {
+H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
     typedef Math<NT> M;
     typedef ColTm<NH> L;
     static_assert(NH % UF == 0, "group width must divide the hidden width");
@@ -70,7 +70,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act, int& heat
         NT pre[UF], hk[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) pre[u] = b[u][0] * s0 + b[u][1] * s1;
-        if (!M::template tanh_vec<UF>(pre, hk, true)) heat |= H3_HEAT_COL;
+        (void)M::template tanh_vec<UF>(pre, hk, true);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
@@ -97,7 +97,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act, int& heat
 //   UP: hidden units per group of passes T and A (their tanh chains are interleaved); V2: units per group of pass C.
 template <typename NT, int NH, int UP, int V2>
 H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n1, NT dr0, NT dr, const NT (&F)[2][2],
-                          const NT (&G)[2], int& heat) {
+                          const NT (&G)[2]) {
     typedef Math<NT> M;
     typedef ColTm<NH> L;
     static_assert(NH % UP == 0 && NH % V2 == 0, "chunk widths must divide the hidden width");
@@ -117,7 +117,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
         NT pre[UP], ht[UP];
 #pragma unroll
         for (int u = 0; u < UP; ++u) pre[u] = b[u][0] * n0 + b[u][1] * n1;
-        if (!M::template tanh_vec<UP>(pre, ht, true)) heat |= H3_HEAT_COL;
+        (void)M::template tanh_vec<UP>(pre, ht, true);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
@@ -142,7 +142,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
 #pragma unroll
             for (int u = 0; u < UP; ++u) pre[u] = c1[u][0] * s0 + c1[u][1] * s1;
         }
-        if (!M::template tanh_vec<UP>(pre, hc, true)) heat |= H3_HEAT_COL;
+        (void)M::template tanh_vec<UP>(pre, hc, true);
         __syncwarp();
         TmemBuf<NT, 6> b[UP];               // c2(0,k) c2(1,k) a1(k,0) a1(k,1) a2(k) h_a(k)
 #pragma unroll
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
 
     // ---- resumable tick loop: leaves whenever a lane terminated, so that its state is stored at once ----
     int j = 0;
-    int heat = 0;                           // which data-dependent slow branches the episode took in its last tick
+    int heat = 0, heat_acc = 0;             // slow data-dependent branches taken: this tick / counted over the launch
     bool just_died = false, finished = false;
     do {
         bool flush = false;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
                 __syncwarp();
-                const NT a_col = col_forward_tm<NT, NHC, UF>(tm, sc0, sc1, Hcol.scale, P.col.final_activation, heat);
+                const NT a_col = col_forward_tm<NT, NHC, UF>(tm, sc0, sc1, Hcol.scale, P.col.final_activation);
                 colv = trim0 + (ET)a_col;
             }
             cyc += (ET)sh_exc[2 * jj + 1];                                          // main_3dof.py:139-140
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT n0 = (NT)pick7(s, P.col.ac_state);
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
                 __syncwarp();
-                col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G, heat);
+                col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G);
             }
             // -------- bookkeeping and termination (main_3dof.py:189-197): frozen for terminated episodes --------
             if (!dead) {
@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 if (k >= P.win_lo && k < P.win_hi) accv[2] += r_lon;
                 refth = nrefth;
                 step = k + 1;
+                heat_acc += heat_counts(heat);
                 const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
                 if (nf) {
                     flags = nf;
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             P.step[e] = step;
             P.flags[e] = flags;
             P.term_step[e] = term_step;
-            if (P.heat != nullptr) P.heat[e] = heat;
+            if (P.heat != nullptr) P.heat[e] = heat_acc;
             P.t[e] = t_ep;
             P.acc[e] = accv[0];
             P.acc[ld + e] = accv[1];
