@@ -94,7 +94,7 @@ typedef struct H3Config {
     double pid_kp, pid_ki, pid_kd, pid_href;     /* PID.py:6-14, main_3dof.py:68 */
     double rls_gamma;                            /* model.py:14 */
     int32_t rls_symmetric;   /* 1: covariance known symmetric, kernel keeps the upper triangle on chip */
-    int32_t store_policy;    /* reserved (0) */
+    int32_t store_policy;    /* 0: default placement; 3: keep the collective agent in shared memory (no tensor memory) */
     int32_t switch_step;     /* tick at which the collective agent takes over (main_3dof.py:127-137) */
     int32_t update_lon;      /* main_3dof.py:87 (always 1 there) */
     int32_t win_lo, win_hi;  /* score window [lo, hi) on the lon reward, train.py:256 */

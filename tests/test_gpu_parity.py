@@ -79,15 +79,28 @@ def _groups(g):
     return keys
 
 
-@pytest.mark.parametrize("mode,variant", [("all64", "fast"), ("all64", "general"), ("all64", "local"),
-                                          ("ref32", "fast")])
+@pytest.mark.parametrize("mode,variant", [("all64", "fast"), ("all64", "general"), ("all64", "lockstep"),
+                                          ("all64", "lockstep_smem"), ("ref32", "fast"), ("ref32", "lockstep")])
 def test_teacher_forced_ticks(h3, mode, variant):
+    """fast / general: heterogeneous launches (every episode from its own tick counter: the shared-memory kernels).
+    lockstep: one launch per (configuration, tick index) with a shared clock -- ticks at or after the switch then run on
+    the TENSOR-MEMORY kernel, i.e. its forward / three-pass update are pinned on the reference's own post-tick
+    snapshots; lockstep_smem: the same launches with the collective agent kept in shared memory (store_policy 3)."""
     g = H.load("ticks_%s.npz" % mode)
     tol = TOL64 if mode == "all64" else 1e-5
     exc = H.excitation()
     total = 0
     flagged = 0
-    for key, idx in _groups(g).items():
+    lock = variant.startswith("lockstep")
+    groups = _groups(g)
+    if lock:                    # split every group by tick index: a lockstep launch has one clock
+        split = {}
+        for key, idx in groups.items():
+            for i in idx:
+                split.setdefault(key + (int(g["pre_step"][i]),), []).append(i)
+        groups = split
+    tm_launches = 0
+    for key, idx in groups.items():
         i0 = idx[0]
         cfg = H.cfg_for(g["task"][i0], g["switch_step"][i0], exc if g["exc_on"][i0] else None, g["hyper"][i0],
                         g["env_gains"][i0])
@@ -95,8 +108,11 @@ def test_teacher_forced_ticks(h3, mode, variant):
         post = H.snaps_from(g, "post_", idx)
         S = O.state_from_snapshots(pre, mode)
         S["theta_trim"] = g["theta_trim"][idx].copy()
-        loop = H.make_loop(S, cfg, mode, heterogeneous=True, assume_symmetric=(variant != "general"),
-                           store_policy=1 if variant == "local" else 0)
+        loop = H.make_loop(S, cfg, mode, heterogeneous=not lock, assume_symmetric=(variant != "general"),
+                           store_policy=3 if variant == "lockstep_smem" else 0)
+        if lock and variant == "lockstep" and int(S["step"][0]) >= cfg["switch_step"]:
+            tm_launches += 1
+            assert loop.info(True)["block"] == 128
         traj = loop.run(1, record=len(idx))
         got = H.loop_state(loop)
         want = O.state_from_snapshots(post, mode)
@@ -112,6 +128,7 @@ def test_teacher_forced_ticks(h3, mode, variant):
         total += len(idx)
         flagged += int((want["flags"] != 0).sum())
     assert total == g["pre_step"].shape[0] and flagged >= 2
+    assert variant != "lockstep" or tm_launches >= 20
 
 
 # ------------------------------------------------------------------------------------------------------
