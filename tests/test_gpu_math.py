@@ -51,3 +51,25 @@ def test_sincos_accuracy():
     assert float(np.nanmax(_ulps(c, np.cos(x)))) <= 3.0
     s, c = _probe(1, np.array([np.nan, np.inf]))
     assert np.isnan(s).all() and np.isnan(c).all()
+
+
+@pytest.mark.parametrize("warps,blocks", [(4, 1), (8, 1), (4, 2 * 148), (8, 148), (4, 8 * 148)])
+def test_tensor_memory_as_thread_private_storage(warps, blocks):
+    """h3_tmem_probe: every thread of 4- and 8-warp CTAs (one CTA, one wave, several waves per SM) fills its 128 private
+    fp64 words of tensor memory (tcgen05.st 32x32b), reads them back in the piece sizes the fused kernel uses
+    (tcgen05.ld x16 + x8 at runtime offsets, x16 tail), runs read-modify-write passes and gets exact values back."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import msc_thesis_b200 as h3
+    L = h3._lib
+    reps = 8
+    nt = blocks * warps * 32
+    out = torch.zeros(137, nt, dtype=torch.float64, device="cuda")
+    cyc = torch.zeros(2 * blocks, dtype=torch.int64, device="cuda")
+    L.check(h3.lib().h3_tmem_probe(warps, blocks, reps, L.ptr(out), L.ptr(cyc), L.stream_ptr(out.device)))
+    torch.cuda.synchronize()
+    gt = torch.arange(nt, dtype=torch.float64, device="cuda")
+    want = gt[None, :] * 1024 + torch.arange(128, dtype=torch.float64, device="cuda")[:, None]
+    assert torch.equal(out[:128], want)
+    assert torch.equal(out[128:136], want[:8] + reps)
+    assert int(cyc.min()) > 0
