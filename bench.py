@@ -581,13 +581,18 @@ def main():
             n_seeds = -(-n_total // len(settings))
             swr = h3.EpisodeRunner(n, device=device, precision=a.precision, per_episode_hyper=True, switch_step=a.switch,
                                    score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
-            kw = dict(grid=S.DEFAULT_GRID, n_seeds=n_seeds, n_total=n_total, n_ticks=a.ticks, rank=rank, world_size=world,
-                      compact_every=a.compact_every, runner=swr)
-            S.run_sweep(seed=1, **kw)
+            lo, hi = h3.shard_range(n_total, rank, world)
+            p4, setting_of = S.sweep_params(keys, settings, n_seeds, lo, hi, device)
+            swr.params.copy_(p4)
+            lp = swr.loop
+            nl4 = (a.ticks + a.launch_ticks - 1) // a.launch_ticks
+            run_step(swr, 1, lo, a.ticks, a.launch_ticks, a.compact_every)          # warm-up pass
             torch.cuda.synchronize(device)
+            log4 = LaunchLog(torch, nl4, device)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _, _, res, lp = S.run_sweep(seed=2, **kw)
+            run_step(swr, 2, lo, a.ticks, a.launch_ticks, a.compact_every, log4)    # init + ticks + statistics all-reduce
+            res = S.sweep_results(lp, setting_of, len(settings), 1000)              # per-setting sums, all-reduced
             e1.record()
             torch.cuda.synchronize(device)
             ms4 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -597,13 +602,15 @@ def main():
             assert st4["n"] == n_total and res["n"].sum() == n_total
             best = int(np.nanargmax(res["success"] / np.maximum(res["n"], 1)))
             rate4 = st4["sum_ticks"] / (float(ms4.item()) * 1e-3)
+            ph4 = phase_summary([log4], a.switch, {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2})
             extras["config4_sweep"] = {
                 "episodes": n_total, "episodes_per_gpu": n, "settings": len(settings), "seeds_per_setting": n_seeds,
                 "ticks": a.ticks, "env_steps_per_s": rate4, "ms": float(ms4.item()), "allreduced_n": int(st4["n"]),
-                "kernel_phase2": lp.info(phase2=True), "success_rate_overall": st4["n_alive"] / st4["n"],
+                "kernel_phase1": lp.info(phase2=False), "kernel_phase2": lp.info(phase2=True),
+                "success_rate_overall": st4["n_alive"] / st4["n"],
                 "best_setting": dict(zip(keys, settings[best].tolist())),
                 "best_setting_success_rate": float(res["success"][best] / max(res["n"][best], 1)),
-                "roofline_frac_whole_run": None,
+                "phases_rank0": ph4,
                 "what": "per-episode hyper-parameter rows (SWEEP kernel variants), device-side init from (seed, global "
                         "episode index), per-setting success / score sums all-reduced (NCCL)"}
             del swr, lp
@@ -632,7 +639,8 @@ def main():
                 torch.cuda.synchronize(device)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                run_step(r5, 6, rank * n5, ticks5, a.launch_ticks, a.compact_every)
+                log5 = LaunchLog(torch, (ticks5 + a.launch_ticks - 1) // a.launch_ticks, device)
+                run_step(r5, 6, rank * n5, ticks5, a.launch_ticks, a.compact_every, log5)
                 e1.record()
                 torch.cuda.synchronize(device)
                 ms5 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -641,7 +649,8 @@ def main():
                 st5 = dict(zip(h3._lib.STATS_FIELDS, r5.loop.stats_dev.cpu().tolist()))
                 assert st5["n"] == world * n5
                 c5[prec] = {"env_steps_per_s": st5["sum_ticks"] / (float(ms5.item()) * 1e-3), "ms": float(ms5.item()),
-                            "alive_fraction_end": st5["n_alive"] / st5["n"], "allreduced_n": int(st5["n"])}
+                            "alive_fraction_end": st5["n_alive"] / st5["n"], "allreduced_n": int(st5["n"]),
+                            "phases_rank0": phase_summary([log5], a.switch, {"phase1": FLOP_PHASE1, "phase2": FLOP_PHASE2})}
                 del r5, p5
                 torch.cuda.empty_cache()
             c5["f32"]["tolerance"] = F32_TOLERANCE
@@ -649,6 +658,17 @@ def main():
         except Exception as exc:
             extras["config5_long_horizon"] = {"error": repr(exc)}
         if rank == 0:
+            for key, prec_keys in (("config4_sweep", (None,)), ("config5_long_horizon", ("f64", "f32"))):
+                for pk in prec_keys:
+                    node = extras.get(key, {}) if pk is None else extras.get(key, {}).get(pk, {})
+                    ph = node.get("phases_rank0")
+                    if not ph:
+                        continue
+                    pk_peak = peak if pk != "f32" else fma_peak(h3, torch, h3._lib.H3_F32, device)
+                    flop = sum((ph[q]["tflops"] or 0.0) * ph[q]["ms"] for q in ph)          # TFLOP/s x ms
+                    node["roofline"] = {"bound": "fp64" if pk != "f32" else "fp32", "unit": "TFLOP/s", "peak": pk_peak / 1e12,
+                                        "frac_by_kernel": {q: (ph[q]["tflops"] or 0.0) * 1e12 / pk_peak for q in ph},
+                                        "frac_whole_run": flop * 1e12 / max(sum(ph[q]["ms"] for q in ph), 1e-9) / pk_peak}
             out["extras"] = extras
 
     # ---- extras, rank 0 at N == 1 only ----
