@@ -193,7 +193,7 @@ class ClosedLoop3DOF:
                 k0, t0 = tab["k0"], float(tab["t"][0])          # same clock: extend the horizon
             else:
                 k0, t0 = k, float(env.t)
-            n = max(need - k0, min_horizon)
+            n = max(need - k0, min_horizon, 2 * len(tab["host"]) if tab is not None and k0 == tab["k0"] else 0)   # grow geometrically
             host, _ = sinusoid_ref_table(t0, env.dt, n, env.ref_amplitude, env.ref_period)
             t = np.empty(n + 1)
             acc = t0
