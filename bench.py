@@ -704,6 +704,39 @@ def main():
                 torch.cuda.empty_cache()
             other["f32"]["tolerance"] = F32_TOLERANCE
             out["extras"]["other_precisions"] = other
+        # out-of-core batches: the episode STATE lives in pinned host memory and streams through two device slots on two
+        # streams (HostBatchPipeline; round 1's e2e definition): 2.9 GB up per 200 ticks of 1,048,576 episodes
+        try:
+            T = 200
+            def make(nc):
+                lp = make_workload(h3, torch, nc, a.precision, device, seed=1, store=0, ticks=T)
+                lp.switch_step = 3 * T + T // 2
+                return lp
+            pipe = h3.HostBatchPipeline(make, n // 8, n_slots=2)
+            for _ in range(3):
+                pipe.slots[0].run(T)
+            pipe.k0, pipe.t0 = pipe.slots[0].k, pipe.slots[0].env.t
+            t_start = float(pipe.slots[0].stats()["sum_ticks"])
+            hc, hr = pipe.host_chunks_from(pipe.slots[0], 8), pipe.result_buffers(8)
+            pipe.run(hc, hr, T)
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                pipe.run(hc, hr, T)
+            e1.record()
+            torch.cuda.synchronize(device)
+            steps_p = sum(float(r[4][7].item()) - t_start for r in hr) * 3
+            out["extras"]["streamed_state_pipeline"] = {
+                "env_steps_per_s": steps_p / (e0.elapsed_time(e1) * 1e-3), "ticks_per_pass": T, "chunks": 8,
+                "h2d_bytes_per_pass": sum(t.numel() * t.element_size() for ch in hc for t in ch),
+                "d2h_bytes_per_pass": sum(t.numel() * t.element_size() for ch in hr for t in ch),
+                "what": "full episode state (2.7 KB per episode) host -> device, one 200-tick launch per chunk across the "
+                        "switch, results device -> host; copies overlap launches"}
+            del pipe, hc, hr
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            out["extras"]["streamed_state_pipeline"] = {"error": repr(exc)}
         # the 6-DOF widening: train.py's loop, 262,144 episodes, phase 1 and phase 2
         try:
             out["extras"]["six_dof_closed_loop"] = bench_6dof(torch, device, no_cpu=a.no_cpu)
