@@ -584,6 +584,7 @@ def main():
             lo, hi = h3.shard_range(n_total, rank, world)
             p4, setting_of = S.sweep_params(keys, settings, n_seeds, lo, hi, device)
             swr.params.copy_(p4)
+            S.use_rows(swr, ("lon",))           # main.py:56-62 sweeps the cyclic agent only: the collective agent's rows stay uniform
             lp = swr.loop
             nl4 = (a.ticks + a.launch_ticks - 1) // a.launch_ticks
             run_step(swr, 1, lo, a.ticks, a.launch_ticks, a.compact_every)          # warm-up pass

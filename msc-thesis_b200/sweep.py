@@ -59,6 +59,15 @@ def sweep_params(keys, settings, n_seeds, lo, hi, device, agents=("lon",)):
     return p, setting_of
 
 
+def use_rows(runner, agents):
+    """An agent the sweep does not touch keeps launch-uniform hyper-parameters: its per-episode rows are dropped, so
+    the kernels do not re-read six constant rows per tick."""
+    from .episodes import ROW as R
+    lp = runner.loop
+    for name, ag in (("col", lp.agent_col), ("lon", lp.agent_lon)):
+        ag.hyper_rows_device = runner.params[R[name + "_gamma"]:R[name + "_gamma"] + L.HYPER_ROWS] if name in agents else None
+
+
 def setting_sums(alive, score, setting_of_shard, n_settings, group=None):
     """(3, n_settings) sums {episodes, successes, score of the successes} of this rank's shard, all-reduced over the
     ranks (NCCL for CUDA tensors, gloo for CPU tensors).  Episodes that did not survive are excluded BEFORE summing: a
@@ -100,6 +109,7 @@ def run_sweep(grid=None, n_seeds=40, n_ticks=12000, rank=0, world_size=1, out_js
         runner = EpisodeRunner(hi - lo, device=device, precision=precision, per_episode_hyper=True,
                                switch_step=switch_step, score_window=score_window, ticks_per_launch=ticks_per_launch)
     loop = runner.loop
+    use_rows(runner, agents)
     params, setting_of = sweep_params(keys, settings, n_seeds, lo, hi, runner.device, agents=agents)
     runner.params.copy_(params)
     loop.init_episodes(seed, episode0=lo, v_trim=runner.params[ROW["v_trim"]],
