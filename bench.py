@@ -323,7 +323,9 @@ class LaunchLog:
         self.first_tick = [0] * n_launches
 
 
-SORT_KEY = staticmethod(lambda lp: lp.sort_key()).__func__     # per-episode sort key for compact(); None: no sorting
+def SORT_KEY(lp):
+    """Per-episode sort key for compact() (tools/prof_episode.py swaps in alternatives; None: no sorting)."""
+    return lp.sort_key()
 
 
 def run_step(runner, seed, episode0, n_ticks, launch_ticks, compact_every, log=None):
