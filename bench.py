@@ -243,10 +243,13 @@ def bench_6dof(torch, device, n=262144, ticks=100, reps=2, no_cpu=False):
     H6 = importlib.import_module("msc-thesis_b200.heli6dof")
     exc = np.load(os.path.join(ROOT, "tests", "golden", "h6_excitation.npz"))["excitation"]
     res = {"episodes": n, "ticks_per_launch": ticks, "dtype": "f64"}
-    for name, switch in (("phase1", 10 ** 6), ("phase2", 1)):     # switch at tick 1: both agents learn from then on
+    res["rls_f32_storage"] = {"what": "RLS weights / covariance stored as float32 between ticks (H6Batch.rls_f32), arithmetic fp64; "
+                                      "full-episode tolerance: tests/test_gpu_parity6.py F32_STORE_TOL"}
+    for name, switch, storage in (("phase1", 10 ** 6, "f64"), ("phase2", 1, "f64"), ("phase1", 10 ** 6, "f32"), ("phase2", 1, "f32")):
+        # switch at tick 1: both agents learn from then on
         ep = dict(H6.env_params_train, step_switch=switch)
         loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device=device, init="batched",
-                                   generator=torch.Generator().manual_seed(2), ticks_per_launch=ticks)
+                                   generator=torch.Generator().manual_seed(2), ticks_per_launch=ticks, rls_storage=storage)
         loop.run(ticks)
         torch.cuda.synchronize(device)
         before = loop.stats()["sum_ticks"]
@@ -258,9 +261,10 @@ def bench_6dof(torch, device, n=262144, ticks=100, reps=2, no_cpu=False):
         torch.cuda.synchronize(device)
         st = loop.stats()
         sec = e0.elapsed_time(e1) * 1e-3
-        res[name] = {"env_steps_per_s": (st["sum_ticks"] - before) / sec, "ms_per_launch": sec / reps * 1e3,
-                     "alive_fraction": st["n_alive"] / st["n"]}
-        if name == "phase2":
+        (res if storage == "f64" else res["rls_f32_storage"])[name] = {
+            "env_steps_per_s": (st["sum_ticks"] - before) / sec, "ms_per_launch": sec / reps * 1e3,
+            "alive_fraction": st["n_alive"] / st["n"]}
+        if name == "phase2" and storage == "f64":
             res["path"] = "split: sim_kernel (thread per episode) + learn_kernel (17 warps per 32 episodes), tiled " \
                           "W / covariance / networks (DESIGN.md section 9)"
             res["fused_kernel_info"] = loop.info()
@@ -278,6 +282,11 @@ def bench_6dof(torch, device, n=262144, ticks=100, reps=2, no_cpu=False):
         gbs = res[name]["env_steps_per_s"] * words[name] * 8 / 1e9
         res[name]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                  "bytes_per_env_step": words[name] * 8}
+        nbytes = words[name] * 8 - 2 * (255 + 153) * 4          # W and the covariance triangle at 4 bytes per element
+        r32 = res["rls_f32_storage"][name]
+        gbs = r32["env_steps_per_s"] * nbytes / 1e9
+        r32["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                           "bytes_per_env_step": nbytes}
     if not no_cpu:
         from oracle import c_oracle6 as C6
         cfg = C6.default_config(excitation=exc, step_switch=100)

@@ -131,6 +131,13 @@ typedef struct H6Batch {
     int64_t tile;        /* 0: rls_W, rls_cov, col_net, lon_net are plain `[row][ld]`; 32: they are tiled
                             `[ceil(n/32)][rows][32]` (32 episodes' rows contiguous: sequential HBM pages for the
                             streaming kernels), see h6_tile_pack.  Only h6_closed_loop accepts tiled buffers. */
+    int64_t rls_f32;     /* 0: rls_W / rls_cov hold doubles.  1 (needs tile = 32, work != NULL, hist == NULL): the two
+                            TILED buffers hold IEEE binary32 elements (h6_tile_pack_f32; the pointers address float
+                            arrays of ceil(n/32) * rows * 32 elements): the RLS estimator is STORED in single precision
+                            between ticks -- half the bytes of the HBM-bound update -- while every product and sum of
+                            model.py:41-59 and agents.py:130-140 is still formed in fp64.  Not the reference's
+                            precision (numpy float64, model.py:84-85): a throughput option with a stated tolerance
+                            (DESIGN.md section 9). */
 } H6Batch;
 
 /* Optional per-tick log of h6_closed_loop (what Logger.log_states records, util.py:30-66), for the first
@@ -197,6 +204,10 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
  * (H6Batch.tile = 32); to_tiled != 0: plain -> tiled, else tiled -> plain.  The tiled buffer holds
  * ceil(n/32) * rows * 32 doubles. */
 int h6_tile_pack(const double* src, double* dst, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream);
+
+/* The same conversion between a plain `[rows][ld]` array of doubles and a tiled array of floats (H6Batch.rls_f32):
+ * to_tiled != 0 rounds plain -> tiled (round to nearest even), else widens tiled -> plain. */
+int h6_tile_pack_f32(double* plain, float* tiled, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream);
 
 /* Bytes of device scratch h6_closed_loop needs next to `stats`. */
 int64_t h6_stats_scratch_bytes(int64_t n);

@@ -75,7 +75,7 @@ H6_MODES = {"train": 0, "test_1": 1, "test_2": 2, "free": 3}
 H6_STATS_FIELDS = ("n", "n_alive", "n_tmax", "n_nan", "n_envelope", "n_landed", "sum_r_col", "sum_r_lon",
                    "sum_window_r_lon", "sum_ticks")
 H6_EXPORTS = ("h6_engine_power", "h6_trim", "h6_env_derivatives", "h6_env_step", "h6_pid_collective", "h6_pid_latped",
-              "h6_refgen_get_ref", "h6_refgen_set_task", "h6_rls_update", "h6_rls_predict", "h6_closed_loop", "h6_tile_pack",
+              "h6_refgen_get_ref", "h6_refgen_set_task", "h6_rls_update", "h6_rls_predict", "h6_closed_loop", "h6_tile_pack", "h6_tile_pack_f32",
               "h6_stats_scratch_bytes", "h6_closed_loop_info")
 
 
@@ -96,7 +96,7 @@ H6_BATCH_FIELDS = ("state", "t", "P_out", "P_avail", "ref", "pid", "gen", "task"
 
 
 class H6Batch(C.Structure):
-    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS] + [("hist", C.c_void_p), ("hist_len", C.c_int64), ("tile", C.c_int64)]
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64)] + [(k, C.c_void_p) for k in H6_BATCH_FIELDS] + [("hist", C.c_void_p), ("hist_len", C.c_int64), ("tile", C.c_int64), ("rls_f32", C.c_int64)]
 
 
 class H6Traj(C.Structure):
@@ -161,6 +161,7 @@ def lib():
     L.h6_rls_predict.argtypes = [b6, vp, vp, vp, vp]
     L.h6_closed_loop.argtypes = [c6, b6, vp, i32, i32, C.POINTER(H6Traj), vp, vp, vp]
     L.h6_tile_pack.argtypes = [vp, vp, i32, i64, i64, i32, vp]
+    L.h6_tile_pack_f32.argtypes = [vp, vp, i32, i64, i64, i32, vp]
     L.h6_stats_scratch_bytes.argtypes = [i64]
     L.h6_stats_scratch_bytes.restype = i64
     L.h6_closed_loop_info.argtypes = [c6] + [C.POINTER(i32)] * 4

@@ -675,14 +675,16 @@ __global__ void __launch_bounds__(BLOCK) rls_predict_kernel(H6Batch b, const dou
     }
 }
 
-__global__ void __launch_bounds__(256) tile_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows,
+// plain `[rows][ld]` doubles <-> tiled `[tile][rows][32]` elements of type ST (double, or float: H6Batch.rls_f32)
+template <typename ST>
+__global__ void __launch_bounds__(256) tile_pack_kernel(double* __restrict__ plain, ST* __restrict__ tiled, int rows,
                                                         int64_t n, int64_t ld, int to_tiled) {
     const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
     if (e >= n) return;
     const int64_t tb = (e >> 5) * ((int64_t)rows * 32) + (e & 31);
     for (int r = threadIdx.x >> 5; r < rows; r += 8) {
-        if (to_tiled) dst[tb + (int64_t)r * 32] = src[(int64_t)r * ld + e];
-        else dst[(int64_t)r * ld + e] = src[tb + (int64_t)r * 32];
+        if (to_tiled) tiled[tb + (int64_t)r * 32] = (ST)plain[(int64_t)r * ld + e];
+        else plain[(int64_t)r * ld + e] = (double)tiled[tb + (int64_t)r * 32];
     }
 }
 
@@ -828,6 +830,11 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
         return H3_E_ARG;
     }
     if (!check_agents(cfg, "h6_closed_loop")) return H3_E_UNSUPPORTED;
+    const bool f32 = b->rls_f32 != 0;
+    if (f32 && (b->tile != 32 || b->work == nullptr || (b->hist != nullptr && b->hist_len > 0))) {
+        set_error("h6_closed_loop: rls_f32 needs the split path on tiled buffers (tile = 32, work != NULL) without a history buffer");
+        return H3_E_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (b->n > 0 && n_ticks > 0) {
         LoopParams P;
@@ -843,7 +850,7 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
             const bool lazy_req = b->hist != nullptr && b->hist_len > 0;
             const char* mix_env = getenv("H6_MIX");                    // H6_MIX=1 opts in (not the default until measured)
             const bool mix_enabled = mix_env != nullptr && mix_env[0] == '1';
-            if (mix_enabled && traj == nullptr && !lazy_req && b->n >= H6_MIX_MIN) {
+            if (mix_enabled && traj == nullptr && !lazy_req && !f32 && b->n >= H6_MIX_MIN) {
                 // overlapped launches: halves A = [0, nA), B = [nA, n); every launch runs role S on one half and role L
                 // on the other (mixed_kernel), alternating; 2 launches per tick
                 const int64_t nA = ((b->n / 2 + 127) / 128) * 128, nB = b->n - nA;
@@ -882,16 +889,24 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
             }
             for (int it = 0; it <= n_ticks; ++it) {
                 if (it > 0) {
-                    if (til) agents_kernel<true><<<ga, 128, 0, st>>>(P, it == n_ticks); else agents_kernel<false><<<ga, 128, 0, st>>>(P, it == n_ticks);
+                    if (f32) agents_kernel<true, float><<<ga, 128, 0, st>>>(P, it == n_ticks);
+                    else if (til) agents_kernel<true><<<ga, 128, 0, st>>>(P, it == n_ticks);
+                    else agents_kernel<false><<<ga, 128, 0, st>>>(P, it == n_ticks);
                 }
                 if (it == n_ticks) {
-                    if (sym) { if (til) mirror_kernel<true><<<gl, LEARN_BLOCK, 0, st>>>(*b); else mirror_kernel<false><<<gl, LEARN_BLOCK, 0, st>>>(*b); }
+                    if (sym) {
+                        if (f32) mirror_kernel<true, float><<<gl, LEARN_BLOCK, 0, st>>>(*b);
+                        else if (til) mirror_kernel<true><<<gl, LEARN_BLOCK, 0, st>>>(*b);
+                        else mirror_kernel<false><<<gl, LEARN_BLOCK, 0, st>>>(*b);
+                    }
                     break;
                 }
                 if (til) sim_kernel<true><<<gs, 128, 0, st>>>(P, it); else sim_kernel<false><<<gs, 128, 0, st>>>(P, it);
                 const int slot = it % T;
                 double* hs = lazy ? b->hist + (int64_t)slot * H6_HIST_ROWS * b->ld : nullptr;
-                if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                if (f32 && sym) learn_kernel<true, true, float><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                else if (f32) learn_kernel<false, true, float><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
+                else if (sym && til) learn_kernel<true, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
                 else if (sym) learn_kernel<true, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
                 else if (til) learn_kernel<false, true><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
                 else learn_kernel<false, false><<<gl, LEARN_BLOCK, 0, st>>>(*b, cfg->rls_gamma, live, hs);
@@ -924,7 +939,16 @@ int h6_closed_loop(const H6Config* cfg, const H6Batch* b, const double* excitati
 int h6_tile_pack(const double* src, double* dst, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream) {
     if (!src || !dst || rows <= 0 || n < 0 || ld < n) { set_error("h6_tile_pack: bad argument"); return H3_E_ARG; }
     if (n == 0) return H3_OK;
-    tile_pack_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, n, ld, to_tiled);
+    double* plain = const_cast<double*>(to_tiled ? src : dst);
+    double* tiled = const_cast<double*>(to_tiled ? dst : src);
+    tile_pack_kernel<double><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(plain, tiled, rows, n, ld, to_tiled);
+    return check_launch("h6 tile_pack_kernel");
+}
+
+int h6_tile_pack_f32(double* plain, float* tiled, int32_t rows, int64_t n, int64_t ld, int32_t to_tiled, void* stream) {
+    if (!plain || !tiled || rows <= 0 || n < 0 || ld < n) { set_error("h6_tile_pack_f32: bad argument"); return H3_E_ARG; }
+    if (n == 0) return H3_OK;
+    tile_pack_kernel<float><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(plain, tiled, rows, n, ld, to_tiled);
     return check_launch("h6 tile_pack_kernel");
 }
 

@@ -25,8 +25,8 @@ enum { AG_S0 = 0, AG_S1 = 1, AG_N0 = 2, AG_N1 = 3, AG_DR = 4 };
 enum { WF_ACTIVE = 1, WF_RLS = 2, WF_COL = 4 };
 
 // get_transition_matrices + update_networks (agents.py:130-196) of one agent from its work rows
-template <typename NetT>
-H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr_c, const double* __restrict__ W, int64_t lw,
+template <typename NetT, typename WT>
+H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr_c, const WT* __restrict__ W, int64_t lw,
                         int64_t ld, const double* wk, bool tau1_fast) {
     const double s0 = wk[AG_S0 * ld], s1 = wk[AG_S1 * ld], n0 = wk[AG_N0 * ld], n1 = wk[AG_N1 * ld], dr = wk[AG_DR * ld];
     double hh[NH], scr[NH], f;
@@ -37,8 +37,8 @@ H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) F[i][j] = W[(int64_t)(idx[j] * NS + idx[i]) * lw];
-        G[i] = W[(int64_t)((NS + h.channel) * NS + idx[i]) * lw];
+        for (int j = 0; j < 2; ++j) F[i][j] = (double)W[(int64_t)(idx[j] * NS + idx[i]) * lw];
+        G[i] = (double)W[(int64_t)((NS + h.channel) * NS + idx[i]) * lw];
     }
     AgentH<double> H;
     H.gamma = h.gamma; H.lr_a = lr_a; H.lr_c = lr_c; H.tau = h.tau; H.scale = h.scale;
@@ -210,7 +210,8 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk, do
 //   fast: tau == 1 and the target critic equals the critic at call entry (H6Config.target_synced): the target rows
 //   are then neither read nor written by the updates (agents.py:196 makes them equal again); they are refreshed from
 //   the critic after an episode's last update of the call (`final`, or the episode has just ended).
-template <bool TILED>
+//   ST: storage type of the tiled W / covariance (H6Batch.rls_f32: float; the arithmetic is fp64 either way).
+template <bool TILED, typename ST = double>
 __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ LoopParams P, int final) {
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ 
     const H3AgentHyper& h = col ? C.col : C.lon;
     const bool fast = h.tau == 1.0 && (C.target_synced & (col ? 1 : 2));
     const int64_t lw = TILED ? 32 : ld;
-    const double* __restrict__ W = b.rls_W + tile_off(b, e, NR * NS);
+    const ST* __restrict__ W = reinterpret_cast<const ST*>(b.rls_W) + tile_off(b, e, NR * NS);
     typename NetOf<TILED>::type net;
     net.v.p = (col ? b.col_net : b.lon_net) + tile_off(b, e, 11 * NH); net.v.ld = lw;
     const int o = col ? 0 : 2;
@@ -268,22 +269,26 @@ constexpr int LEARN_WARPS = NR, LEARN_BLOCK = 32 * LEARN_WARPS;
 #define H6_LEARN_CH 6
 #endif
 constexpr int LEARN_CH = H6_LEARN_CH;
+#ifndef H6_LEARN_CH32
+#define H6_LEARN_CH32 12    // float storage (H6Batch.rls_f32): the same registers hold twice the elements
+#endif
 
-template <bool SYM, bool TILED>
+template <bool SYM, bool TILED, typename ST = double>
 __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Batch b, double gamma, unsigned live_mask,
                                                                            double* __restrict__ hist) {
     __shared__ double Xs[NR][32], cXs[NR][32], Xcs[SYM ? 1 : NR][32];
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * 32 + lane, ld = b.ld;
+    constexpr int CH = sizeof(ST) == 4 ? H6_LEARN_CH32 : LEARN_CH;  // raw elements in flight per thread and chunk
     const bool in = e < b.n;
     const int wf = in ? (int)b.work[WR_FLAGS * ld + e] : 0;
     const bool on = (wf & (WF_ACTIVE | WF_RLS)) == (WF_ACTIVE | WF_RLS);
     const double* __restrict__ wk = b.work + e;
     const int64_t lw = TILED ? 32 : ld;
-    double* __restrict__ cov = b.rls_cov + tile_off(b, e, NR * NR);
-    double* __restrict__ rowp = cov + (int64_t)(r * NR) * lw;       // element (r, j) at rowp[j * lw]
-    const double* __restrict__ colp = cov + (int64_t)r * lw;          // element (j, r) at colp[j * NR * lw]
-    double* __restrict__ wp = b.rls_W + tile_off(b, e, NR * NS) + (int64_t)r * lw;     // W(i, r) at wp[i * NS * lw]
+    ST* __restrict__ cov = reinterpret_cast<ST*>(b.rls_cov) + tile_off(b, e, NR * NR);
+    ST* __restrict__ rowp = cov + (int64_t)(r * NR) * lw;           // element (r, j) at rowp[j * lw]
+    const ST* __restrict__ colp = cov + (int64_t)r * lw;              // element (j, r) at colp[j * NR * lw]
+    ST* __restrict__ wp = reinterpret_cast<ST*>(b.rls_W) + tile_off(b, e, NR * NS) + (int64_t)r * lw;     // W(i, r) at wp[i * NS * lw]
     // hist != nullptr: this tick's slot of the history, [H6_HIST_ROWS][ld]; columns of W outside live_mask are not
     // touched here but brought up to date later by lazy_w_kernel from the recorded X, cov.X, 1/d, Y
     double* __restrict__ hs = hist != nullptr ? hist + e : nullptr;
@@ -298,33 +303,33 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
     if (on) {
         double a0 = 0, a1 = 0;
 #pragma unroll
-        for (int j0 = 0; j0 < NR; j0 += LEARN_CH) {
-            double c[LEARN_CH];
+        for (int j0 = 0; j0 < NR; j0 += CH) {
+            ST c[CH];
 #pragma unroll
-            for (int u = 0; u < LEARN_CH; ++u) {
+            for (int u = 0; u < CH; ++u) {
                 const int j = j0 + u;
                 if (j < NR) c[u] = (SYM && j < r) ? colp[(int64_t)(j * NR) * lw] : rowp[(int64_t)j * lw];
             }
             h3::row_fence<true>();
 #pragma unroll
-            for (int u = 0; u < LEARN_CH; ++u) {
+            for (int u = 0; u < CH; ++u) {
                 const int j = j0 + u;
-                if (j < NR) { if (u & 1) a1 += c[u] * Xs[j][lane]; else a0 += c[u] * Xs[j][lane]; }    // model.py:53
+                if (j < NR) { if (u & 1) a1 += (double)c[u] * Xs[j][lane]; else a0 += (double)c[u] * Xs[j][lane]; }    // model.py:53
             }
         }
         cx = a0 + a1;
         if (!SYM) {
             a0 = 0; a1 = 0;
 #pragma unroll
-            for (int i0 = 0; i0 < NR; i0 += LEARN_CH) {
-                double c[LEARN_CH];
+            for (int i0 = 0; i0 < NR; i0 += CH) {
+                ST c[CH];
 #pragma unroll
-                for (int u = 0; u < LEARN_CH; ++u)
+                for (int u = 0; u < CH; ++u)
                     if (i0 + u < NR) c[u] = colp[(int64_t)((i0 + u) * NR) * lw];
                 h3::row_fence<true>();
 #pragma unroll
-                for (int u = 0; u < LEARN_CH; ++u)
-                    if (i0 + u < NR) { if (u & 1) a1 += Xs[i0 + u][lane] * c[u]; else a0 += Xs[i0 + u][lane] * c[u]; }   // model.py:54
+                for (int u = 0; u < CH; ++u)
+                    if (i0 + u < NR) { if (u & 1) a1 += Xs[i0 + u][lane] * (double)c[u]; else a0 += Xs[i0 + u][lane] * (double)c[u]; }   // model.py:54
             }
             xc = a0 + a1;
         }
@@ -343,32 +348,33 @@ __global__ void __launch_bounds__(LEARN_BLOCK, H6_LEARN_MINB) learn_kernel(H6Bat
     {
         const double gr = cx * inv_d;
 #pragma unroll
-        for (int j0 = 0; j0 < NR; j0 += LEARN_CH) {
-            double c[LEARN_CH];
+        for (int j0 = 0; j0 < NR; j0 += CH) {
+            ST c[CH];
 #pragma unroll
-            for (int u = 0; u < LEARN_CH; ++u)
+            for (int u = 0; u < CH; ++u)
                 if (j0 + u < NR && (!SYM || j0 + u >= r)) c[u] = rowp[(int64_t)(j0 + u) * lw];
             h3::row_fence<true>();
 #pragma unroll
-            for (int u = 0; u < LEARN_CH; ++u)
+            for (int u = 0; u < CH; ++u)
                 if (j0 + u < NR && (!SYM || j0 + u >= r))
-                    rowp[(int64_t)(j0 + u) * lw] = (c[u] - gr * (SYM ? cXs[j0 + u][lane] : Xcs[j0 + u][lane])) * inv_gamma;
+                    rowp[(int64_t)(j0 + u) * lw] = (ST)(((double)c[u] - gr * (SYM ? cXs[j0 + u][lane] : Xcs[j0 + u][lane])) * inv_gamma);
         }
     }
     // model.py:49-50, :58, column r of W
     if (r < NS && hs != nullptr && !((live_mask >> r) & 1u)) {
         hs[(int64_t)(2 * NR + 1 + r) * ld] = wk[(WR_Y + r) * ld];
     } else if (r < NS) {
-        double w[NR], ya = wk[(WR_Y + r) * ld], yb = 0;
+        ST w[NR];
+        double ya = wk[(WR_Y + r) * ld], yb = 0;
 #pragma unroll
         for (int i = 0; i < NR; ++i) w[i] = wp[(int64_t)(i * NS) * lw];
 #pragma unroll
-        for (int i = 0; i < NR; i += 2) ya -= Xs[i][lane] * w[i];
+        for (int i = 0; i < NR; i += 2) ya -= Xs[i][lane] * (double)w[i];
 #pragma unroll
-        for (int i = 1; i < NR; i += 2) yb += Xs[i][lane] * w[i];
+        for (int i = 1; i < NR; i += 2) yb += Xs[i][lane] * (double)w[i];
         const double err = (ya - yb) * inv_d;
 #pragma unroll
-        for (int i = 0; i < NR; ++i) wp[(int64_t)(i * NS) * lw] = w[i] + cXs[i][lane] * err;
+        for (int i = 0; i < NR; ++i) wp[(int64_t)(i * NS) * lw] = (ST)((double)w[i] + cXs[i][lane] * err);
     }
 }
 
@@ -565,14 +571,14 @@ __global__ void __launch_bounds__(MIX_BLOCK, H6_SIM_MINB) mixed_kernel(const __g
 }
 
 // lower triangle := upper triangle (once per call, after the last tick): thread = (episode, row)
-template <bool TILED>
+template <bool TILED, typename ST = double>
 __global__ void __launch_bounds__(LEARN_BLOCK) mirror_kernel(H6Batch b) {
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * 32 + lane, ld = b.ld;
     if (e >= b.n) return;
     const int64_t lw = TILED ? 32 : ld;
-    double* __restrict__ cov = b.rls_cov + tile_off(b, e, NR * NR);
-    double c[NR];
+    ST* __restrict__ cov = reinterpret_cast<ST*>(b.rls_cov) + tile_off(b, e, NR * NR);
+    ST c[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j)
         if (j > r) c[j] = cov[(int64_t)(r * NR + j) * lw];

@@ -500,7 +500,12 @@ class ClosedLoop6DOF:
 
     def __init__(self, env, lateral_pid, collective_pid, ref_generator, rls, agent_col, agent_lon, mode="train",
                  step_switch=6000, excitation=None, load_agents=False, score_window=(5000, 6000), ref=None,
-                 ticks_per_launch=500):
+                 ticks_per_launch=500, rls_storage="f64"):
+        if rls_storage not in ("f64", "f32"):
+            raise ValueError("rls_storage must be 'f64' (the reference's numpy float64, model.py:84-85) or 'f32'")
+        # 'f32': inside run() the RLS weights and covariance are STORED as float32 between ticks (half the bytes of the
+        # HBM-bound update; all arithmetic stays fp64).  A throughput option, not the reference's precision.
+        self.rls_storage = rls_storage
         self.env, self.lat_pid, self.col_pid, self.gen, self.rls = env, lateral_pid, collective_pid, ref_generator, rls
         self.agent_col, self.agent_lon = agent_col, agent_lon
         self.n = n = env.n_envs
@@ -544,7 +549,8 @@ class ClosedLoop6DOF:
         # work on these (32 episodes' rows are contiguous in HBM); they are packed / unpacked once per run() call
         self.tiled = True
         nt = (n + 31) // 32
-        self._tiles = {k: torch.zeros(nt * rows * 32, dtype=F64, device=dev)
+        f32 = rls_storage == "f32"
+        self._tiles = {k: torch.zeros(nt * rows * 32, dtype=torch.float32 if (f32 and k.startswith("rls_")) else F64, device=dev)
                        for k, rows in (("rls_W", NR * NS), ("rls_cov", NR * NR), ("col_net", 11 * NH), ("lon_net", 11 * NH))}
         # lazy=True: only the 4 columns of W the agents read are updated every tick, the other 11 are advanced every
         # hist_len ticks from a recorded history (H6Batch.hist).  Same results, 28 % less RLS traffic, but measured no
@@ -600,6 +606,9 @@ class ClosedLoop6DOF:
     def _pack(self, to_tiled):
         lib, st, n = L.lib(), L.stream_ptr(self.device), self.n
         for k, plain in self._plain().items():
+            if self._tiles[k].dtype == torch.float32:
+                L.check(lib.h6_tile_pack_f32(L.ptr(plain), L.ptr(self._tiles[k]), plain.shape[0], n, n, int(to_tiled), st))
+                continue
             src, dst = (plain, self._tiles[k]) if to_tiled else (self._tiles[k], plain)
             L.check(lib.h6_tile_pack(L.ptr(src), L.ptr(dst), plain.shape[0], n, n, int(to_tiled), st))
 
@@ -613,6 +622,10 @@ class ClosedLoop6DOF:
                       flags=env.flags, term_step=env.term_step, update_col=self.update_col,
                       excitation_phase=self.excitation_phase, acc=self.acc, work=self.work if self.split else None)
         b.tile = 32 if self.tiled else 0
+        if self.rls_storage == "f32":
+            if not (self.tiled and self.split) or self.lazy:
+                raise NotImplementedError("rls_storage='f32' runs on the tiled split path only (tiled = split = True, lazy = False)")
+            b.rls_f32 = 1
         if self.split and self.lazy:
             if self._hist is None or self._hist.shape[0] != self.hist_len:
                 self._hist = torch.zeros(self.hist_len, L.H6_HIST_ROWS, self.n, dtype=F64, device=self.device)
@@ -706,7 +719,7 @@ class ClosedLoop6DOF:
 
 def make_closed_loop(n_envs, mode="train", env_params=None, ac_params=None, rls_params_=None, pid_params_=None,
                      excitation=None, load_agents=False, device=None, init="auto", generator=None, seed=None,
-                     ticks_per_launch=500):
+                     ticks_per_launch=500, rls_storage="f64"):
     """The wiring of train.py:52-106 for N episodes -> ClosedLoop6DOF."""
     ep = dict({"train": env_params_train, "test_1": env_params_test1, "test_2": env_params_test2}[mode]
               if env_params is None else env_params)
@@ -727,7 +740,8 @@ def make_closed_loop(n_envs, mode="train", env_params=None, ac_params=None, rls_
     lat = LatPedPID(phi_trim=trim_state[6], lat_trim=trim_actions[2], pedal_trim=trim_actions[3], dt=ep["dt"], gains_dict=pp)
     col = CollectivePID6DOF(col_trim=trim_actions[0], h_ref=ep['initial_altitude'], dt=ep['dt'], proportional_gain=pp['Kh'])
     return ClosedLoop6DOF(env, lat, col, gen, rls, agent_col, agent_lon, mode=mode, step_switch=ep['step_switch'],
-                          excitation=excitation, load_agents=load_agents, ticks_per_launch=ticks_per_launch)
+                          excitation=excitation, load_agents=load_agents, ticks_per_launch=ticks_per_launch,
+                          rls_storage=rls_storage)
 
 
 class Logger:
@@ -799,13 +813,13 @@ class Logger:
 
 def train(mode, env_params, ac_params, rls_params, pid_params, excitation, n_envs=1, seed=0, device=None,
           load_agents=False, agents=None, record=0, return_logs=False, save_weights=False, weight_save_interval=10,
-          log_episode=0):
+          log_episode=0, rls_storage="f64"):
     """train.train (train.py:20-264) for N episodes: runs the whole episode in fused launches and returns
     (ClosedLoop6DOF, success (N,) bool, score (N,), log or None).  return_logs=True: the last element is a Logger for
     episode `log_episode` (state history; with save_weights the network / RLS histories every weight_save_interval
     ticks, train.py:193-195 -- the loop then runs in launches of that many ticks)."""
     loop = make_closed_loop(n_envs, mode, env_params, ac_params, rls_params, pid_params, excitation=excitation,
-                            load_agents=load_agents, device=device, seed=seed)
+                            load_agents=load_agents, device=device, seed=seed, rls_storage=rls_storage)
     if agents is not None:                                                # train.py:68-72
         loop.agent_col.net.copy_(agents["col"]); loop.agent_lon.net.copy_(agents["lon"])
         loop.rls._W.copy_(agents["rls_W"]); loop.rls._cov.copy_(agents["rls_cov"])

@@ -524,3 +524,73 @@ def test_free_mode_with_host_driven_events_equals_train_mode():
         assert H.rel_err(a[k], b[k]) < 1e-12, k
     for k in ("step", "flags", "task", "update_col", "excitation_phase"):
         assert np.array_equal(a[k], b[k]), k
+
+
+# RLS estimator stored in float32 between ticks (H6Batch.rls_f32; arithmetic fp64).  Stated tolerance against the fp64
+# path over WHOLE training episodes of train.py (12,001 ticks, switch at 6000), per episode:
+# (measured worst of 48 episodes: 9.9e-5, 4.7e-5 rad, 6.9e-4 m/s, 1.1e-4)
+F32_STORE_TOL = {"score_rel": 1e-3, "theta_rms_rad": 2e-4, "u_rms_mps": 5e-3, "action_rms": 1e-3}
+
+
+def test_rls_f32_storage_first_tick_and_pack_round_trip():
+    """The wiring: packing rounds W / cov to float32 (round to nearest even, what torch does), nothing else; the model
+    step of the first tick does not depend on the estimator, so the states agree bit for bit and the networks (which
+    see F, G from the rounded W) to 1e-6."""
+    H6 = pkg()
+    n = 70
+    make = lambda st: H6.make_closed_loop(n, "train", excitation=H.excitation(), device=DEV, init="batched",
+                                          generator=torch.Generator().manual_seed(4), ticks_per_launch=50, rls_storage=st)
+    a, b = make("f64"), make("f32")
+    for lp in (a, b):
+        lp.run(3)                       # past the skipped first update: W and cov are no longer the initial values
+    W64 = a.rls.W.clone()
+    b.rls._W.copy_(a.rls._W); b.rls._cov.copy_(a.rls._cov)
+    b._pack(True); b._pack(False)
+    assert torch.equal(b.rls._W, a.rls._W.float().double()) and torch.equal(b.rls._cov, a.rls._cov.float().double())
+    assert not torch.equal(b.rls.W, W64)
+    a2, b2 = make("f64"), make("f32")
+    a2.run(1); b2.run(1)
+    sa, sb = H.loop_state(a2), H.loop_state(b2)
+    assert np.array_equal(sa["state"], sb["state"]) and np.array_equal(sa["step"], sb["step"])
+    a2.run(2); b2.run(2)
+    sa, sb = H.loop_state(a2), H.loop_state(b2)
+    for k in ("col_a_w1", "lon_a_w1", "lon_c_w2"):
+        assert H.rel_err(sb[k], sa[k]) < 1e-4, k
+    assert H.rel_err(sb["rls_W"], sa["rls_W"]) < 1e-4 and not np.array_equal(sb["rls_W"], sa["rls_W"])
+
+
+def test_rls_f32_storage_full_episode_tolerance():
+    """Whole training episodes (train.py __main__ configuration, 48 seeds) with the estimator stored in float32 against the
+    fp64 path: same outcomes, per-episode score / pitch / speed / controls within F32_STORE_TOL."""
+    H6 = pkg()
+    n, total = 48, H6.env_params_train["n_steps"] + 2
+    runs = {}
+    for st in ("f64", "f32"):
+        lp = H6.make_closed_loop(n, "train", excitation=H.excitation(), device=DEV, init="batched",
+                                 generator=torch.Generator().manual_seed(11), ticks_per_launch=1000, rls_storage=st)
+        log = lp.run(total, record=n)
+        ok, score = lp.scores()
+        runs[st] = (log.cpu().numpy(), ok.cpu().numpy(), score.cpu().numpy(), H.loop_state(lp))
+    (la, oka, sca, sa), (lb, okb, scb, sb) = runs["f64"], runs["f32"]
+    assert np.array_equal(sa["flags"], sb["flags"]) and np.array_equal(sa["step"], sb["step"]) and np.array_equal(oka, okb)
+    assert oka.mean() > 0.9                                  # the comparison is over episodes that fly the whole task
+    live = (la[:, 25, :] > 0) & (lb[:, 25, :] > 0)           # (ticks, episodes)
+    rms = lambda d: np.sqrt((np.where(live, d, 0.0) ** 2).sum(0) / np.maximum(live.sum(0), 1))
+    good = oka & np.isfinite(sca) & (sca > 0)
+    worst = {"score_rel": float(np.max(np.abs(scb - sca)[good] / sca[good])),
+             "theta_rms_rad": float(rms(lb[:, 7, :] - la[:, 7, :])[good].max()),
+             "u_rms_mps": float(rms(lb[:, 0, :] - la[:, 0, :])[good].max()),
+             "action_rms": float(max(rms(lb[:, 18 + i, :] - la[:, 18 + i, :])[good].max() for i in range(2)))}
+    print("rls_f32 storage, worst episode of %d:" % int(good.sum()), worst)
+    for k, tol in F32_STORE_TOL.items():
+        assert worst[k] < tol, (k, worst)
+
+
+def test_rls_f32_storage_needs_the_tiled_split_path():
+    H6 = pkg()
+    lp = H6.make_closed_loop(8, "train", device=DEV, init="batched", rls_storage="f32")
+    lp.split = False
+    with pytest.raises(NotImplementedError):
+        lp.run(1)
+    with pytest.raises(ValueError):
+        H6.make_closed_loop(8, "train", device=DEV, init="batched", rls_storage="f16")

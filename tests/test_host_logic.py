@@ -74,7 +74,7 @@ def test_6dof_exports_and_struct_layout(tmp_path):
 int main(void) {
   printf("%zu %zu %zu\\n", sizeof(H6Config), sizeof(H6Batch), sizeof(H6Traj));
   printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(H6Config, lat_gains), offsetof(H6Config, amp), offsetof(H6Config, run_mode), offsetof(H6Config, win_hi), offsetof(H6Config, col), offsetof(H6Config, lon));
-  printf("%zu %zu %zu %zu\\n", offsetof(H6Batch, state), offsetof(H6Batch, trim_act), offsetof(H6Batch, rls_skip), offsetof(H6Batch, acc));
+  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(H6Batch, state), offsetof(H6Batch, trim_act), offsetof(H6Batch, rls_skip), offsetof(H6Batch, acc), offsetof(H6Batch, tile), offsetof(H6Batch, rls_f32));
   return 0;
 }''')
     exe = tmp_path / "layout6"
@@ -84,7 +84,7 @@ int main(void) {
     assert [int(x) for x in lines[1].split()] == [getattr(L.H6Config, k).offset for k in
                                                   ("lat_gains", "amp", "run_mode", "win_hi", "col", "lon")]
     assert [int(x) for x in lines[2].split()] == [getattr(L.H6Batch, k).offset for k in
-                                                  ("state", "trim_act", "rls_skip", "acc")]
+                                                  ("state", "trim_act", "rls_skip", "acc", "tile", "rls_f32")]
     assert len(L.H6_BATCH_FIELDS) == 25 and L.H6Batch.tile.offset == L.H6Batch.work.offset + 24
 
 

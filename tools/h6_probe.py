@@ -18,7 +18,7 @@ def main():
     for switch in (10 ** 6, 1):      # 1: the collective agent takes over (and learns) from tick 1 on
         ep = dict(H6.env_params_train, step_switch=switch)
         loop = H6.make_closed_loop(n, "train", env_params=ep, excitation=exc, device="cuda", init="batched",
-                                   ticks_per_launch=ticks)
+                                   ticks_per_launch=ticks, rls_storage=os.environ.get("H6_STORAGE", "f64"))
         loop.split = os.environ.get("H6_SPLIT", "1") != "0"
         loop.tiled = os.environ.get("H6_TILED", "1") != "0"
         loop.lazy = os.environ.get("H6_LAZY", "0") != "0"
