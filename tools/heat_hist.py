@@ -1,6 +1,7 @@
+"""Distribution of the slow-branch duty-cycle counters (H3Batch.heat) over whole episodes: python tools/heat_hist.py"""
 import sys, torch
 sys.path.insert(0, ".")
-import bench, msc_thesis_b200 as h3
+import msc_thesis_b200 as h3
 from msc_thesis_b200 import episodes as EP
 dev = torch.device("cuda", 0)
 n = 1 << 18
