@@ -420,6 +420,7 @@ template <typename ET, typename NT, int NH>
 __global__ void __launch_bounds__(SMALL_BLOCK)
     agent_action_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
                         const ET* __restrict__ ref, NT* out, int64_t n, int64_t ld) {
+    Math<NT>::prepare();                        // tanh table -> shared memory (all threads, before the bounds check)
     const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
     if (e >= n) return;
     double w_r;
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
                         const ET* __restrict__ next_state, const ET* __restrict__ ref,
                         const ET* __restrict__ next_ref, const NT* __restrict__ dr_ds, const NT* __restrict__ Fm,
                         const NT* __restrict__ Gm, int64_t n, int64_t ld) {
+    Math<NT>::prepare();                        // tanh table -> shared memory (all threads, before the bounds check)
     const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
     if (e >= n) return;
     double w_r;
@@ -503,6 +505,7 @@ template <typename ET, typename NT>
 __global__ void __launch_bounds__(SMALL_BLOCK)
     agent_action_rt_kernel(H3AgentHyper h, const double* __restrict__ hyper, NT* net, const ET* __restrict__ state,
                            const ET* __restrict__ ref, NT* out, int64_t n, int64_t ld) {
+    Math<NT>::prepare();                        // tanh table -> shared memory (all threads, before the bounds check)
     const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
     if (e >= n) return;
     double w_r;
@@ -521,6 +524,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
                            const ET* __restrict__ next_state, const ET* __restrict__ ref,
                            const ET* __restrict__ next_ref, const NT* __restrict__ dr_ds, const NT* __restrict__ Fm,
                            const NT* __restrict__ Gm, int64_t n, int64_t ld) {
+    Math<NT>::prepare();                        // tanh table -> shared memory (all threads, before the bounds check)
     const int64_t e = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
     if (e >= n) return;
     double w_r;
@@ -609,6 +613,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, T* out) {
 // direct access to the kernel's own fp64 math (tests/test_gpu_math.py)
 __global__ void __launch_bounds__(SMALL_BLOCK) math_probe_kernel(int fn, const double* __restrict__ x, double* y,
                                                                  double* y2, int64_t n) {
+    Math<double>::prepare();
     const int64_t i = (int64_t)blockIdx.x * SMALL_BLOCK + threadIdx.x;
     if (i >= n) return;
     if (fn == 0) {

@@ -135,7 +135,7 @@ struct LoopLayout {
         sizeof(NT) * N_STASH;
     static constexpr size_t tile_bytes = ((bytes_per_lane * LANES + 15) / 16) * 16;
     __host__ __device__ static constexpr size_t head_bytes(int warps) {
-        return sizeof(double) * (3 * TICK_CHUNK + warps * H3_N_STATS);
+        return sizeof(double) * warps * (3 * TICK_CHUNK + H3_N_STATS);
     }
     __host__ __device__ static constexpr size_t smem_bytes(int warps) {
         return head_bytes(warps) + tile_bytes * warps;
@@ -165,11 +165,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     constexpr int NNL = LY::NNL;
     constexpr int BLOCK = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sh_ref = reinterpret_cast<double*>(smem_raw);               // [TICK_CHUNK]
-    double* sh_exc = sh_ref + TICK_CHUNK;                               // [TICK_CHUNK][2]
-    double* sh_red = sh_exc + 2 * TICK_CHUNK;                           // [WARPS][H3_N_STATS]
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // reference / excitation slices are staged per warp (no CTA barrier in the tick loop: the warps of a CTA drift apart)
+    double* sh_ref = reinterpret_cast<double*>(smem_raw) + warp * 3 * TICK_CHUNK;       // [TICK_CHUNK]
+    double* sh_exc = sh_ref + TICK_CHUNK;                                               // [TICK_CHUNK][2]
+    double* sh_red = reinterpret_cast<double*>(smem_raw) + WARPS * 3 * TICK_CHUNK;      // [WARPS][H3_N_STATS]
+
     const int sub = lane;                               // episode slot inside the warp
     const int64_t e = ((int64_t)blockIdx.x * WARPS + warp) * LANES + sub;
     const bool valid = (sub < LANES) && (e < P.n);
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     const int64_t ec = valid ? e : 0;          // idle lanes read episode 0 (in bounds) and never store
     const int lc = sub < LANES ? sub : 0;       // ... and alias slot 0's tile column (never written: flags != 0)
     const EnvK<ET>& K = P.K;
+    Math<NT>::prepare();                        // tanh table -> (static) shared memory
 
     // ---- carve the warp's tile ----
     unsigned char* tp = smem_raw + LY::head_bytes(WARPS) + LY::tile_bytes * warp;
@@ -267,15 +269,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     for (int c0 = 0; c0 < P.n_ticks; c0 += TICK_CHUNK) {
         const int cn = min(TICK_CHUNK, P.n_ticks - c0);
         if (lockstep) {
-            __syncthreads();
-            for (int i = tid; i < cn; i += BLOCK) {
-                if (table_ref) sh_ref[i] = P.ref_table[c0 + i];
-                const int kk = P.step0 + c0 + i;
+            static_assert(TICK_CHUNK <= 32, "one lane stages one tick");
+            __syncwarp();
+            if (lane < cn) {
+                if (table_ref) sh_ref[lane] = P.ref_table[c0 + lane];
+                const int kk = P.step0 + c0 + lane;
                 const bool on = (P.excitation != nullptr) && (kk < P.exc_len);
-                sh_exc[2 * i] = on ? P.excitation[2 * kk] : 0.0;
-                sh_exc[2 * i + 1] = on ? P.excitation[2 * kk + 1] : 0.0;
+                sh_exc[2 * lane] = on ? P.excitation[2 * kk] : 0.0;
+                sh_exc[2 * lane + 1] = on ? P.excitation[2 * kk + 1] : 0.0;
             }
-            __syncthreads();
+            __syncwarp();
         }
         for (int jj = 0; jj < cn; ++jj) {
             constexpr unsigned amask = 0xffffffffu;

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
     const int64_t ec = valid ? e : 0;
     const EnvK<ET>& K = P.K;
     __shared__ double sh_red[(RT_BLOCK / 32) * H3_N_STATS];
+    Math<NT>::prepare();
 
     CovFull<ET, GVec<ET>> cov;              // model.py:53-59 literally, on the full matrix
     cov.v.p = P.rls_cov + ec;

@@ -215,11 +215,13 @@ template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int 
 struct TmLayout {
     static constexpr int WARPS = WARPS_;           // 4 or 8: warps w and w + 4 share a lane quadrant, own column ranges
     static constexpr int STRIDE = LANES < 32 ? LANES + 1 : 32;      // + one dummy column for the idle lanes
-    static constexpr size_t bytes_per_col = sizeof(double) * 3 + sizeof(ET) * (45 + 63) + ((TAU1L || H3_TM_TARGET_REGS) ? 0 : sizeof(NT) * 4 * NHL);
+    static constexpr size_t bytes_per_col = sizeof(ET) * (45 + 63) + ((TAU1L || H3_TM_TARGET_REGS) ? 0 : sizeof(NT) * 4 * NHL);
     static constexpr size_t tile_bytes = ((bytes_per_col * STRIDE + 15) / 16) * 16;
     static constexpr size_t head_bytes = sizeof(double) * WARPS * (3 * TICK_CHUNK + H3_N_STATS) + 16;
     static constexpr size_t smem_bytes = head_bytes + tile_bytes * WARPS;
-    static constexpr int tm_words = ColTm<NHC>::WORDS * (int)(sizeof(NT) / 4);
+    // after the collective agent: the three reward accumulators (doubles, + one pad word) -- 8 columns
+    static constexpr int acc_col = ColTm<NHC>::WORDS * (int)(sizeof(NT) / 4);
+    static constexpr int tm_words = acc_col + 8;
     static constexpr int tm_cols = tm_words <= 32 ? 32 : (tm_words <= 64 ? 64 : (tm_words <= 128 ? 128 : (tm_words <= 256 ? 256 : 512)));
     static_assert(tm_cols * (WARPS / 4) <= 512 && (WARPS == 4 || WARPS == 8), "collective agent does not fit a thread's tensor-memory columns");
 };
@@ -249,6 +251,8 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     const int64_t ec = valid ? e : 0;               // idle lanes read episode 0 (in bounds) and never store
     const int lc = lane < LANES ? lane : LANES;     // ... and share the tile's dummy column
     const EnvK<ET>& K = P.K;
+    const uint32_t tm_acc = tm + (uint32_t)LY::acc_col;     // sum r_col, sum r_lon, sum r_lon inside the score window
+    Math<NT>::prepare();                                    // tanh table -> (static) shared memory
 
     // ---- carve the warp's tile ----
     unsigned char* tp = smem_raw + LY::head_bytes + LY::tile_bytes * warp;
@@ -256,11 +260,8 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     CovSym<ET, CovVec> cov;
     WMatD<ET, SmemVec<ET, 63, STRIDE>> Wm;
     LonNetTm<NT, NHL, STRIDE, !TAU1L> lon;
-    SmemVec<double, 3, STRIDE> accv;        // sum r_col, sum r_lon, sum r_lon inside the score window
     {
-        double* pd = reinterpret_cast<double*>(tp);
-        accv.p = pd + lc; pd += 3 * STRIDE;
-        ET* pe = reinterpret_cast<ET*>(pd);
+        ET* pe = reinterpret_cast<ET*>(tp);
         cov.v.p = pe + lc; pe += 45 * STRIDE;
         Wm.v.p = pe + lc; pe += 63 * STRIDE;
         NT* pn = reinterpret_cast<NT*>(pe);
@@ -292,12 +293,13 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     for (int i = 0; i < 7; ++i) prev[i] = P.rls_x[i * ld + ec];
     prev[7] = P.rls_u[ec];
     prev[8] = P.rls_u[ld + ec];
-    // cold per-episode scalars stay out of the register file: the accumulators live in the tile, the trimmed
-    // controls (read-only) are re-read from L2 every tick, the PID / velocity-task integrators are read and written
-    // in place by the ticks that use them (PID collective: ticks < switch_step only)
-    accv[0] = P.acc[ec];
-    accv[1] = P.acc[ld + ec];
-    accv[2] = P.acc[2 * ld + ec];
+    // cold per-episode scalars stay out of the register file: the accumulators live in tensor memory (one load / store
+    // pair per tick), the trimmed controls (read-only) are re-read from L2 every tick, the PID / velocity-task
+    // integrators are read and written in place by the ticks that use them (PID collective: ticks < switch_step only)
+    {
+        const double a0[4] = {P.acc[ec], P.acc[ld + ec], P.acc[2 * ld + ec], 0.0};
+        tmem_store<double, 4>(tm_acc, 0, a0);
+    }
     t_ep = P.t[ec];
 #pragma unroll
     for (int i = 0; i < 9; ++i)
@@ -471,6 +473,19 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 col_update_tm<NT, NHC, UP, V2>(tm, Hcol, P.col.final_activation, n0, n1, (NT)0, dr, F, G);
             }
             // -------- bookkeeping and termination (main_3dof.py:189-197): frozen for terminated episodes --------
+            {   // accumulators: warp-collective round trip through tensor memory, the sums committed by live lanes only
+                __syncwarp();
+                tmem_wait_st();
+                double a[4];
+                tmem_load<double, 4>(tm_acc, 0, a);
+                if (!dead) {
+                    a[0] += r_col;
+                    a[1] += r_lon;
+                    if (k >= P.win_lo && k < P.win_hi) a[2] += r_lon;
+                }
+                __syncwarp();
+                tmem_store<double, 4>(tm_acc, 0, a);
+            }
             if (!dead) {
                 if (rec) {
                     row[10 * P.ld_traj] = (ET)r_col;
@@ -478,9 +493,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 }
                 t_ep = t_new;
                 if (P.task == H3_TASK_VELOCITY) P.corr_u[ec] = cu;
-                accv[0] += r_col;
-                accv[1] += r_lon;
-                if (k >= P.win_lo && k < P.win_hi) accv[2] += r_lon;
                 refth = nrefth;
                 step = k + 1;
                 heat_acc += heat_counts(heat);
@@ -499,6 +511,9 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
         //      of the launch every live episode ----
         const bool st = valid && (just_died || (finished && flags == 0));
         __syncwarp();
+        double accv[4];
+        tmem_wait_st();
+        tmem_load<double, 4>(tm_acc, 0, accv);
         {
             typedef ColTm<NHC> L;
 #pragma unroll 1
@@ -558,6 +573,9 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
         v[2] = (valid && (flags & H3_FLAG_DONE)) ? 1.0 : 0.0;
         v[3] = (valid && (flags & H3_FLAG_NAN)) ? 1.0 : 0.0;
         // (a terminated episode's accumulators are frozen: every update above is guarded by !dead)
+        double accv[4];
+        __syncwarp();
+        tmem_load<double, 4>(tm_acc, 0, accv);
         v[4] = valid ? accv[0] : 0.0;
         v[5] = valid ? accv[1] : 0.0;
         v[6] = valid ? accv[2] : 0.0;

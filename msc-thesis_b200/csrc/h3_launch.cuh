@@ -36,6 +36,9 @@ struct KernelSel {
 enum { VAR_FAST = 0, VAR_SWEEP = 1, VAR_GENERAL = 2 };
 
 constexpr size_t SMEM_PER_BLOCK_MAX = 232448;   // 227 KB opt-in limit per CTA on sm_100
+constexpr size_t SMEM_PER_SM = 233472;          // 228 KB per SM, 1 KB of it reserved per resident CTA
+// static shared memory of the fused kernels: the tanh table of h3_math.cuh (fp64 networks) + the epilogue's flag
+constexpr size_t SMEM_STATIC = ((sizeof(double) * H3_TANHT_N + 127) / 128) * 128 + 128;
 
 // On-chip placement per variant.  Phase-1 launches (COL == false) keep everything
 // but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM).  Launches with the collective agent
@@ -59,14 +62,16 @@ struct Tune {
     // the full cyclic agent (11 nh words) goes to the tile in collective-agent launches of the SWEEP / GENERAL
     // variants; phase-1 launches keep it in registers (7 instead of 4 warps per SM)
     static constexpr bool lon_smem = !TAU1L && (COL || !H3_SWEEP_P1_REGS);
-    static constexpr int MINB = 1;
+    static constexpr int MINB = COL ? 1 : 2;
     static constexpr int PLACE = (COL ? P_STASHC : 0) | (lon_smem ? (P_LON | P_STASHL) : 0);
     static constexpr int UL = lon_smem ? NHL / 2 : NHL;
     static constexpr int UC = COL ? NHC / 2 : NHC;
-    static constexpr int WARPS = COL ? 4 : 1;
+    // four warps per CTA, two CTAs per SM: the tanh table is staged once per CTA
+    static constexpr int WARPS = 4;
+    static constexpr int CTAS = COL ? 1 : 2;
     static constexpr int RD = COL ? H3_RD_P2 : H3_RD_P1;    // RLS stream look-ahead (groups)
     typedef LoopLayout<ET, NT, NHL, NHC, COL, SYM, HYP, TAU1L, PLACE, 32> L32;
-    static constexpr size_t room = (SMEM_PER_BLOCK_MAX / MINB - 1024 * (MINB - 1) - L32::head_bytes(WARPS)) / WARPS - 16;
+    static constexpr size_t room = ((COL ? SMEM_PER_BLOCK_MAX : SMEM_PER_SM / CTAS - 1024) - SMEM_STATIC - L32::head_bytes(WARPS)) / WARPS - 16;
     static constexpr int fit = (int)(room / L32::bytes_per_lane);
     static constexpr int LANES = fit >= 32 ? 32 : fit;
     static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");
@@ -115,7 +120,6 @@ static KernelSel<ET, NT> sel_flags(bool col, int variant) {
 #ifndef H3_TM_UP
 #define H3_TM_UP 5          // hidden units of the collective agent whose critic + target tanh chains are interleaved
 #endif
-constexpr size_t SMEM_PER_SM = 233472;          // 228 KB per SM, 1 KB of it reserved per resident CTA
 
 template <typename ET, typename NT, int NHL, int NHC, int VAR>
 struct TuneTm {
@@ -123,7 +127,7 @@ struct TuneTm {
     typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, 32, H3_TM_WARPS> L32;
     // eight warps per SM in one or two CTAs: the tile of a warp gets an eighth of what is left of the SM's shared memory
     static constexpr int CTAS = 8 / H3_TM_WARPS;
-    static constexpr size_t room = (SMEM_PER_SM / CTAS - 1024 - L32::head_bytes) / L32::WARPS - 16;
+    static constexpr size_t room = (SMEM_PER_SM / CTAS - 1024 - SMEM_STATIC - L32::head_bytes) / L32::WARPS - 16;
     static constexpr int fit = (int)(room / L32::bytes_per_col);       // columns incl. the idle lanes' dummy column
     static constexpr int LANES = fit >= 32 ? 32 : fit - 1;
     static_assert(LANES >= 8, "episode state does not fit the shared-memory tile");

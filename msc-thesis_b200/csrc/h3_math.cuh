@@ -11,12 +11,12 @@ namespace h3 {
 #define H3_DEV __device__ __forceinline__
 
 // fp64 tanh / sincos written for this kernel: every polynomial coefficient is a constant-bank operand of
-// its DFMA (tools/fit_math_coef.py derives them; <= 1.6 ulp end to end), where the inlined CUDA library
-// routine spends two UMOV issue slots per coefficient.  tanh has two straight-line branches:
-//   |x| <  0.55 : x + x z P(z), z = x^2                      (hidden pre-activations of the cyclic agent)
-//   otherwise   : E / (E + 2), E = expm1(2x)                 (collective agent: inputs in m and m/s)
+// its DFMA (tools/fit_math_coef.py derives them), where the inlined CUDA library routine spends two UMOV issue
+// slots per coefficient.  tanh has two straight-line branches:
+//   |x| <  0.55 : x + x z P(z), z = x^2                      (hidden pre-activations of the cyclic agent; 14 DFMA-pipe ops)
+//   otherwise   : table-driven, every x (tanh_tab, 17 ops)   (collective agent: inputs in m and m/s)
 // and the branch is taken once per CHUNK of hidden units (tanh_vec), so each side is straight-line code in
-// which the compiler interleaves the independent polynomial chains.
+// which the compiler interleaves the independent chains.
 // sin/cos use one polynomial pair on |x| <= pi/4 (flight angles) and the library, out of line, beyond.
 static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { ::sincos(x, s, c); }
 
@@ -36,30 +36,43 @@ H3_DEV double tanh_small(double x) {
     return fma(x * z, p, x);
 }
 
-// tanh(x) = E / (E + 2), E = expm1(2x) = 2^n expm1(r) + (2^n - 1), 2x = n ln2 + r: one straight-line formula
-// without cancellation for every x (2.4 ulp), used whenever a chunk holds an argument >= 0.55.
-H3_DEV double tanh_any(double x) {
-    const double xc = x > 20.0 ? 20.0 : (x < -20.0 ? -20.0 : x);    // |tanh| == 1 to the last bit beyond 19.1; NaN passes
-    const double y = xc + xc;
-    // n = rint(y / ln2) by the 1.5 * 2^52 trick: the integer lands in the low word of t
-    const double t = fma(y, H3_LN2[2], 6755399441055744.0);
-    const double nf = t - 6755399441055744.0;
-    double r = fma(nf, -H3_LN2[0], y);
-    r = fma(nf, -H3_LN2[1], r);                             // |r| <= ln2 / 2
-    double q = H3_EXP_C[10];
-#pragma unroll
-    for (int i = 9; i >= 0; --i) q = fma(q, r, H3_EXP_C[i]);
-    const double p = fma(r * r, q, r);                      // expm1(r)
-    const int n = __double2loint(t);                        // in [-58, 58]; NaN: E is NaN whatever n is
-    const double sc = __hiloint2double((n + 1023) << 20, 0);
-    const double E = fma(sc, p, sc - 1.0);
-    const double den = E + 2.0;                             // in [1, 2^58]: no special cases in the division
-    double rc = rcp_seed(den);
-    rc = fma(rc, fma(-den, rc, 1.0), rc);
-    rc = fma(rc, fma(-den, rc, 1.0), rc);
-    const double q0 = E * rc;
-    return fma(fma(-q0, den, E), rc, q0);
+// Full-range tanh from a 313-entry table in shared memory (2.5 KB per CTA, staged by tanh_table_stage()):
+//   x0 = floor(16 |x|) / 16, d = |x| - x0 in [0, 1/16]      (exact: DFMA.RM with the 1.5 * 2^52 constant, one DFMA)
+//   tanh(x0 + d) = t0 + (1 - t0^2) p / (1 + t0 p),  t0 = tanh(x0) (table),  p = tanh(d) = d + d z Q(z), z = d^2
+// Every term is non-negative, so nothing cancels: 1.4 ulp measured (tests/test_gpu_math.py), against 2.4 ulp and 29
+// FP64-pipe instructions of the expm1-based formula E / (E + 2) this replaces.  The division is one MUFU.RCP64H seed
+// (relative error e0 < 2^-19) and one third-order step rc (1 + e0 + e0^2): the quotient only scales the correction
+// term.  Beyond 19.5 the result is 1 to the last bit (t0 = 1, 1 - t0^2 = 0); NaN comes out as NaN (the table index is
+// clamped, d is NaN).  32 lanes with unrelated arguments gather 32 different words: a few bank conflicts per call on
+// the LSU, which these kernels leave mostly idle.
+#define H3_TANHT_MAGIC 6755399441055744.0
+__shared__ double h3_tanht[H3_TANHT_N];
+
+// every thread of the CTA; contains __syncthreads()
+H3_DEV void tanh_table_stage() {
+    for (int i = threadIdx.x; i < H3_TANHT_N; i += blockDim.x) h3_tanht[i] = H3_TANHT_G[i];
+    __syncthreads();
 }
+
+H3_DEV double tanh_tab(double x) {
+    const double ax = ::fabs(x);
+    const double xc = ax > H3_TANHT_XMAX ? H3_TANHT_XMAX : ax;          // NaN passes
+    const double t = __fma_rd(xc, 16.0, H3_TANHT_MAGIC);                // floor(16 xc) in the low word of t
+    const double d = fma(t - H3_TANHT_MAGIC, -0.0625, xc);
+    const unsigned k = min((unsigned)__double2loint(t), (unsigned)(H3_TANHT_N - 1));
+    const double t0 = h3_tanht[k];
+    const double z = d * d;
+    const double q = fma(fma(fma(H3_TANHT_C[3], z, H3_TANHT_C[2]), z, H3_TANHT_C[1]), z, H3_TANHT_C[0]);
+    const double p = fma(d * z, q, d);
+    const double S = fma(-t0, t0, 1.0);
+    const double den = fma(t0, p, 1.0);                                 // in [1, 1.0625]
+    double rc = rcp_seed(den);
+    const double e0 = fma(-den, rc, 1.0);
+    rc = fma(rc, fma(e0, e0, e0), rc);
+    return ::copysign(fma(p * S, rc, t0), x);
+}
+
+H3_DEV double tanh_any(double x) { return tanh_tab(x); }
 
 H3_DEV double tanh_f64(double x) {
     if (::fabs(x) < 0.55) return tanh_small(x);             // NaN compares false -> tanh_any -> NaN
@@ -111,44 +124,41 @@ H3_DEV void sincos_f64(double x, double* s, double* c) {
 #define H3_TANH_G 5
 #endif
 
-// tanh_any on elements [G0, min(G0 + H3_TANH_G, U)) of x, interleaved, then the next group
+// tanh_tab on elements [G0, min(G0 + H3_TANH_G, U)) of x, stage by stage so that the chains interleave, then the
+// next group
 template <int G0, int U>
 H3_DEV void tanh_any_group(const double (&x)[U], double (&y)[U]) {
     constexpr int G = (U - G0) < H3_TANH_G ? (U - G0) : H3_TANH_G;
     if constexpr (G > 0) {
-        double r[G], q[G], t[G];
+        double d[G], t0[G], q[G], z[G];
 #pragma unroll
         for (int u = 0; u < G; ++u) {
-            const double xu = x[G0 + u];
-            const double xc = xu > 20.0 ? 20.0 : (xu < -20.0 ? -20.0 : xu);
-            const double yy = xc + xc;
-            t[u] = fma(yy, H3_LN2[2], 6755399441055744.0);
-            const double nf = t[u] - 6755399441055744.0;
-            r[u] = fma(nf, -H3_LN2[1], fma(nf, -H3_LN2[0], yy));
-            q[u] = H3_EXP_C[10];
+            const double ax = ::fabs(x[G0 + u]);
+            const double xc = ax > H3_TANHT_XMAX ? H3_TANHT_XMAX : ax;
+            const double t = __fma_rd(xc, 16.0, H3_TANHT_MAGIC);
+            d[u] = fma(t - H3_TANHT_MAGIC, -0.0625, xc);
+            t0[u] = h3_tanht[min((unsigned)__double2loint(t), (unsigned)(H3_TANHT_N - 1))];
+            z[u] = d[u] * d[u];
+            q[u] = H3_TANHT_C[3];
         }
 #pragma unroll
-        for (int i = 9; i >= 0; --i)
+        for (int i = 2; i >= 0; --i)
 #pragma unroll
-            for (int u = 0; u < G; ++u) q[u] = fma(q[u], r[u], H3_EXP_C[i]);
-        double E[G], den[G], rc[G];
+            for (int u = 0; u < G; ++u) q[u] = fma(q[u], z[u], H3_TANHT_C[i]);
+        double p[G], den[G], rc[G], e0[G];
 #pragma unroll
         for (int u = 0; u < G; ++u) {
-            const double p = fma(r[u] * r[u], q[u], r[u]);
-            const double sc = __hiloint2double((__double2loint(t[u]) + 1023) << 20, 0);
-            E[u] = fma(sc, p, sc - 1.0);
-            den[u] = E[u] + 2.0;
+            p[u] = fma(d[u] * z[u], q[u], d[u]);
+            den[u] = fma(t0[u], p[u], 1.0);
             rc[u] = rcp_seed(den[u]);
         }
 #pragma unroll
-        for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+        for (int u = 0; u < G; ++u) e0[u] = fma(-den[u], rc[u], 1.0);
 #pragma unroll
-        for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(-den[u], rc[u], 1.0), rc[u]);
+        for (int u = 0; u < G; ++u) rc[u] = fma(rc[u], fma(e0[u], e0[u], e0[u]), rc[u]);
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const double q0 = E[u] * rc[u];
-            y[G0 + u] = fma(fma(-q0, den[u], E[u]), rc[u], q0);
-        }
+        for (int u = 0; u < G; ++u)
+            y[G0 + u] = ::copysign(fma(p[u] * fma(-t0[u], t0[u], 1.0), rc[u], t0[u]), x[G0 + u]);
         tanh_any_group<G0 + G, U>(x, y);
     }
 }
@@ -158,6 +168,8 @@ struct Math;
 
 template <>
 struct Math<double> {
+    // once per kernel, by every thread, before the first tanh: stages the table of tanh_tab (contains __syncthreads())
+    static H3_DEV void prepare() { tanh_table_stage(); }
     static H3_DEV double tanh_(double x) { return tanh_f64(x); }
     static H3_DEV double tanh_wide_(double x) { return tanh_any(x); }
     // U independent arguments at once; the polynomial loops run coefficient-major so that consecutive DFMAs
@@ -230,6 +242,7 @@ struct Math<double> {
 
 template <>
 struct Math<float> {
+    static H3_DEV void prepare() {}
     static H3_DEV float tanh_(float x) { return ::tanhf(x); }
     static H3_DEV float tanh_wide_(float x) { return ::tanhf(x); }
     template <int U>

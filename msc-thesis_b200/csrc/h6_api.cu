@@ -185,6 +185,7 @@ H3_DEV void agent_step_update(const H3AgentHyper& h, NetT& net, double lr_a, dou
 
 template <bool SYM, bool TILED>
 __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __grid_constant__ LoopParams P) {
+    Math<double>::prepare();                                            // tanh table of the agents' hidden layers (h3_math.cuh)
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x, ld = b.ld;

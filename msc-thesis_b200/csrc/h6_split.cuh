@@ -213,6 +213,7 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk, do
 //   ST: storage type of the tiled W / covariance (H6Batch.rls_f32: float; the arithmetic is fp64 either way).
 template <bool TILED, typename ST = double>
 __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ LoopParams P, int final) {
+    Math<double>::prepare();                                // tanh table of the agents' hidden layers (h3_math.cuh)
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ 
 // One tick of PIDs, reference generator, actions and the RK4 model step for every live episode.
 template <bool TILED>
 __global__ void __launch_bounds__(128, H6_SIM_MINB) sim_kernel(const __grid_constant__ LoopParams P, int it) {
+    Math<double>::prepare();
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
     if (e >= b.n) return;
@@ -526,6 +528,7 @@ template <bool SYM, bool TILED>
 __global__ void __launch_bounds__(MIX_BLOCK, H6_SIM_MINB) mixed_kernel(const __grid_constant__ LoopParams PS, int it_s, int mode_s,
                                                                        int64_t n_s, H6Batch bl, double gamma, int64_t n_l) {
     __shared__ double smem[30 * MIX_BLOCK];                 // RK4 arrays (role S) / X, cov.X rows (role L)
+    Math<double>::prepare();
     const int64_t q = blockIdx.x / 5;
     const int r5 = blockIdx.x % 5;
     if (r5 != 0) {                                          // role L: 4 of every 5 blocks

@@ -123,6 +123,15 @@ def main():
     t = np.ldexp(1.0 + (r + (r * r) * horner(ce, r)), nf.astype(np.int64))
     yt = (1.0 - t) / (1.0 + t)
     print("tanh large branch (emulated in double, true division): %.2f ulp" % ulp_err(yt, mp.tanh, xs))
+    # table-driven full-range tanh (h3_math.cuh: tanh_tab): x0 = floor(16 |x|) / 16, d = |x| - x0 in [0, 1/16],
+    # tanh(x0 + d) = t0 + (1 - t0^2) p / (1 + t0 p), t0 = tanh(x0) from a table, p = tanh(d) = d + d z Q(z)
+    tab_h, tab_xmax = mp.mpf(1) / 16, mp.mpf("19.5")
+    cq = [float(c) for c in cheb_fit(f_tanh, mp.mpf(0), tab_h ** 2, 3)]
+    xs = rng.uniform(0.0, float(tab_h), 5000)
+    z = xs * xs
+    spec.append(("H3_TANHT_C", cq, ulp_err(xs + xs * (z * horner(cq, z)), mp.tanh, xs)))
+    tab = [float(mp.tanh(k * tab_h)) for k in range(int(tab_xmax / tab_h) + 1)]
+    assert tab[-1] == 1.0 and tab[0] == 0.0
     lines = ["// GENERATED by tools/fit_math_coef.py -- do not edit.  Coefficients (lowest order first) of the reduced",
              "// functions  tanh(x) = x + x z P(z),  sin(x) = x + x z S(z),  cos(x) = 1 - z/2 + z^2 C(z),  z = x^2,",
              "// valid for |x| < 0.55 (tanh) and |x| <= pi/4 (sin, cos).  Hex = IEEE-754 bits of the double.",
@@ -136,6 +145,14 @@ def main():
         lines.append("};")
         lines.append("")
         print(name, "degree", len(coef) - 1, "max err %.2f ulp" % err)
+    lines.append("// tanh(k / 16), k = 0 .. %d, correctly rounded (mpmath, 60 digits); staged into shared memory by the kernels" % (len(tab) - 1))
+    lines.append("#define H3_TANHT_N %d" % len(tab))
+    lines.append("#define H3_TANHT_XMAX %s" % repr(float(tab_xmax)))
+    lines.append("static __device__ const double H3_TANHT_G[H3_TANHT_N] = {")
+    for i in range(0, len(tab), 4):
+        lines.append("    " + " ".join("%s," % float(t).hex() for t in tab[i:i + 4]))
+    lines.append("};")
+    lines.append("")
     with open(OUT, "w") as f:
         f.write("\n".join(lines))
     print("wrote", OUT)
