@@ -386,15 +386,16 @@ class ClosedLoop3DOF:
         return n_alive
 
     def sort_key(self):
-        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branches in the
-        next launch: the number of ticks of the last launch in which the episode left the short tanh branch (cyclic
-        agent) or the short sin / cos branch (H3Batch.heat) -- the reference signal is periodic, so an episode's duty
-        cycle on the slow branches is what persists from launch to launch --, with the current pitch-loop agitation
-        |theta - theta_ref| + 0.1 |q| as the tie-break (and as the whole key before the first launch has counted)."""
+        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branch in the
+        next launch: the number of ticks of the last launch in which the episode left the short sin / cos branch
+        (H3Batch.heat; tanh has had no branch since the table-driven formula) -- the reference signal is periodic, so an
+        episode's duty cycle on the slow branch is what persists from launch to launch --, with the current pitch-loop
+        agitation |theta - theta_ref| + 0.1 |q| as the tie-break (and as the whole key before the first launch has
+        counted): agitated episodes are also the ones that terminate next, so the sort keeps the dying lanes together."""
         st = self.env.state
         agitation = (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
         h = self.heat
-        counts = ((h & 1023) + 2 * ((h >> 20) & 1023)).double()
+        counts = ((h >> 20) & 1023).double()
         return counts + agitation / (1.0 + agitation)
 
     def original_order(self, t):

@@ -432,8 +432,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     const NT s0 = (NT)state[h.ac_state * ld + e];
     const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
     NT hh[NH], f;
-    out[e] = actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f, 0xffffffffu, nullptr, 0,
-                                      h.channel == 0);
+    out[e] = actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f);
 }
 
 template <typename ET, typename NT, int NH>
@@ -465,10 +464,9 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     }
     NT hh[NH], scr[NH], f;
     // chunks of 2 hidden units: weights are addressed in global memory, activations in local arrays
-    const bool wide = h.channel == 0;           // the collective agent's hidden layers: full-range tanh (h3_math.cuh)
-    (void)actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f, 0xffffffffu, nullptr, 0, wide);
+    (void)actor_forward<NT, NH, 2>(N, s0, s1, H.scale, h.final_activation, hh, f);
     agent_update<NT, NH, 2, false>(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, hh, f,
-                                   scr, 0xffffffffu, nullptr, 0, wide);
+                                   scr);
 }
 
 // get_reward (agents.py:123-128) and get_transition_matrices (agents.py:130-140)
@@ -515,7 +513,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
     const NT s0 = (NT)state[h.ac_state * ld + e];
     const NT s1 = (NT)(state[h.tracked_state * ld + e] - ref[ri * ld + e]);
     NT f;
-    out[e] = actor_forward_rt(N, s0, s1, H.scale, h.final_activation, f, h.channel == 0);
+    out[e] = actor_forward_rt(N, s0, s1, H.scale, h.final_activation, f);
 }
 
 template <typename ET, typename NT>
@@ -543,7 +541,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK)
         for (int j = 0; j < 2; ++j) F[i][j] = Fm[(i * 2 + j) * ld + e];
         G[i] = Gm[i * ld + e];
     }
-    agent_update_rt(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G, h.channel == 0);
+    agent_update_rt(N, H, h.final_activation, s0, s1, n0, n1, dr_ds[e], dr_ds[ld + e], F, G);
 }
 
 struct AgentArgs {

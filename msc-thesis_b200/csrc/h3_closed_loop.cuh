@@ -22,10 +22,10 @@ namespace h3 {
 // PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
-// H3Batch.heat: per slow data-dependent branch, in how many ticks of the launch the episode took it (three 10-bit
-// counters: bits 0-9 cyclic agent's tanh beyond the polynomial range, 10-19 collective agent's, 20-29 sin / cos beyond pi/4)
-enum { H3_HEAT_LON = 1, H3_HEAT_COL = 2, H3_HEAT_TRIG = 4 };
-H3_DEV int heat_counts(int bits) { return (bits & 1) + ((bits & 2) << 9) + ((bits & 4) << 18); }
+// H3Batch.heat: in how many ticks of the launch the episode took the one data-dependent slow branch that is left, sin / cos
+// beyond pi/4 (a 10-bit counter at bits 20-29; bits 0-19 counted the tanh branches, which no longer exist)
+enum { H3_HEAT_TRIG = 4 };
+H3_DEV int heat_counts(int bits) { return (bits & 4) << 18; }
 
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
@@ -86,8 +86,6 @@ H3_DEV void transition_matrices(WAcc& Wm, const H3AgentHyper& h, NT (&F)[2][2], 
     }
 }
 
-template <typename T, typename Vec>
-struct WMatD : WMat<T, Vec> {};     // shared-memory flavour (runtime-indexed reads are plain address arithmetic)
 
 template <int NWARP>
 H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [NWARP][H3_N_STATS] */) {
@@ -108,6 +106,9 @@ H3_DEV void block_reduce_stats(double (&v)[H3_N_STATS], double* sh /* [NWARP][H3
         }
     }
 }
+
+template <typename T, typename Vec>
+struct WMatD : WMat<T, Vec> {};     // shared-memory flavour (runtime-indexed reads are plain address arithmetic)
 
 // view of a group starting at element `off`
 template <typename Vec, typename T>
@@ -281,7 +282,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             __syncwarp();
         }
         for (int jj = 0; jj < cn; ++jj) {
-            constexpr unsigned amask = 0xffffffffu;
             if (flags != 0) continue;       // terminated (or idle) lane: frozen
             heat = 0;
             const int k = lockstep ? (P.step0 + c0 + jj) : step;
@@ -303,8 +303,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 NT fl;
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
-                const NT a_lon = actor_forward<NT, NHL, UL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, stl, fl,
-                                                            amask, &heat, H3_HEAT_LON);
+                const NT a_lon = actor_forward<NT, NHL, UL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, stl, fl);
                 cyc = misce[3] + (ET)a_lon;
                 stl[NHL] = fl;
                 stl[NHL + 1] = sl0;
@@ -314,8 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 NT fc;
                 const NT sc0 = (NT)pick7(s, P.col.ac_state);
                 const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
-                const NT a_col = actor_forward<NT, NHC, UC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, stc, fc,
-                                                            amask, &heat, H3_HEAT_COL, true);
+                const NT a_col = actor_forward<NT, NHC, UC>(col, sc0, sc1, Hcol.scale, P.col.final_activation, stc, fc);
                 colv = misce[2] + (ET)a_col;
                 stc[NHC] = fc;
                 stc[NHC + 1] = sc0;
@@ -406,7 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
                 agent_update<NT, NHL, UL, TAU1L>(lon, Hlon, P.lon.final_activation, stl[NHL + 1], stl[NHL + 2], n0, n1,
-                                                 (NT)0, dr, F, G, stl, stl[NHL], scr, amask, &heat, H3_HEAT_LON);
+                                                 (NT)0, dr, F, G, stl, stl[NHL], scr);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -419,7 +417,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
                 const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
                 SubVec<decltype(stc), NT> scr{stc, NHC + 3};
                 agent_update<NT, NHC, UC, false>(col, Hcol, P.col.final_activation, stc[NHC + 1], stc[NHC + 2], n0, n1,
-                                                 (NT)0, dr, F, G, stc, stc[NHC], scr, amask, &heat, H3_HEAT_COL, true);
+                                                 (NT)0, dr, F, G, stc, stc[NHC], scr);
             }
             if (rec) {
                 row[10 * P.ld_traj] = (ET)r_col;

@@ -33,16 +33,16 @@ struct RtNet {              // rows of the `[11*nh][ld]` network block (include/
 };
 
 template <typename NT>
-H3_DEV NT tanh_rt(NT x, bool wide) {        // hidden-layer tanh: full-range formula for the collective agent (wide)
-    return wide ? Math<NT>::tanh_wide_(x) : Math<NT>::tanh_(x);
+H3_DEV NT tanh_rt(NT x) {
+    return Math<NT>::tanh_(x);
 }
 
 // DHPActor.forward (agents.py:59-63)
 template <typename NT>
-H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& f, bool wide) {
+H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& f) {
     typedef Math<NT> M;
     NT y = (NT)0;
-    for (int k = 0; k < net.nh; ++k) y += net.a2(k) * tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1, wide);
+    for (int k = 0; k < net.nh; ++k) y += net.a2(k) * tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
     f = (act == H3_ACT_TANH) ? M::tanh_(y) : M::sigmoid_(y);
     return scale * f;
 }
@@ -52,19 +52,19 @@ H3_DEV NT actor_forward_rt(RtNet<NT>& net, NT s0, NT s1, NT scale, int act, NT& 
 // unit's rows are written only after they were read).
 template <typename NT>
 H3_DEV void agent_update_rt(RtNet<NT>& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
-                            const NT (&F)[2][2], const NT (&G)[2], bool wide) {
+                            const NT (&F)[2][2], const NT (&G)[2]) {
     NT f;
-    (void)actor_forward_rt(net, s0, s1, H.scale, act, f, wide);
+    (void)actor_forward_rt(net, s0, s1, H.scale, act, f);
     const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);
     NT lam1[2] = {(NT)0, (NT)0}, lam2[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
     for (int k = 0; k < net.nh; ++k) {
-        const NT hc = tanh_rt(net.c1(k, 0) * s0 + net.c1(k, 1) * s1, wide);
-        const NT ht = tanh_rt(net.t1(k, 0) * n0 + net.t1(k, 1) * n1, wide);
+        const NT hc = tanh_rt(net.c1(k, 0) * s0 + net.c1(k, 1) * s1);
+        const NT ht = tanh_rt(net.t1(k, 0) * n0 + net.t1(k, 1) * n1);
         lam1[0] += net.c2(0, k) * hc;
         lam1[1] += net.c2(1, k) * hc;
         lam2[0] += net.t2(0, k) * ht;
         lam2[1] += net.t2(1, k) * ht;
-        const NT ha = tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1, wide);
+        const NT ha = tanh_rt(net.a1(k, 0) * s0 + net.a1(k, 1) * s1);
         const NT pk = delta * net.a2(k) * ((NT)1 - ha * ha);
         da_ds[0] += net.a1(k, 0) * pk;
         da_ds[1] += net.a1(k, 1) * pk;
@@ -77,20 +77,22 @@ H3_DEV void agent_update_rt(RtNet<NT>& net, const AgentH<NT>& H, int act, NT s0,
         e_c[j] = lam1[j] - (tg0 * (F[0][j] + G[0] * da_ds[j]) + tg1 * (F[1][j] + G[1] * da_ds[j]));
     const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
     const NT one_m_tau = (NT)1 - H.tau;
+    const NT ka_s0 = ka * s0, ka_s1 = ka * s1, ka_d = ka * delta;       // as in agent_update (h3_tick.cuh)
+    const NT lc_s0 = H.lr_c * s0, lc_s1 = H.lr_c * s1, lc_e0 = H.lr_c * e_c[0], lc_e1 = H.lr_c * e_c[1];
     for (int k = 0; k < net.nh; ++k) {
         const NT a10 = net.a1(k, 0), a11 = net.a1(k, 1), a2k = net.a2(k);
         const NT c10 = net.c1(k, 0), c11 = net.c1(k, 1), c20 = net.c2(0, k), c21 = net.c2(1, k);
-        const NT ha = tanh_rt(a10 * s0 + a11 * s1, wide);
-        const NT hc = tanh_rt(c10 * s0 + c11 * s1, wide);
+        const NT ha = tanh_rt(a10 * s0 + a11 * s1);
+        const NT hc = tanh_rt(c10 * s0 + c11 * s1);
         const NT pk = delta * a2k * ((NT)1 - ha * ha);
         const NT back = (c20 * e_c[0] + c21 * e_c[1]) * ((NT)1 - hc * hc);
-        net.a1(k, 0) = a10 + ka * (pk * s0);
-        net.a1(k, 1) = a11 + ka * (pk * s1);
-        net.a2(k) = a2k + ka * (delta * ha);
-        const NT n10 = c10 - H.lr_c * (back * s0);
-        const NT n11 = c11 - H.lr_c * (back * s1);
-        const NT n20 = c20 - H.lr_c * (e_c[0] * hc);
-        const NT n21 = c21 - H.lr_c * (e_c[1] * hc);
+        net.a1(k, 0) = a10 + ka_s0 * pk;
+        net.a1(k, 1) = a11 + ka_s1 * pk;
+        net.a2(k) = a2k + ka_d * ha;
+        const NT n10 = c10 - lc_s0 * back;
+        const NT n11 = c11 - lc_s1 * back;
+        const NT n20 = c20 - lc_e0 * hc;
+        const NT n21 = c21 - lc_e1 * hc;
         net.c1(k, 0) = n10;
         net.c1(k, 1) = n11;
         net.c2(0, k) = n20;
@@ -154,11 +156,11 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
         const NT sl0 = (NT)pick7(s, P.lon.ac_state);
         const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
         NT fdummy;
-        ET cyc = trim1 + (ET)actor_forward_rt(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, fdummy, false);
+        ET cyc = trim1 + (ET)actor_forward_rt(lon, sl0, sl1, Hlon.scale, P.lon.final_activation, fdummy);
         const NT sc0 = (NT)pick7(s, P.col.ac_state);
         const NT sc1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth);
         ET colv = (ET)0;
-        if (phase2) colv = trim0 + (ET)actor_forward_rt(col, sc0, sc1, Hcol.scale, P.col.final_activation, fdummy, true);
+        if (phase2) colv = trim0 + (ET)actor_forward_rt(col, sc0, sc1, Hcol.scale, P.col.final_activation, fdummy);
         ET exc0 = (ET)0, exc1 = (ET)0;                                          // main_3dof.py:139-140
         if (P.excitation != nullptr && k < P.exc_len) {
             exc0 = (ET)P.excitation[2 * k];
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
             transition_matrices<ET, NT>(Wm, P.lon, F, G);
             const NT n0 = (NT)pick7(s, P.lon.ac_state);
             const NT n1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - nrefth);
-            agent_update_rt(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr, F, G, false);
+            agent_update_rt(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr, F, G);
         }
         if (phase2) {
             const ET e_tr = P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - refth;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
             transition_matrices<ET, NT>(Wm, P.col, F, G);
             const NT n0 = (NT)pick7(s, P.col.ac_state);
             const NT n1 = (NT)(P.col.tracked_state == 1 ? s[1] : pick7(s, P.col.tracked_state) - nrefth);
-            agent_update_rt(col, Hcol, P.col.final_activation, sc0, sc1, n0, n1, (NT)0, dr, F, G, true);
+            agent_update_rt(col, Hcol, P.col.final_activation, sc0, sc1, n0, n1, (NT)0, dr, F, G);
         }
         if (rec) {
             row[10 * P.ld_traj] = (ET)r_col;

@@ -70,7 +70,7 @@ H3_DEV NT col_forward_tm(uint32_t tm, NT s0, NT s1, NT scale, int act) {
         NT pre[UF], hk[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) pre[u] = b[u][0] * s0 + b[u][1] * s1;
-        (void)M::template tanh_vec<UF>(pre, hk, true);
+        M::template tanh_vec<UF>(pre, hk);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
@@ -117,7 +117,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
         NT pre[UP], ht[UP];
 #pragma unroll
         for (int u = 0; u < UP; ++u) pre[u] = b[u][0] * n0 + b[u][1] * n1;
-        (void)M::template tanh_vec<UP>(pre, ht, true);
+        M::template tanh_vec<UP>(pre, ht);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
@@ -129,6 +129,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
     const NT tg0 = dr0 + H.gamma * lam2[0];
     const NT tg1 = dr + H.gamma * lam2[1];
     const NT ka = H.lr_a * (tg0 * G[0] + tg1 * G[1]);
+    const NT ka_s0 = ka * s0, ka_s1 = ka * s1, ka_d = ka * delta;       // as in agent_update (h3_tick.cuh)
     // ---- pass A ----
     NT lam1[2] = {(NT)0, (NT)0}, da_ds[2] = {(NT)0, (NT)0};
 #pragma unroll 1
@@ -142,7 +143,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
 #pragma unroll
             for (int u = 0; u < UP; ++u) pre[u] = c1[u][0] * s0 + c1[u][1] * s1;
         }
-        (void)M::template tanh_vec<UP>(pre, hc, true);
+        M::template tanh_vec<UP>(pre, hc);
         __syncwarp();
         TmemBuf<NT, 6> b[UP];               // c2(0,k) c2(1,k) a1(k,0) a1(k,1) a2(k) h_a(k)
 #pragma unroll
@@ -156,7 +157,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
             const NT pk = delta * a2k * ((NT)1 - ha * ha);
             da_ds[0] += b[u][2] * pk;
             da_ds[1] += b[u][3] * pk;
-            const NT o[4] = {b[u][2] + ka * (pk * s0), b[u][3] + ka * (pk * s1), a2k + ka * (delta * ha), hc[u]};
+            const NT o[4] = {b[u][2] + ka_s0 * pk, b[u][3] + ka_s1 * pk, a2k + ka_d * ha, hc[u]};
             tmem_store<NT, 4>(tm, L::UNIT * (k0 + u) + L::A10, o);
         }
     }
@@ -166,6 +167,7 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
     for (int j = 0; j < 2; ++j)
         e_c[j] = lam1[j] - (tg0 * (F[0][j] + G[0] * da_ds[j]) + tg1 * (F[1][j] + G[1] * da_ds[j]));
     const NT one_m_tau = (NT)1 - H.tau;
+    const NT lc_s0 = H.lr_c * s0, lc_s1 = H.lr_c * s1, lc_e0 = H.lr_c * e_c[0], lc_e1 = H.lr_c * e_c[1];
     tmem_wait_st();                                     // pass A stored the critic's hidden activations
     // ---- pass C ----
 #pragma unroll 1
@@ -182,10 +184,10 @@ H3_DEV void col_update_tm(uint32_t tm, const AgentH<NT>& H, int act, NT n0, NT n
         for (int u = 0; u < V2; ++u) {
             const NT hc = h[u][0], c20 = b[u][6], c21 = b[u][7];
             const NT back = (c20 * e_c[0] + c21 * e_c[1]) * ((NT)1 - hc * hc);
-            const NT n10 = b[u][4] - H.lr_c * (back * s0);
-            const NT n11 = b[u][5] - H.lr_c * (back * s1);
-            const NT n20 = c20 - H.lr_c * (e_c[0] * hc);
-            const NT n21 = c21 - H.lr_c * (e_c[1] * hc);
+            const NT n10 = b[u][4] - lc_s0 * back;
+            const NT n11 = b[u][5] - lc_s1 * back;
+            const NT n20 = c20 - lc_e0 * hc;
+            const NT n21 = c21 - lc_e1 * hc;
             const NT o[8] = {H.tau * n10 + one_m_tau * b[u][0], H.tau * n11 + one_m_tau * b[u][1],
                              H.tau * n20 + one_m_tau * b[u][2], H.tau * n21 + one_m_tau * b[u][3], n10, n11, n20, n21};
             tmem_store<NT, 8>(tm, L::UNIT * (k0 + u) + L::T10, o);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl0 = (NT)pick7(s, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? s[1] : pick7(s, P.lon.tracked_state) - refth);
                 const NT a_lon = actor_forward<NT, NHL, NHL>(lon, sl0, sl1, Hlon.scale, P.lon.final_activation,
-                                                                    stl, fl, FULL, &heat, H3_HEAT_LON);
+                                                                    stl, fl);
                 cyc = trim1 + (ET)a_lon;
                 stl[NHL] = fl;
             }
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? prev[1] : pick7(prev, P.lon.tracked_state) - refth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
                 agent_update<NT, NHL, NHL, TAU1L>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
-                                                         F, G, stl, stl[NHL], scr, FULL, &heat, H3_HEAT_LON);
+                                                         F, G, stl, stl[NHL], scr);
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {

@@ -12,11 +12,8 @@ namespace h3 {
 
 // fp64 tanh / sincos written for this kernel: every polynomial coefficient is a constant-bank operand of
 // its DFMA (tools/fit_math_coef.py derives them), where the inlined CUDA library routine spends two UMOV issue
-// slots per coefficient.  tanh has two straight-line branches:
-//   |x| <  0.55 : x + x z P(z), z = x^2                      (hidden pre-activations of the cyclic agent; 14 DFMA-pipe ops)
-//   otherwise   : table-driven, every x (tanh_tab, 17 ops)   (collective agent: inputs in m and m/s)
-// and the branch is taken once per CHUNK of hidden units (tanh_vec), so each side is straight-line code in
-// which the compiler interleaves the independent chains.
+// slots per coefficient.  tanh is ONE straight-line, table-driven formula for every argument (tanh_tab below): no
+// data-dependent branch, so episodes whose pre-activations are small and episodes that saturate share a warp for free.
 // sin/cos use one polynomial pair on |x| <= pi/4 (flight angles) and the library, out of line, beyond.
 static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { ::sincos(x, s, c); }
 
@@ -28,19 +25,13 @@ H3_DEV double rcp_seed(double a) {
     return r;
 }
 
-H3_DEV double tanh_small(double x) {
-    const double z = x * x;
-    double p = H3_TANH_C[11];
-#pragma unroll
-    for (int i = 10; i >= 0; --i) p = fma(p, z, H3_TANH_C[i]);
-    return fma(x * z, p, x);
-}
-
 // Full-range tanh from a 313-entry table in shared memory (2.5 KB per CTA, staged by tanh_table_stage()):
 //   x0 = floor(16 |x|) / 16, d = |x| - x0 in [0, 1/16]      (exact: DFMA.RM with the 1.5 * 2^52 constant, one DFMA)
 //   tanh(x0 + d) = t0 + (1 - t0^2) p / (1 + t0 p),  t0 = tanh(x0) (table),  p = tanh(d) = d + d z Q(z), z = d^2
-// Every term is non-negative, so nothing cancels: 1.4 ulp measured (tests/test_gpu_math.py), against 2.4 ulp and 29
-// FP64-pipe instructions of the expm1-based formula E / (E + 2) this replaces.  The division is one MUFU.RCP64H seed
+// Every term is non-negative, so nothing cancels: 1.4 ulp measured (tests/test_gpu_math.py); 17 FP64-pipe instructions.
+// (Round 2 started with two branches -- an 11th-degree polynomial below 0.55, 14 instructions, and the expm1-based
+// E / (E + 2) beyond, 29 instructions, chosen per chunk of hidden units: warps whose lanes disagreed paid for both.)
+// The division is one MUFU.RCP64H seed
 // (relative error e0 < 2^-19) and one third-order step rc (1 + e0 + e0^2): the quotient only scales the correction
 // term.  Beyond 19.5 the result is 1 to the last bit (t0 = 1, 1 - t0^2 = 0); NaN comes out as NaN (the table index is
 // clamped, d is NaN).  32 lanes with unrelated arguments gather 32 different words: a few bank conflicts per call on
@@ -70,13 +61,6 @@ H3_DEV double tanh_tab(double x) {
     const double e0 = fma(-den, rc, 1.0);
     rc = fma(rc, fma(e0, e0, e0), rc);
     return ::copysign(fma(p * S, rc, t0), x);
-}
-
-H3_DEV double tanh_any(double x) { return tanh_tab(x); }
-
-H3_DEV double tanh_f64(double x) {
-    if (::fabs(x) < 0.55) return tanh_small(x);             // NaN compares false -> tanh_any -> NaN
-    return tanh_any(x);
 }
 
 // sin / cos polynomials on the reduced argument |r| <= pi/4
@@ -121,13 +105,13 @@ H3_DEV void sincos_f64(double x, double* s, double* c) {
 }
 
 #ifndef H3_TANH_G
-#define H3_TANH_G 5
+#define H3_TANH_G 10
 #endif
 
 // tanh_tab on elements [G0, min(G0 + H3_TANH_G, U)) of x, stage by stage so that the chains interleave, then the
 // next group
 template <int G0, int U>
-H3_DEV void tanh_any_group(const double (&x)[U], double (&y)[U]) {
+H3_DEV void tanh_tab_group(const double (&x)[U], double (&y)[U]) {
     constexpr int G = (U - G0) < H3_TANH_G ? (U - G0) : H3_TANH_G;
     if constexpr (G > 0) {
         double d[G], t0[G], q[G], z[G];
@@ -159,7 +143,7 @@ H3_DEV void tanh_any_group(const double (&x)[U], double (&y)[U]) {
 #pragma unroll
         for (int u = 0; u < G; ++u)
             y[G0 + u] = ::copysign(fma(p[u] * fma(-t0[u], t0[u], 1.0), rc[u], t0[u]), x[G0 + u]);
-        tanh_any_group<G0 + G, U>(x, y);
+        tanh_tab_group<G0 + G, U>(x, y);
     }
 }
 
@@ -170,42 +154,12 @@ template <>
 struct Math<double> {
     // once per kernel, by every thread, before the first tanh: stages the table of tanh_tab (contains __syncthreads())
     static H3_DEV void prepare() { tanh_table_stage(); }
-    static H3_DEV double tanh_(double x) { return tanh_f64(x); }
-    static H3_DEV double tanh_wide_(double x) { return tanh_any(x); }
-    // U independent arguments at once; the polynomial loops run coefficient-major so that consecutive DFMAs
-    // belong to different elements (a single warp per scheduler then covers the DFMA latency by itself).
-    // Returns whether the short (polynomial) branch was taken: the kernels keep that per episode as a sort key, so
-    // that episodes taking the same branches can be grouped into the same warps (ClosedLoop3DOF.compact).
-    // wide: every element takes the full-range formula (no test, no divergence): for the collective agent, whose
-    // inputs are a speed in m/s and an altitude error in m -- its pre-activations leave the polynomial's range as soon
-    // as the episode is under way, and a warp in which only SOME lanes have left it pays for both branches.
+    static H3_DEV double tanh_(double x) { return tanh_tab(x); }
+    // U independent arguments at once, stage by stage, so that consecutive DFMAs belong to different elements (a single
+    // warp per scheduler then covers the DFMA latency by itself)
     template <int U>
-    static H3_DEV bool tanh_vec(const double (&x)[U], double (&y)[U], bool wide = false) {
-        if (wide) {
-            tanh_any_group<0, U>(x, y);
-            return false;
-        }
-        bool all_small = true;
-#pragma unroll
-        for (int u = 0; u < U; ++u) all_small = all_small && (::fabs(x[u]) < 0.55);
-        if (all_small) {
-            double z[U], p[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                z[u] = x[u] * x[u];
-                p[u] = H3_TANH_C[11];
-            }
-#pragma unroll
-            for (int i = 10; i >= 0; --i)
-#pragma unroll
-                for (int u = 0; u < U; ++u) p[u] = fma(p[u], z[u], H3_TANH_C[i]);
-#pragma unroll
-            for (int u = 0; u < U; ++u) y[u] = fma(x[u] * z[u], p[u], x[u]);
-        } else {
-            // at most H3_TANH_G elements in flight: each carries ~6 live doubles through the pipeline below
-            tanh_any_group<0, U>(x, y);
-        }
-        return all_small;
+    static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
+        tanh_tab_group<0, U>(x, y);
     }
     // sin/cos of two independent angles (theta and the cyclic pitch): four interleaved polynomial chains
     static H3_DEV bool sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
@@ -244,12 +198,10 @@ template <>
 struct Math<float> {
     static H3_DEV void prepare() {}
     static H3_DEV float tanh_(float x) { return ::tanhf(x); }
-    static H3_DEV float tanh_wide_(float x) { return ::tanhf(x); }
     template <int U>
-    static H3_DEV bool tanh_vec(const float (&x)[U], float (&y)[U], bool = false) {
+    static H3_DEV void tanh_vec(const float (&x)[U], float (&y)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
-        return true;
     }
     static H3_DEV bool sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
         ::sincosf(a, sa, ca);
