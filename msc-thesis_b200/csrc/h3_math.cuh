@@ -63,6 +63,31 @@ H3_DEV double tanh_tab(double x) {
     return ::copysign(fma(p * S, rc, t0), x);
 }
 
+// Table-free full-range tanh: E / (E + 2), E = expm1(2x) = 2^n expm1(r) + (2^n - 1), 2x = n ln2 + r -- one straight-line
+// formula without cancellation for every x (2.4 ulp, 29 FP64-pipe instructions).  For kernels that are not bound by the
+// FP64 pipe and are too short to stage the table: the per-tick kernels of the 6-DOF loop (MathExp below).
+H3_DEV double tanh_exp(double x) {
+    const double xc = x > 20.0 ? 20.0 : (x < -20.0 ? -20.0 : x);    // |tanh| == 1 to the last bit beyond 19.1; NaN passes
+    const double y = xc + xc;
+    const double t = fma(y, H3_LN2[2], H3_TANHT_MAGIC);             // n = rint(y / ln2) in the low word of t
+    const double nf = t - H3_TANHT_MAGIC;
+    double r = fma(nf, -H3_LN2[0], y);
+    r = fma(nf, -H3_LN2[1], r);                                     // |r| <= ln2 / 2
+    double q = H3_EXP_C[10];
+#pragma unroll
+    for (int i = 9; i >= 0; --i) q = fma(q, r, H3_EXP_C[i]);
+    const double p = fma(r * r, q, r);                              // expm1(r)
+    const int n = __double2loint(t);                                // in [-58, 58]; NaN: E is NaN whatever n is
+    const double sc = __hiloint2double((n + 1023) << 20, 0);
+    const double E = fma(sc, p, sc - 1.0);
+    const double den = E + 2.0;                                     // in [1, 2^58]: no special cases in the division
+    double rc = rcp_seed(den);
+    rc = fma(rc, fma(-den, rc, 1.0), rc);
+    rc = fma(rc, fma(-den, rc, 1.0), rc);
+    const double q0 = E * rc;
+    return fma(fma(-q0, den, E), rc, q0);
+}
+
 // sin / cos polynomials on the reduced argument |r| <= pi/4
 H3_DEV void sincos_poly(double r, double* s, double* c) {
     const double z = r * r;
@@ -192,6 +217,17 @@ struct Math<double> {
     static H3_DEV double abs_(double x) { return ::fabs(x); }
     static H3_DEV void sincos_(double x, double* s, double* c) { sincos_f64(x, s, c); }
     static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }
+};
+
+// fp64 math without the shared-memory table (tanh_exp): nothing to stage
+struct MathExp : Math<double> {
+    static H3_DEV void prepare() {}
+    static H3_DEV double tanh_(double x) { return tanh_exp(x); }
+    template <int U>
+    static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) y[u] = tanh_exp(x[u]);
+    }
 };
 
 template <>

@@ -295,9 +295,9 @@ struct AgentH {             // hyper-parameters in network precision
 };
 
 // DHPActor.forward (agents.py:59-63); keeps h = tanh(W1 s) and f = final_activation(W2 h) for the update
-template <typename NT, int NH, int U, typename Net, typename HVec>
+//   M: math policy (Math<NT>; MathExp for kernels that do not stage the tanh table)
+template <typename NT, int NH, int U, typename M = Math<NT>, typename Net, typename HVec>
 H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& f) {
-    typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     NT y = (NT)0;
 #pragma unroll 1
@@ -329,10 +329,9 @@ H3_DEV NT actor_forward(Net& net, NT s0, NT s1, NT scale, int act, HVec& h, NT& 
 //   TAU1: tau_target_critic == 1 for every episode of the launch -> the target critic IS the critic after
 //   every update (agents.py:196: 1*p + 0*t), so its rows are neither kept on chip nor updated; lambda_t2
 //   is evaluated with the critic's (pre-update) weights, which are the target's.
-template <typename NT, int NH, int U, bool TAU1, typename Net, typename HVec, typename SVec>
+template <typename NT, int NH, int U, bool TAU1, typename M = Math<NT>, typename Net, typename HVec, typename SVec>
 H3_DEV void agent_update(Net& net, const AgentH<NT>& H, int act, NT s0, NT s1, NT n0, NT n1, NT dr0, NT dr,
                          const NT (&F)[2][2], const NT (&G)[2], HVec& h_a, NT f, SVec& scr) {
-    typedef Math<NT> M;
     static_assert(NH % U == 0, "chunk width must divide the hidden width");
     // action.backward() (:174): delta = da/dy, p_k = da/d(pre-activation of hidden k)
     const NT delta = (act == H3_ACT_TANH) ? H.scale * ((NT)1 - f * f) : H.scale * f * ((NT)1 - f);

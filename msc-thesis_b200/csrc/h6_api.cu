@@ -158,7 +158,7 @@ H3_DEV void agent_step_update(const H3AgentHyper& h, NetT& net, double lr_a, dou
     if (!io.fwd) {          // the actor forward pass of this (obs, ref) was not needed for the action
         io.s0 = obs[ac];
         io.s1 = obs[tr] - ref_slot(ref, tr);
-        (void)h3::actor_forward<double, NH, H6_U>(net, io.s0, io.s1, h.scale, h.final_activation, hh, io.f);
+        (void)h3::actor_forward<double, NH, H6_U, h3::MathExp>(net, io.s0, io.s1, h.scale, h.final_activation, hh, io.f);
     }
     const double n0 = nxt[ac], n1 = nxt[tr] - ref_slot(nref, tr);
     const double et = nxt[tr] - ref_slot(ref, tr);                      // agents.py:125
@@ -178,14 +178,13 @@ H3_DEV void agent_step_update(const H3AgentHyper& h, NetT& net, double lr_a, dou
     // tau == 1: after one update the target critic IS the critic (agents.py:196), so later ticks of the launch
     // neither read nor write its rows; they are refreshed from the critic at launch exit
     if (tau1_fast)
-        h3::agent_update<double, NH, H6_U, true>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
+        h3::agent_update<double, NH, H6_U, true, h3::MathExp>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
     else
-        h3::agent_update<double, NH, H6_U, false>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
+        h3::agent_update<double, NH, H6_U, false, h3::MathExp>(net, H, h.final_activation, io.s0, io.s1, n0, n1, 0.0, dr, F, G, hh, io.f, scr);
 }
 
 template <bool SYM, bool TILED>
 __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __grid_constant__ LoopParams P) {
-    Math<double>::prepare();                                            // tanh table of the agents' hidden layers (h3_math.cuh)
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x, ld = b.ld;
@@ -249,13 +248,13 @@ __global__ void __launch_bounds__(BLOCK, H6_MINB) closed_loop_kernel(const __gri
         io_lon.s0 = obs[C.lon.ac_state];
         io_lon.s1 = obs[C.lon.tracked_state] - ref_slot(ref, C.lon.tracked_state);
         io_lon.fwd = true;
-        act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U>(nlon, io_lon.s0, io_lon.s1, C.lon.scale,
+        act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U, h3::MathExp>(nlon, io_lon.s0, io_lon.s1, C.lon.scale,
                                                                    C.lon.final_activation, h_lon, io_lon.f);
         io_col.fwd = both;
         if (both) {
             io_col.s0 = obs[C.col.ac_state];
             io_col.s1 = obs[C.col.tracked_state] - ref_slot(ref, C.col.tracked_state);
-            act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U>(ncol, io_col.s0, io_col.s1, C.col.scale,
+            act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U, h3::MathExp>(ncol, io_col.s0, io_col.s1, C.col.scale,
                                                                        C.col.final_activation, h_col, io_col.f);
         } else {
             act[0] = pid_collective(C, obs, g, trim[0], pid[0]);

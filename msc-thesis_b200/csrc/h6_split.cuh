@@ -31,7 +31,7 @@ H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr
     const double s0 = wk[AG_S0 * ld], s1 = wk[AG_S1 * ld], n0 = wk[AG_N0 * ld], n1 = wk[AG_N1 * ld], dr = wk[AG_DR * ld];
     double hh[NH], scr[NH], f;
     // the actor forward pass of (obs, ref) with the pre-update weights (== get_action's pass, agents.py:169)
-    (void)h3::actor_forward<double, NH, H6_U>(net, s0, s1, h.scale, h.final_activation, hh, f);
+    (void)h3::actor_forward<double, NH, H6_U, h3::MathExp>(net, s0, s1, h.scale, h.final_activation, hh, f);
     double F[2][2], G[2];                                               // agents.py:130-140, post-update W
     const int idx[2] = {h.ac_state, h.tracked_state};
 #pragma unroll
@@ -42,8 +42,8 @@ H3_DEV void agent_learn(const H3AgentHyper& h, NetT& net, double lr_a, double lr
     }
     AgentH<double> H;
     H.gamma = h.gamma; H.lr_a = lr_a; H.lr_c = lr_c; H.tau = h.tau; H.scale = h.scale;
-    if (tau1_fast) h3::agent_update<double, NH, H6_U, true>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
-    else h3::agent_update<double, NH, H6_U, false>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
+    if (tau1_fast) h3::agent_update<double, NH, H6_U, true, h3::MathExp>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
+    else h3::agent_update<double, NH, H6_U, false, h3::MathExp>(net, H, h.final_activation, s0, s1, n0, n1, 0.0, dr, F, G, hh, f, scr);
 }
 
 // Phase S of one tick (PIDs, reference generator, actions, RK4, bookkeeping) for one episode; leaves what
@@ -114,8 +114,8 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk, do
     double hh[NH], f;
     const double lon_s0 = obs[C.lon.ac_state], lon_s1 = obs[C.lon.tracked_state] - ref_slot(ref, C.lon.tracked_state);
     const double col_s0 = obs[C.col.ac_state], col_s1 = obs[C.col.tracked_state] - ref_slot(ref, C.col.tracked_state);
-    act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U>(nlon, lon_s0, lon_s1, C.lon.scale, C.lon.final_activation, hh, f);
-    if (both) act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U>(ncol, col_s0, col_s1, C.col.scale, C.col.final_activation, hh, f);
+    act[1] = trim[1] - 0.5 + h3::actor_forward<double, NH, H6_U, h3::MathExp>(nlon, lon_s0, lon_s1, C.lon.scale, C.lon.final_activation, hh, f);
+    if (both) act[0] = trim[0] - 0.5 + h3::actor_forward<double, NH, H6_U, h3::MathExp>(ncol, col_s0, col_s1, C.col.scale, C.col.final_activation, hh, f);
     else act[0] = pid_collective(C, obs, g, trim[0], pid[0]);
     if (exc_phase && P.excitation != nullptr && k < P.exc_len) {                                          // :173-174
 #pragma unroll
@@ -213,7 +213,6 @@ H3_DEV void tick_simulate(const LoopParams& P, int64_t e, int it, double* wk, do
 //   ST: storage type of the tiled W / covariance (H6Batch.rls_f32: float; the arithmetic is fp64 either way).
 template <bool TILED, typename ST = double>
 __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ LoopParams P, int final) {
-    Math<double>::prepare();                                // tanh table of the agents' hidden layers (h3_math.cuh)
     const H6Config& C = P.C;
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
@@ -242,7 +241,6 @@ __global__ void __launch_bounds__(128, 4) agents_kernel(const __grid_constant__ 
 // One tick of PIDs, reference generator, actions and the RK4 model step for every live episode.
 template <bool TILED>
 __global__ void __launch_bounds__(128, H6_SIM_MINB) sim_kernel(const __grid_constant__ LoopParams P, int it) {
-    Math<double>::prepare();
     const H6Batch& b = P.b;
     const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x, ld = b.ld;
     if (e >= b.n) return;
@@ -528,7 +526,6 @@ template <bool SYM, bool TILED>
 __global__ void __launch_bounds__(MIX_BLOCK, H6_SIM_MINB) mixed_kernel(const __grid_constant__ LoopParams PS, int it_s, int mode_s,
                                                                        int64_t n_s, H6Batch bl, double gamma, int64_t n_l) {
     __shared__ double smem[30 * MIX_BLOCK];                 // RK4 arrays (role S) / X, cov.X rows (role L)
-    Math<double>::prepare();
     const int64_t q = blockIdx.x / 5;
     const int r5 = blockIdx.x % 5;
     if (r5 != 0) {                                          // role L: 4 of every 5 blocks
