@@ -41,10 +41,10 @@ constexpr size_t SMEM_PER_SM = 233472;          // 228 KB per SM, 1 KB of it res
 constexpr size_t SMEM_STATIC = ((sizeof(double) * H3_TANHT_N + 127) / 128) * 128 + 128;
 
 // On-chip placement per variant.  Phase-1 launches (COL == false) keep everything
-// but the RLS matrices in registers and run one warp per CTA (8 CTAs per SM).  Launches with the collective agent
-// go to the tensor-memory kernel (below) when they are lockstep and the covariance is symmetric; the rest
-// (heterogeneous batches, the literal non-symmetric update) run one 4-warp CTA per SM with as many episodes per
-// warp as the shared-memory tile allows.
+// but the RLS matrices in registers and run two 4-warp CTAs per SM (the CTA is the unit that stages the tanh table).
+// Launches with the collective agent go to the tensor-memory kernel (below) when they are lockstep and the covariance
+// is symmetric; the rest (heterogeneous batches, the literal non-symmetric update) run one 4-warp CTA per SM with as
+// many episodes per warp as the shared-memory tile allows.
 // ---- tuning knobs (compile-time; defaults are the measured best) ----
 #ifndef H3_SWEEP_P1_REGS
 #define H3_SWEEP_P1_REGS 1
