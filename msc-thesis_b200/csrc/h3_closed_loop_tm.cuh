@@ -213,7 +213,10 @@ struct LonNetTm {
     H3_DEV NT& t2(int j, int k) { return tv[2 * NH + j * NH + k]; }
 };
 
-template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int WARPS_ = 4>
+//   COLT: the launch reaches the switch -- the collective agent lives in tensor memory.  false (launches that end before
+//         the switch, per-episode-hyper variant): its networks stay in HBM and the columns hold the cyclic agent's TARGET
+//         critic instead (tau != 1), which is then in registers only while agent_update runs.
+template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int WARPS_ = 4, bool COLT = true>
 struct TmLayout {
     static constexpr int WARPS = WARPS_;           // 4 or 8: warps w and w + 4 share a lane quadrant, own column ranges
     static constexpr int STRIDE = LANES < 32 ? LANES + 1 : 32;      // + one dummy column for the idle lanes
@@ -221,8 +224,10 @@ struct TmLayout {
     static constexpr size_t tile_bytes = ((bytes_per_col * STRIDE + 15) / 16) * 16;
     static constexpr size_t head_bytes = sizeof(double) * WARPS * (3 * TICK_CHUNK + H3_N_STATS) + 16;
     static constexpr size_t smem_bytes = head_bytes + tile_bytes * WARPS;
-    // after the collective agent: the three reward accumulators (doubles, + one pad word) -- 8 columns
-    static constexpr int acc_col = ColTm<NHC>::WORDS * (int)(sizeof(NT) / 4);
+    static constexpr bool TGT_TM = !COLT && !TAU1L;                 // cyclic agent's target critic in tensor memory
+    static constexpr int tgt_col = (COLT ? ColTm<NHC>::WORDS : 0) * (int)(sizeof(NT) / 4);
+    // after the networks: the three reward accumulators (doubles, + one pad word) -- 8 columns
+    static constexpr int acc_col = tgt_col + (TGT_TM ? 4 * NHL : 0) * (int)(sizeof(NT) / 4);
     static constexpr int tm_words = acc_col + 8;
     static constexpr int tm_cols = tm_words <= 32 ? 32 : (tm_words <= 64 ? 64 : (tm_words <= 128 ? 128 : (tm_words <= 256 ? 256 : 512)));
     static_assert(tm_cols * (WARPS / 4) <= 512 && (WARPS == 4 || WARPS == 8), "collective agent does not fit a thread's tensor-memory columns");
@@ -232,9 +237,12 @@ struct TmLayout {
 //           agent not carried, see agent_update); LANES: episodes per warp (<= 32, as many as the tile allows);
 //   RD    : look-ahead of the RLS shared-memory streams; UF / UP / V2: hidden units per group of the collective
 //           agent's forward pass / critic passes / weight update
-template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int RD, int UF, int UP, int V2, int WARPS_>
+template <typename ET, typename NT, int NHL, int NHC, bool HYP, bool TAU1L, int LANES, int RD, int UF, int UP, int V2, int WARPS_,
+          bool COLT = true>
 __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel(const LoopParams<ET, NT> P) {
-    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, WARPS_> LY;
+    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, WARPS_, COLT> LY;
+    constexpr bool TGT_TM = LY::TGT_TM;
+    static_assert(!TGT_TM || H3_TM_TARGET_REGS, "the target critic moves between tensor memory and registers");
     constexpr int WARPS = LY::WARPS, STRIDE = LY::STRIDE, BLOCK = WARPS * 32;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     const int lc = lane < LANES ? lane : LANES;     // ... and share the tile's dummy column
     const EnvK<ET>& K = P.K;
     const uint32_t tm_acc = tm + (uint32_t)LY::acc_col;     // sum r_col, sum r_lon, sum r_lon inside the score window
+    const uint32_t tm_tgt = tm + (uint32_t)LY::tgt_col;     // cyclic agent's target critic (TGT_TM)
     Math<NT>::prepare();                                    // tanh table -> (static) shared memory
 
     // ---- carve the warp's tile ----
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     }
 
     // ---- entry load (coalesced SoA rows) ----
-    {   // collective agent -> TMEM, one hidden unit at a time
+    if constexpr (COLT) {   // collective agent -> TMEM, one hidden unit at a time
         typedef ColTm<NHC> L;
 #pragma unroll 1
         for (int k = 0; k < NHC; ++k) {
@@ -311,6 +320,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
     for (int i = 0; i < 63; ++i) Wm.v[i] = P.rls_W[i * ld + ec];
     lon.v.load(P.lon_net + ec, ld);                                     // actor + critic rows [0, 7 nh)
     if constexpr (!TAU1L) lon.tv.load(P.lon_net + (int64_t)7 * NHL * ld + ec, ld);
+    if constexpr (TGT_TM) tmem_store<NT, 4 * NHL>(tm_tgt, 0, lon.tv.v);
     tmem_wait_st();
     __syncwarp();
 
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             if (__all_sync(FULL, dead)) continue;       // every episode of this warp has terminated
             heat = 0;
             const int k = P.step0 + j;
-            const bool phase2 = k >= P.switch_step;                                 // main_3dof.py:127-137
+            const bool phase2 = COLT && (k >= P.switch_step);                       // main_3dof.py:127-137
             if (dead) {                     // frozen episode: run on harmless values, commit nothing
 #pragma unroll
                 for (int i = 0; i < 7; ++i) s[i] = (ET)0;
@@ -459,8 +469,17 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 const NT sl0 = (NT)pick7(prev, P.lon.ac_state);
                 const NT sl1 = (NT)(P.lon.tracked_state == 1 ? prev[1] : pick7(prev, P.lon.tracked_state) - refth);
                 SubVec<decltype(stl), NT> scr{stl, NHL + 3};
+                if constexpr (TGT_TM) {         // target critic: out of tensor memory for the update only
+                    __syncwarp();
+                    tmem_wait_st();
+                    tmem_load<NT, 4 * NHL>(tm_tgt, 0, lon.tv.v);
+                }
                 agent_update<NT, NHL, NHL, TAU1L>(lon, Hlon, P.lon.final_activation, sl0, sl1, n0, n1, (NT)0, dr,
                                                          F, G, stl, stl[NHL], scr);
+                if constexpr (TGT_TM) {
+                    __syncwarp();
+                    tmem_store<NT, 4 * NHL>(tm_tgt, 0, lon.tv.v);
+                }
             }
             // -------- collective agent (main_3dof.py:156-159) --------
             if (phase2) {
@@ -516,7 +535,8 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
         double accv[4];
         tmem_wait_st();
         tmem_load<double, 4>(tm_acc, 0, accv);
-        {
+        if constexpr (TGT_TM) tmem_load<NT, 4 * NHL>(tm_tgt, 0, lon.tv.v);
+        if constexpr (COLT) {
             typedef ColTm<NHC> L;
 #pragma unroll 1
             for (int k = 0; k < NHC; ++k) {

@@ -121,10 +121,15 @@ static KernelSel<ET, NT> sel_flags(bool col, int variant) {
 #define H3_TM_UP 5          // hidden units of the collective agent whose critic + target tanh chains are interleaved
 #endif
 
-template <typename ET, typename NT, int NHL, int NHC, int VAR>
+#ifndef H3_TM_P1_SWEEP
+#define H3_TM_P1_SWEEP 1    // per-episode-hyper launches that end before the switch: tensor-memory kernel with the cyclic
+                            // agent's target critic in TMEM (0: shared-memory kernel, target in registers + spills)
+#endif
+
+template <typename ET, typename NT, int NHL, int NHC, int VAR, bool COLT = true>
 struct TuneTm {
     static constexpr bool HYP = VAR != VAR_FAST, TAU1L = VAR == VAR_FAST;
-    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, 32, H3_TM_WARPS> L32;
+    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, 32, H3_TM_WARPS, COLT> L32;
     // eight warps per SM in one or two CTAs: the tile of a warp gets an eighth of what is left of the SM's shared memory
     static constexpr int CTAS = 8 / H3_TM_WARPS;
     static constexpr size_t room = (SMEM_PER_SM / CTAS - 1024 - SMEM_STATIC - L32::head_bytes) / L32::WARPS - 16;
@@ -134,14 +139,14 @@ struct TuneTm {
     static constexpr int UF = (NHC % 5 == 0) ? 5 : ((NHC % 4 == 0) ? 4 : ((NHC % 3 == 0) ? 3 : ((NHC % 2 == 0) ? 2 : 1)));
     static constexpr int UP = (NHC % H3_TM_UP == 0) ? H3_TM_UP : ((NHC % 4 == 0) ? 4 : ((NHC % 3 == 0) ? 3 : ((NHC % 2 == 0) ? 2 : 1)));
     static constexpr int V2 = (NHC % H3_TM_V2 == 0) ? H3_TM_V2 : 1;
-    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, H3_TM_WARPS> LY;
+    typedef TmLayout<ET, NT, NHL, NHC, HYP, TAU1L, LANES, H3_TM_WARPS, COLT> LY;
 };
 
-template <typename ET, typename NT, int NHL, int NHC, int VAR>
+template <typename ET, typename NT, int NHL, int NHC, int VAR, bool COLT = true>
 static KernelSel<ET, NT> sel_tm() {
-    typedef TuneTm<ET, NT, NHL, NHC, VAR> T;
+    typedef TuneTm<ET, NT, NHL, NHC, VAR, COLT> T;
     KernelSel<ET, NT> k;
-    k.fn = closed_loop_tm_kernel<ET, NT, NHL, NHC, T::HYP, T::TAU1L, T::LANES, H3_TM_RD, T::UF, T::UP, T::V2, H3_TM_WARPS>;
+    k.fn = closed_loop_tm_kernel<ET, NT, NHL, NHC, T::HYP, T::TAU1L, T::LANES, H3_TM_RD, T::UF, T::UP, T::V2, H3_TM_WARPS, COLT>;
     k.block = T::LY::WARPS * 32;
     k.lanes = T::LANES;
     k.warps = T::LY::WARPS;
@@ -153,6 +158,7 @@ template <typename ET, typename NT, int NHL, int NHC>
 static KernelSel<ET, NT> sel_flags(bool col, int variant, bool tm) {
     if (col && tm && variant == VAR_FAST) return sel_tm<ET, NT, NHL, NHC, VAR_FAST>();
     if (col && tm && variant == VAR_SWEEP) return sel_tm<ET, NT, NHL, NHC, VAR_SWEEP>();
+    if (!col && tm && variant == VAR_SWEEP) return sel_tm<ET, NT, NHL, NHC, VAR_SWEEP, false>();
     return sel_flags<ET, NT, NHL, NHC>(col, variant);
 }
 
@@ -169,7 +175,8 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
     const int variant = (cfg.rls_symmetric == 0) ? VAR_GENERAL
                                                  : ((per_ep || cfg.lon.tau != 1.0) ? VAR_SWEEP : VAR_FAST);
     // tensor-memory kernel: needs a warp-uniform tick index (lockstep) and the symmetric covariance
-    const bool tm = H3_TM && col && (step0 >= 0 || info_only != nullptr) && variant != VAR_GENERAL && cfg.store_policy != 3;
+    const bool tm = H3_TM && (col || (H3_TM_P1_SWEEP && variant == VAR_SWEEP)) && (step0 >= 0 || info_only != nullptr) &&
+                    variant != VAR_GENERAL && cfg.store_policy != 3;
     KernelSel<ET, NT> k;
     if (nhl == 6 && nhc == 10) k = sel_flags<ET, NT, 6, 10>(col, variant, tm);
 #ifndef H3_FAST_BUILD
