@@ -27,6 +27,7 @@ struct KernelSel {
     void (*fn)(const LoopParams<ET, NT>);
     int block, lanes, warps;
     size_t smem;
+    int tm_cols = 0;        // tensor-memory columns a CTA allocates (tensor-memory kernel), 0: none
 };
 
 // Kernel variants (a pruned cross product, see closed_loop_kernel's template flags):
@@ -151,6 +152,7 @@ static KernelSel<ET, NT> sel_tm() {
     k.lanes = T::LANES;
     k.warps = T::LY::WARPS;
     k.smem = T::LY::smem_bytes;
+    k.tm_cols = T::LY::tm_cols * (T::LY::WARPS / 4);
     return k;
 }
 
@@ -217,6 +219,17 @@ int launch_closed_loop(const H3Config& cfg, const H3Batch& b, int step0, const d
         if (err != cudaSuccess) {
             set_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor: %s", cudaGetErrorString(err));
             return H3_E_CUDA;
+        }
+        if (!rt && k.tm_cols > 0) {
+            // The occupancy API answers 1 for any kernel that allocates tensor memory (it cannot know how many of the 512
+            // columns the kernel asks for at run time).  What the SM really holds: the minimum over shared memory
+            // (dynamic + static + 1 KB reserved per CTA), registers (allocated in units of 8 per thread) and columns
+            // -- ncu agrees (launch__occupancy_limit_registers / _shared_mem 2, 7.6 warps active per cycle).
+            const int by_smem = (int)(SMEM_PER_SM / (k.smem + fa.sharedSizeBytes + 1024));
+            const int by_regs = 65536 / (((fa.numRegs + 7) / 8) * 8 * k.block);
+            const int by_tmem = 512 / k.tm_cols;
+            nb = by_smem < by_regs ? by_smem : by_regs;
+            nb = nb < by_tmem ? nb : by_tmem;
         }
         info_only->block = k.block;
         info_only->smem_bytes = (int)k.smem;

@@ -632,6 +632,18 @@ def test_host_batch_pipeline_compact_and_full_formats_agree(h3):
                     assert torch.equal(got, w)
 
 
+def test_fused_kernels_keep_eight_warps_of_32_episodes_per_sm(h3):
+    """main_3dof.py configuration: both fused kernels run two 4-warp CTAs per SM with one lane per episode (DESIGN.md
+    section 4) -- the PID-phase kernel limited by its shared-memory tiles, the tensor-memory kernel by tiles, registers
+    and its 256 TMEM columns per CTA (h3_closed_loop_info computes that minimum itself: the occupancy API answers 1 for a
+    kernel that allocates tensor memory)."""
+    run = h3.EpisodeRunner(256, device="cuda", per_episode_hyper=False)
+    for phase2 in (False, True):
+        info = run.loop.info(phase2)
+        assert info["block"] == 128 and info["blocks_per_sm"] == 2 and info["lanes_per_warp"] == 32, (phase2, info)
+        assert info["regs"] <= 255 and info["smem_bytes"] + 2560 + 1024 <= 233472 // 2
+
+
 def test_lockstep_run_issues_no_synchronising_call(h3):
     """The reference table of the lockstep clock is built once for the whole horizon and lives on the device: after the
     first run() a lockstep launch sequence (phase switch, statistics, several launches) contains no host <-> device copy

@@ -164,6 +164,9 @@ def test_sweep_variant_1e5_random_episodes_vs_c_oracle(h3):
     torch.cuda.synchronize()
     info = runner.loop.info(phase2=True)
     assert info["block"] == 128 and info["smem_bytes"] > 100000        # the tensor-memory kernel, per-episode-hyper variant
+    assert info["blocks_per_sm"] == 2 and info["lanes_per_warp"] == 32  # 8 warps x 32 episodes per SM, one lane per episode
+    info1 = runner.loop.info(phase2=False)      # launches that end before the switch: the same kernel, target critic in TMEM
+    assert info1["block"] == 128 and info1["blocks_per_sm"] == 2 and info1["lanes_per_warp"] == 32
     got = H.loop_state(runner.loop)
     worst = 0.0
     for s_i, (tau, std, gamma) in enumerate(settings):
