@@ -60,7 +60,7 @@ class ClosedLoop3DOF:
             ref = env.get_ref()
         self.ref2 = ref[[1, 4]].to(env.dtype).contiguous() if ref.shape[0] == 7 else ref.to(env.dtype).contiguous()
         self.acc = torch.zeros(3, n, dtype=torch.float64, device=self.device)
-        self.heat = torch.zeros(n, dtype=torch.int32, device=self.device)   # branch pattern of the last tick (sort key)
+        self.heat = torch.zeros(n, dtype=torch.int32, device=self.device)   # slow-branch tick count of the last launch (sort key)
         self.stats_dev = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
         nbytes = int(L.lib().h3_stats_scratch_bytes(n))
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)

@@ -1,4 +1,5 @@
-"""Distribution of the slow-branch duty-cycle counters (H3Batch.heat) over whole episodes: python tools/heat_hist.py"""
+"""Distribution of the slow-branch duty-cycle counter (H3Batch.heat: sin / cos beyond pi/4) over whole episodes:
+python tools/heat_hist.py"""
 import sys, torch
 sys.path.insert(0, ".")
 import msc_thesis_b200 as h3
@@ -14,9 +15,8 @@ for k in range(0, 9000, 1000):
     na = lp.n_active
     h = lp.heat[:na]
     alive = lp.env.flags[:na] == 0
-    lon = (h & 1023)[alive].float(); trig = ((h >> 20) & 1023)[alive].float()
+    trig = ((h >> 20) & 1023)[alive].float()        # ticks of the launch on the sin / cos branch beyond pi/4
     q = torch.tensor([0.1, 0.25, 0.5, 0.75, 0.9, 0.99], device=dev)
-    print("after tick %5d: alive %6d  lon-hot ticks quantiles %s  zero: %.2f  trig quantiles %s zero %.2f" % (
-        k + 1000, int(alive.sum()), [int(x) for x in torch.quantile(lon, q).tolist()], float((lon == 0).float().mean()),
-        [int(x) for x in torch.quantile(trig, q).tolist()], float((trig == 0).float().mean())))
+    print("after tick %5d: alive %6d  sin/cos slow-branch ticks quantiles %s  zero: %.2f" % (
+        k + 1000, int(alive.sum()), [int(x) for x in torch.quantile(trig, q).tolist()], float((trig == 0).float().mean())))
     lp.compact(sort_key=lp.sort_key())
