@@ -144,12 +144,13 @@ def test_init_and_run_are_shard_independent(h3):
 def test_sweep_variant_1e5_random_episodes_vs_c_oracle(h3):
     """102,400 episodes of a main.py-style sweep (8 settings of per-episode tau / nn_stdev / gamma / learning rates on
     the cyclic agent x 12,800 seeds, random trim speeds): device-side init + 50 ticks through the phase switch (the
-    per-episode-hyper kernels: phase-1 variant and the tensor-memory variant) against the compiled C oracle run
+    per-episode-hyper variants of the tensor-memory kernel: the launch that ends before the switch keeps the cyclic
+    agent's target critic in TMEM, the launch that contains it the collective agent) against the compiled C oracle run
     setting by setting on the same Philox draws."""
     import torch
     from oracle import c_oracle as CO
     grid = {"tau_target_critic": [0.1, 1.0], "nn_stdev": [0.1, 0.3], "discount_factor": [0.8, 0.95]}
-    n_seeds, n_ticks, switch = 12800, 50, 20
+    n_seeds, n_ticks, switch = 12800, 50, 30      # launches of 25 ticks: one ends before the switch, one contains it
     keys, settings, n = h3.sweep.expand_grid(grid, n_seeds)
     assert n == 102400
     seed = 4242
