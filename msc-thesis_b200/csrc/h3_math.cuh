@@ -129,6 +129,13 @@ H3_DEV void sincos_f64(double x, double* s, double* c) {
     }
 }
 
+// No branch at all: Cody-Waite reduction for every argument.  For callers whose angles are spread over the circle and
+// bounded by the physics (the 6-DOF model: rotor azimuth offsets, attitude, heading -- a warp takes both branches of
+// sincos_f64 anyway, and the out-of-line library fallback costs registers around the call).  The quadrant index is the low
+// word of x * 2/pi + 1.5 * 2^52, so the result is a sin / cos pair for |x| < 2^31 (2 ulp to 1e5, degrading slowly beyond);
+// inf and NaN give NaN.
+H3_DEV void sincos_wide(double x, double* s, double* c) { sincos_reduced(x, s, c); }
+
 #ifndef H3_TANH_G
 #define H3_TANH_G 10
 #endif
