@@ -147,11 +147,9 @@ typedef struct H3Batch {
     int32_t* term_step;     /* [ld] */
     /* per-episode accumulators (f64): [0] sum r_col, [1] sum r_lon, [2] sum r_lon inside the window */
     double* acc;            /* [3][ld] */
-    /* optional OUTPUT of h3_closed_loop (NULL to skip): in how many ticks of the launch the episode took the one
-     * data-dependent slow branch of the tick, sin / cos beyond pi/4 -- a 10-bit counter in bits 20-29 (bits 0-19
-     * counted the branches of the two-branch tanh of earlier builds and are 0 now).
-     * Episodes are independent, so the caller may reorder them between launches; ordering by this count puts
-     * episodes that take the same branch into the same warps (ClosedLoop3DOF.compact / sort_key). */
+    /* optional OUTPUT of h3_closed_loop (NULL to skip), kept for ABI stability: earlier builds counted here the ticks
+     * an episode spent on data-dependent slow branches of tanh / sincos (a sort key for the host).  The tick has no such
+     * branch any more; the kernels write 0. */
     int32_t* heat;          /* [ld] */
 } H3Batch;
 

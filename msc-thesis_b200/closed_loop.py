@@ -60,7 +60,6 @@ class ClosedLoop3DOF:
             ref = env.get_ref()
         self.ref2 = ref[[1, 4]].to(env.dtype).contiguous() if ref.shape[0] == 7 else ref.to(env.dtype).contiguous()
         self.acc = torch.zeros(3, n, dtype=torch.float64, device=self.device)
-        self.heat = torch.zeros(n, dtype=torch.int32, device=self.device)   # slow-branch tick count of the last launch (sort key)
         self.stats_dev = torch.zeros(L.N_STATS, dtype=torch.float64, device=self.device)
         nbytes = int(L.lib().h3_stats_scratch_bytes(n))
         self._scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
@@ -145,7 +144,7 @@ class ClosedLoop3DOF:
                            pid_corr=self.pid.hdot_corr, rls_W=rls._W, rls_cov=rls._cov, rls_x=rls.x, rls_u=rls.u,
                            rls_skip=rls._skip, col_net=self.agent_col.net, lon_net=self.agent_lon.net,
                            col_hyper=col_hyper, lon_hyper=lon_hyper, step=env.step_count, flags=env.flags,
-                           term_step=env.term_step, acc=self.acc, heat=self.heat)
+                           term_step=env.term_step, acc=self.acc)
 
     def _config(self, ref_mode):
         return build_config(env=self.env, pid=self.pid, rls=self.rls, col=self.agent_col, lon=self.agent_lon,
@@ -330,7 +329,7 @@ class ClosedLoop3DOF:
         env, rls = self.env, self.rls
         ts = [env.state, env.t_ep, self.ref2, env.corr_u, env.trimmed_controls, env.trimmed_state, self.pid.hdot_corr,
               rls._W, rls._cov, rls.x, rls.u, rls._skip, rls.X, self.agent_col.net, self.agent_lon.net,
-              env.step_count, env.flags, env.term_step, self.acc, self.order, self.heat]
+              env.step_count, env.flags, env.term_step, self.acc, self.order]
         if env.ref_params is not None:
             ts.append(env.ref_params)
         for ag in (self.agent_col, self.agent_lon):
@@ -386,17 +385,12 @@ class ClosedLoop3DOF:
         return n_alive
 
     def sort_key(self):
-        """Per-episode key for compact(sort_key=...) that groups episodes taking the same data-dependent branch in the
-        next launch: the number of ticks of the last launch in which the episode left the short sin / cos branch
-        (H3Batch.heat; tanh has had no branch since the table-driven formula) -- the reference signal is periodic, so an
-        episode's duty cycle on the slow branch is what persists from launch to launch --, with the current pitch-loop
-        agitation |theta - theta_ref| + 0.1 |q| as the tie-break (and as the whole key before the first launch has
-        counted): agitated episodes are also the ones that terminate next, so the sort keeps the dying lanes together."""
+        """Per-episode key for compact(sort_key=...): the current pitch-loop agitation |theta - theta_ref| + 0.1 |q|.
+        The tick has no data-dependent branch (tanh and sin / cos are one formula for every argument), so the order no
+        longer decides which lanes diverge; it still matters because agitated episodes are the ones that terminate next:
+        sorted, the lanes that die inside the next launch sit in the same warps (2-3 % over the launches)."""
         st = self.env.state
-        agitation = (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
-        h = self.heat
-        counts = ((h >> 20) & 1023).double()
-        return counts + agitation / (1.0 + agitation)
+        return (st[4] - self.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
 
     def original_order(self, t):
         """Per-episode tensor `t` (episode axis last) re-ordered to the original episode indices."""

@@ -22,10 +22,8 @@ namespace h3 {
 // PLACE bits: group lives in the shared-memory tile (always there: RLS covariance + weights, collective nets)
 enum { P_LON = 1, P_PREV = 2, P_MISC = 4, P_STASHC = 8, P_STASHL = 16 };
 
-// H3Batch.heat: in how many ticks of the launch the episode took the one data-dependent slow branch that is left, sin / cos
-// beyond pi/4 (a 10-bit counter at bits 20-29; bits 0-19 counted the tanh branches, which no longer exist)
-enum { H3_HEAT_TRIG = 4 };
-H3_DEV int heat_counts(int bits) { return (bits & 4) << 18; }
+// (H3Batch.heat counted the ticks an episode spent on data-dependent slow branches of tanh / sincos; the tick has none
+// left, the kernels write 0.)
 
 constexpr int TICK_CHUNK = 16;      // ticks of reference / excitation staged through smem at a time
 
@@ -262,7 +260,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
     }
 
     const bool lockstep = P.step0 >= 0;
-    int heat = 0, heat_acc = 0;
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
     const bool table_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_TABLE);
 
@@ -283,7 +280,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         }
         for (int jj = 0; jj < cn; ++jj) {
             if (flags != 0) continue;       // terminated (or idle) lane: frozen
-            heat = 0;
             const int k = lockstep ? (P.step0 + c0 + jj) : step;
             const bool phase2 = COL && (k >= P.switch_step);                    // main_3dof.py:127-137
             AgentH<NT> Hcol = P.col_h, Hlon = P.lon_h;
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             cyc += exc1;
             // sin/cos of theta (model + PID) and of the cyclic pitch (model) in one interleaved evaluation
             ET scy, ccy;
-            if (!Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy)) heat |= H3_HEAT_TRIG;
+            Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
             if (!phase2) {
                 ET pc = misce[1];
                 colv = pid_collective(K, s, sth, cth, pc);                      // PID.py:16-24
@@ -429,7 +425,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
             // -------- next step / termination (main_3dof.py:189-197) --------
             refth = nrefth;
             step = k + 1;
-            heat_acc += heat_counts(heat);
             const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
             if (nf) {
                 flags = nf;
@@ -454,7 +449,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) closed_loop_kernel(const Loo
         P.step[e] = step;
         P.flags[e] = flags;
         P.term_step[e] = term_step;
-        if (P.heat != nullptr) P.heat[e] = heat_acc;
+        if (P.heat != nullptr) P.heat[e] = 0;
         acc0 = miscd[0];
         acc1 = miscd[1];
         acc2 = miscd[2];

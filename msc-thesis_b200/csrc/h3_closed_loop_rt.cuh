@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
     const bool lockstep = P.step0 >= 0;
     const bool in_kernel_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_KERNEL);
     const bool table_ref = (P.task == H3_TASK_SINUSOID) && (P.ref_mode == H3_REF_TABLE);
-    int heat = 0;
 
     for (int j = 0; j < P.n_ticks && flags == 0; ++j) {
         const int k = lockstep ? (P.step0 + j) : step;
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
         }
         cyc += exc1;
         ET sth, cth, scy, ccy;
-        (void)Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
+        Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
         if (!phase2) colv = pid_collective(K, s, sth, cth, pid_corr);          // PID.py:16-24
         colv += exc0;
         // -------- env.step (main_3dof.py:141) --------
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(RT_BLOCK) closed_loop_rt_kernel(const LoopPara
         P.step[e] = step;
         P.flags[e] = flags;
         P.term_step[e] = term_step;
-        if (P.heat != nullptr) P.heat[e] = heat;
+        if (P.heat != nullptr) P.heat[e] = 0;
         P.t[e] = t_ep;
         P.acc[e] = acc0;
         P.acc[ld + e] = acc1;

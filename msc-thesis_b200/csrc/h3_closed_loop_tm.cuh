@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
 
     // ---- resumable tick loop: leaves whenever a lane terminated, so that its state is stored at once ----
     int j = 0;
-    int heat = 0, heat_acc = 0;             // slow data-dependent branches taken: this tick / counted over the launch
     bool just_died = false, finished = false;
     do {
         bool flush = false;
@@ -349,7 +348,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             }
             const bool dead = flags != 0;
             if (__all_sync(FULL, dead)) continue;       // every episode of this warp has terminated
-            heat = 0;
             const int k = P.step0 + j;
             const bool phase2 = COLT && (k >= P.switch_step);                       // main_3dof.py:127-137
             if (dead) {                     // frozen episode: run on harmless values, commit nothing
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             cyc += (ET)sh_exc[2 * jj + 1];                                          // main_3dof.py:139-140
             if (dead) cyc = (ET)0;
             ET scy, ccy;
-            if (!Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy)) heat |= H3_HEAT_TRIG;
+            Math<ET>::sincos2_(s[4], cyc, &sth, &cth, &scy, &ccy);
             if (!phase2) {
                 ET pc = P.pid_corr[ec];
                 colv = pid_collective(K, s, sth, cth, pc);                          // PID.py:16-24
@@ -516,7 +514,6 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
                 if (P.task == H3_TASK_VELOCITY) P.corr_u[ec] = cu;
                 refth = nrefth;
                 step = k + 1;
-                heat_acc += heat_counts(heat);
                 const int nf = (done ? H3_FLAG_DONE : 0) | (nan_act ? H3_FLAG_NAN : 0);
                 if (nf) {
                     flags = nf;
@@ -561,7 +558,7 @@ __global__ void __launch_bounds__(WARPS_ * 32, 8 / WARPS_) closed_loop_tm_kernel
             P.step[e] = step;
             P.flags[e] = flags;
             P.term_step[e] = term_step;
-            if (P.heat != nullptr) P.heat[e] = heat_acc;
+            if (P.heat != nullptr) P.heat[e] = 0;
             P.t[e] = t_ep;
             P.acc[e] = accv[0];
             P.acc[ld + e] = accv[1];

@@ -14,8 +14,7 @@ namespace h3 {
 // its DFMA (tools/fit_math_coef.py derives them), where the inlined CUDA library routine spends two UMOV issue
 // slots per coefficient.  tanh is ONE straight-line, table-driven formula for every argument (tanh_tab below): no
 // data-dependent branch, so episodes whose pre-activations are small and episodes that saturate share a warp for free.
-// sin/cos use one polynomial pair on |x| <= pi/4 (flight angles) and the library, out of line, beyond.
-static __device__ __noinline__ void sincos_libm(double x, double* s, double* c) { ::sincos(x, s, c); }
+// sin/cos: Cody-Waite reduction by multiples of pi/2 and one polynomial pair, also one formula for every argument.
 
 // ~20-bit reciprocal seed from the high word: one MUFU.RCP64H.  (__frcp_rn on the float-converted value is
 // IEEE-rounded and drags a slow-path branch into every element, which also stops the interleaving.)
@@ -101,11 +100,15 @@ H3_DEV void sincos_poly(double r, double* s, double* c) {
     *c = fma(z * z, pc, fma(-0.5, z, 1.0));
 }
 
-// |x| <= 1e5: Cody-Waite reduction by multiples of pi/2 (three FMA pieces), polynomial pair, quadrant swap --
-// straight-line code.  Pitch angles between 45 and 90 degrees (episodes on their way to termination) stay on
-// this path instead of dragging their whole warp through the library's out-of-line routine.
-H3_DEV void sincos_reduced(double x, double* s, double* c) {
-    const double t = fma(x, H3_PIO2[3], 6755399441055744.0);      // q = rint(x * 2/pi) in the low word of t
+// Cody-Waite reduction by multiples of pi/2 (three FMA pieces of 53 bits each), polynomial pair, quadrant swap --
+// straight-line code for EVERY argument: no polynomial-only branch for small angles (a warp whose lanes disagree pays for
+// both sides; 5 instructions saved when they agree) and no out-of-line library fallback (a call site costs registers
+// around it even when it is never taken).  q = rint(x * 2/pi) lands in the low word of x * 2/pi + 1.5 * 2^52 and is exact
+// as a double below 2^51, so the pair is valid for |x| < 3.5e15 (2 ulp in the ranges the loops visit, tests/
+// test_gpu_math.py); inf and NaN give NaN.  Angles of the closed loops are bounded by the physics: the pitch-angle
+// termination (heli_models.py:210-213) ends an episode long before.
+H3_DEV void sincos_f64(double x, double* s, double* c) {
+    const double t = fma(x, H3_PIO2[3], 6755399441055744.0);
     const double q = t - 6755399441055744.0;
     double r = fma(-q, H3_PIO2[0], x);
     r = fma(-q, H3_PIO2[1], r);
@@ -117,24 +120,6 @@ H3_DEV void sincos_reduced(double x, double* s, double* c) {
     *s = (n & 2) ? -a : a;
     *c = ((n + 1) & 2) ? -b : b;
 }
-
-H3_DEV void sincos_f64(double x, double* s, double* c) {
-    const double ax = ::fabs(x);
-    if (ax <= 0.78539816339744828) {
-        sincos_poly(x, s, c);
-    } else if (ax <= 1.0e5) {
-        sincos_reduced(x, s, c);
-    } else {
-        sincos_libm(x, s, c);                                     // huge, inf, NaN
-    }
-}
-
-// No branch at all: Cody-Waite reduction for every argument.  For callers whose angles are spread over the circle and
-// bounded by the physics (the 6-DOF model: rotor azimuth offsets, attitude, heading -- a warp takes both branches of
-// sincos_f64 anyway, and the out-of-line library fallback costs registers around the call).  The quadrant index is the low
-// word of x * 2/pi + 1.5 * 2^52, so the result is a sin / cos pair for |x| < 2^31 (2 ulp to 1e5, degrading slowly beyond);
-// inf and NaN give NaN.
-H3_DEV void sincos_wide(double x, double* s, double* c) { sincos_reduced(x, s, c); }
 
 #ifndef H3_TANH_G
 #define H3_TANH_G 10
@@ -193,31 +178,10 @@ struct Math<double> {
     static H3_DEV void tanh_vec(const double (&x)[U], double (&y)[U]) {
         tanh_tab_group<0, U>(x, y);
     }
-    // sin/cos of two independent angles (theta and the cyclic pitch): four interleaved polynomial chains
-    static H3_DEV bool sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
-        const bool poly = ::fabs(a) <= 0.78539816339744828 && ::fabs(b) <= 0.78539816339744828;
-        if (poly) {
-            const double za = a * a, zb = b * b;
-            double psa = H3_SIN_C[7], pca = H3_COS_C[7], psb = H3_SIN_C[7], pcb = H3_COS_C[7];
-#pragma unroll
-            for (int i = 6; i >= 0; --i) {
-                psa = fma(psa, za, H3_SIN_C[i]);
-                pca = fma(pca, za, H3_COS_C[i]);
-                psb = fma(psb, zb, H3_SIN_C[i]);
-                pcb = fma(pcb, zb, H3_COS_C[i]);
-            }
-            *sa = fma(a * za, psa, a);
-            *ca = fma(za * za, pca, fma(-0.5, za, 1.0));
-            *sb = fma(b * zb, psb, b);
-            *cb = fma(zb * zb, pcb, fma(-0.5, zb, 1.0));
-        } else if (::fabs(a) <= 1.0e5 && ::fabs(b) <= 1.0e5) {
-            sincos_reduced(a, sa, ca);
-            sincos_reduced(b, sb, cb);
-        } else {
-            sincos_f64(a, sa, ca);
-            sincos_f64(b, sb, cb);
-        }
-        return poly;
+    // sin/cos of two independent angles (theta and the cyclic pitch): straight-line, the four polynomial chains interleave
+    static H3_DEV void sincos2_(double a, double b, double* sa, double* ca, double* sb, double* cb) {
+        sincos_f64(a, sa, ca);
+        sincos_f64(b, sb, cb);
     }
     static H3_DEV double exp_(double x) { return ::exp(x); }
     static H3_DEV double sqrt_(double x) { return ::sqrt(x); }
@@ -246,10 +210,9 @@ struct Math<float> {
 #pragma unroll
         for (int u = 0; u < U; ++u) y[u] = ::tanhf(x[u]);
     }
-    static H3_DEV bool sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
+    static H3_DEV void sincos2_(float a, float b, float* sa, float* ca, float* sb, float* cb) {
         ::sincosf(a, sa, ca);
         ::sincosf(b, sb, cb);
-        return true;
     }
     static H3_DEV float exp_(float x) { return ::expf(x); }
     static H3_DEV float sqrt_(float x) { return ::sqrtf(x); }

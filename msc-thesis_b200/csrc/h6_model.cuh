@@ -140,8 +140,8 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     const double V2 = u * u + v * v + w * w, V = sqrt(V2);
     const double omega_r = omega * K.R_mr, inv_or = 1.0 / omega_r, inv_om = K.R_mr * inv_or;
     double sa, ca, sf, cf;
-    h3::sincos_wide(c.theta_1s - alpha_fus, &sa, &ca);                   // alpha_cp, :513
-    h3::sincos_wide(alpha_fus, &sf, &cf);
+    h3::sincos_f64(c.theta_1s - alpha_fus, &sa, &ca);                   // alpha_cp, :513
+    h3::sincos_f64(alpha_fus, &sf, &cf);
     const double mu_x = V * ca * inv_or, mu_z = -V * sa * inv_or, mu2 = mu_x * mu_x;
     // flapping (:522-547): rows of A x = b, only a1 and b1 are used
     const double den1 = gamma * K.den1_c, den2 = gamma * mu2 * K.den2_c;
@@ -163,8 +163,8 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     const double or2 = omega_r * omega_r;
     const double T_mr = Ct * rho * or2 * K.disc_mr;
     double s1, c1, s2, c2;
-    h3::sincos_wide(a1 - c.theta_1s + K.gamma_s, &s1, &c1);              // a1t1s
-    h3::sincos_wide(b1 + c.theta_1c, &s2, &c2);                          // b1t1c
+    h3::sincos_f64(a1 - c.theta_1s + K.gamma_s, &s1, &c1);              // a1t1s
+    h3::sincos_f64(b1 + c.theta_1c, &s2, &c2);                          // b1t1c
     const double Le = or2 * K.ecc * s2, Me = or2 * K.ecc * s1;          // :561-562
     const double Ct_gl_mr = 2 * l0mr * sqrt(mu2 + lam * lam);           // :566
     // tail rotor (:572-589)
@@ -209,9 +209,9 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     const double Mmr = -Xmr * K.zh - Zmr * K.xh + Me;
     const double Nmr = P_eng * inv_om + Xmr * K.yh - Ymr * K.xh;
     double sph, cph, sth, cth, sps, cps;
-    h3::sincos_wide(phi, &sph, &cph);
-    h3::sincos_wide(theta, &sth, &cth);
-    h3::sincos_wide(psi, &sps, &cps);
+    h3::sincos_f64(phi, &sph, &cph);
+    h3::sincos_f64(theta, &sth, &cth);
+    h3::sincos_f64(psi, &sps, &cps);
     const double Fx = -K.W * sth + (Xmr + X_fus);
     const double Fy = K.W * cth * sph + (Ymr + Y_tr + Y_fin);
     const double Fz = K.W * cth * cph + (Zmr + Z_fus + Z_hs);
@@ -294,9 +294,9 @@ struct ObsTrig {
 };
 H3_DEV ObsTrig obs_trig(const double (&o)[15]) {
     ObsTrig t;
-    h3::sincos_wide(o[6], &t.sph, &t.cph);
-    h3::sincos_wide(o[7], &t.sth, &t.cth);
-    h3::sincos_wide(o[8], &t.sps, &t.cps);
+    h3::sincos_f64(o[6], &t.sph, &t.cph);
+    h3::sincos_f64(o[7], &t.sth, &t.cth);
+    h3::sincos_f64(o[8], &t.sps, &t.cps);
     return t;
 }
 

@@ -50,16 +50,20 @@ def test_tanh_accuracy(fn, bound):
 
 
 def test_sincos_accuracy():
+    """One branch-free formula (Cody-Waite by pi/2 in three pieces + a polynomial pair) for every argument: flight angles,
+    the pi/4 hand-over of the polynomial pair, many periods, and far beyond anything a live episode produces."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     rng = np.random.default_rng(1)
     x = np.concatenate([rng.uniform(-np.pi / 4, np.pi / 4, 200000), rng.uniform(-1e-6, 1e-6, 10000),
-                        rng.uniform(-10, 10, 100000), rng.uniform(-1e6, 1e6, 10000),
-                        [0.0, np.pi / 4, -np.pi / 4, np.nextafter(np.pi / 4, 1), 1e22]])
+                        rng.uniform(-10, 10, 100000), rng.uniform(-1e6, 1e6, 10000), rng.uniform(-1e9, 1e9, 10000),
+                        np.arange(-64, 65) * (np.pi / 4), np.nextafter(np.arange(-64, 65) * (np.pi / 4), 1e9),
+                        [0.0, -0.0, 5e-324, 1e-300, np.pi / 4, -np.pi / 4, np.nextafter(np.pi / 4, 1), 1e12, -3e14]])
     s, c = _probe(1, x)
     assert float(np.nanmax(_ulps(s, np.sin(x)))) <= 3.0
     assert float(np.nanmax(_ulps(c, np.cos(x)))) <= 3.0
-    s, c = _probe(1, np.array([np.nan, np.inf]))
+    assert np.all(np.abs(s) <= 1.0) and np.all(np.abs(c) <= 1.0)
+    s, c = _probe(1, np.array([np.nan, np.inf, -np.inf]))
     assert np.isnan(s).all() and np.isnan(c).all()
 
 

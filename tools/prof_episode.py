@@ -28,25 +28,6 @@ elif a.sort == "z":
     bench.SORT_KEY = lambda lp: lp.env.state[1].abs()
 elif a.sort == "th":
     bench.SORT_KEY = lambda lp: (lp.env.state[4] - lp.ref2[1]).abs() + 0.1 * lp.env.state[5].abs()
-elif a.sort == "heat_th":
-    bench.SORT_KEY = lambda lp: lp.heat.double() + (lambda x: x / (1 + x))((lp.env.state[4] - lp.ref2[1]).abs() + 0.1 * lp.env.state[5].abs())
-elif a.sort.startswith("lex"):
-    def _lex(lp, mode=a.sort):
-        h = lp.heat
-        lon, trig = (h & 1023), ((h >> 20) & 1023)
-        st = lp.env.state
-        ag = (st[4] - lp.ref2[1]).abs().double() + 0.1 * st[5].abs().double()
-        tie = ag / (1.0 + ag)
-        if mode == "lex_tl":      # trig bucket (4 levels) major, lon count minor
-            return ((trig + 255) // 256).double() * 4096 + lon.double() + tie
-        if mode == "lex_lt":      # lon bucket major, trig minor
-            return ((lon + 255) // 256).double() * 4096 + trig.double() + tie
-        if mode == "lex_l":       # lon count only
-            return lon.double() + tie
-        if mode == "lex_max":
-            return torch.maximum(lon, trig).double() * 2048 + (lon + trig).double() + tie
-        raise SystemExit("unknown sort")
-    bench.SORT_KEY = _lex
 elif a.sort == "zt":
     bench.SORT_KEY = lambda lp: lp.env.state[1].abs() + 20 * (lp.env.state[4] - lp.ref2[1]).abs()
 n = a.episodes
