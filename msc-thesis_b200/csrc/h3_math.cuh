@@ -24,6 +24,33 @@ H3_DEV double rcp_seed(double a) {
     return r;
 }
 
+// Division and square root without the compiler's slow-path call sites (subnormal / huge operands): reciprocal seed + one
+// third-order step (relative error < 2^-58), quotient with one residual correction -- within 1 ulp of a / b for normal
+// operands; b == 0 gives NaN instead of +-inf (such an episode has diverged and ends on the NaN check).
+H3_DEV double div_nr(double a, double b) {
+    double rc = rcp_seed(b);
+    const double e = fma(-b, rc, 1.0);
+    rc = fma(rc, fma(e, e, e), rc);
+    const double q = a * rc;
+    return fma(fma(-q, b, a), rc, q);
+}
+
+// sqrt: MUFU.RSQ64H seed, two coupled Newton steps on (g ~ sqrt a, h ~ 1 / (2 sqrt a)), one residual correction.
+// Arguments below 1e-290 (incl. 0 and subnormals, which the seed flushes) give 0; negative arguments NaN.
+H3_DEV double sqrt_nr(double a) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double g = a * r, h = 0.5 * r;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    g = fma(fma(-g, g, a), h, g);
+    return (a < 1.0e-290 && a >= 0.0) ? 0.0 : g;
+}
+
 // Full-range tanh from a 313-entry table in shared memory (2.5 KB per CTA, staged by tanh_table_stage()):
 //   x0 = floor(16 |x|) / 16, d = |x| - x0 in [0, 1/16]      (exact: DFMA.RM with the 1.5 * 2^52 constant, one DFMA)
 //   tanh(x0 + d) = t0 + (1 - t0^2) p / (1 + t0 p),  t0 = tanh(x0) (table),  p = tanh(d) = d + d z Q(z), z = d^2
@@ -184,10 +211,11 @@ struct Math<double> {
         sincos_f64(b, sb, cb);
     }
     static H3_DEV double exp_(double x) { return ::exp(x); }
-    static H3_DEV double sqrt_(double x) { return ::sqrt(x); }
+    static H3_DEV double sqrt_(double x) { return sqrt_nr(x); }
+    static H3_DEV double div_(double a, double b) { return div_nr(a, b); }
     static H3_DEV double abs_(double x) { return ::fabs(x); }
     static H3_DEV void sincos_(double x, double* s, double* c) { sincos_f64(x, s, c); }
-    static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }
+    static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }     // (IEEE: exp overflows to inf -> 0)
 };
 
 // fp64 math without the shared-memory table (tanh_exp): nothing to stage
@@ -216,6 +244,7 @@ struct Math<float> {
     }
     static H3_DEV float exp_(float x) { return ::expf(x); }
     static H3_DEV float sqrt_(float x) { return ::sqrtf(x); }
+    static H3_DEV float div_(float a, float b) { return a / b; }
     static H3_DEV float abs_(float x) { return ::fabsf(x); }
     static H3_DEV void sincos_(float x, float* s, float* c) { ::sincosf(x, s, c); }
     static H3_DEV float sigmoid_(float x) { return 1.0f / (1.0f + ::expf(-x)); }

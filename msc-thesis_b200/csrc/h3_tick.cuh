@@ -67,8 +67,8 @@ H3_DEV void env_step(const EnvK<T>& K, T (&s)[7], T col, T cyc, T sth, T cth, T 
     const T mu = (u * cc + w * sc) * K.inv_vtip;            // :163
     const T lc = (u * sc - w * cc) * K.inv_vtip;            // :164
     const T lsum = lc + li;
-    const T a1 = (K.k_a1_q * q_diml + (T)(8.0 / 3.0) * mu * col - (T)2 * mu * lsum) /
-                 ((T)1 - mu * mu * (T)0.5);                 // :167
+    const T a1 = M::div_(K.k_a1_q * q_diml + (T)(8.0 / 3.0) * mu * col - (T)2 * mu * lsum,
+                         (T)1 - mu * mu * (T)0.5);          // :167
     const T ct_bem = K.k_bem * ((T)(2.0 / 3.0) * col * ((T)1 + (T)1.5 * mu * mu) - lsum);   // :170
     T s1, c1;
     M::sincos_(cyc - a1, &s1, &c1);
@@ -112,11 +112,11 @@ H3_DEV T pid_collective(const EnvK<T>& K, const T (&s)[7], T sth, T cth, T& corr
 // (t is accumulated in fp64 for every precision path).
 // ----------------------------------------------------------------------------------------------
 H3_DEV double sinusoid_ref(double t_plus_dt, double amp, double period) {
-    const double x = 3.14159265358979323846 * t_plus_dt / period;
+    const double x = div_nr(3.14159265358979323846 * t_plus_dt, period);
     double sx, cx;
-    ::sincos(x, &sx, &cx);
+    sincos_f64(x, &sx, &cx);
     // sin x + sin 2x = sin x (1 + 2 cos x)
-    return (amp / 1.76 * (sx * (1.0 + 2.0 * cx))) * (3.14159265358979323846 / 180.0);
+    return (div_nr(amp, 1.76) * (sx * (1.0 + 2.0 * cx))) * (3.14159265358979323846 / 180.0);
 }
 
 template <typename T>
@@ -169,7 +169,7 @@ H3_DEV void rls_update(const EnvK<T>& K, WAcc& Wm, CAcc& Cv, const T (&X)[9], co
     const T d0 = (K.rls_gamma + Xcov[0] * X[0]) + Xcov[1] * X[1] + Xcov[2] * X[2];      // :55 (three partial sums)
     const T d1 = Xcov[3] * X[3] + Xcov[4] * X[4] + Xcov[5] * X[5];
     const T d2 = Xcov[6] * X[6] + Xcov[7] * X[7] + Xcov[8] * X[8];
-    const T inv_d = (T)1 / (d0 + (d1 + d2));
+    const T inv_d = Math<T>::div_((T)1, d0 + (d1 + d2));
     T g[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = covX[i] * inv_d;
