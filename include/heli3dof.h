@@ -238,8 +238,8 @@ int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int
                         int32_t* blocks_per_sm, int32_t* regs, int32_t* lanes_per_warp);
 
 /* The kernels' own fp64 elementary functions, exposed for accuracy tests: fn 0: y = tanh(x), table-driven (3-DOF
- * kernels); fn 1: y = sin(x), y2 = cos(x); fn 2: y = tanh(x), table-free (6-DOF per-tick kernels).  DEVICE pointers,
- * n elements. */
+ * kernels); fn 1: y = sin(x), y2 = cos(x); fn 2: y = tanh(x), table-free (6-DOF per-tick kernels); fn 3: y = atan2(x, y2),
+ * fn 4: y = x / y2 (y2 is an INPUT for these two); fn 5: y = sqrt(x).  DEVICE pointers, n elements. */
 int h3_math_probe(int32_t fn, const double* x, double* y, double* y2, int64_t n, void* stream);
 
 /* Roofline denominators measured with dependent-free FMA chains: runs `iters` x 8 independent

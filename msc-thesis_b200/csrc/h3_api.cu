@@ -618,6 +618,12 @@ __global__ void __launch_bounds__(SMALL_BLOCK) math_probe_kernel(int fn, const d
         y[i] = Math<double>::tanh_(x[i]);       // table-driven (3-DOF kernels)
     } else if (fn == 2) {
         y[i] = MathExp::tanh_(x[i]);            // table-free (6-DOF per-tick kernels)
+    } else if (fn == 3) {
+        y[i] = atan2_nr(x[i], y2[i]);           // y2 is the second INPUT here
+    } else if (fn == 4) {
+        y[i] = div_nr(x[i], y2[i]);
+    } else if (fn == 5) {
+        y[i] = sqrt_nr(x[i]);
     } else {
         double s, c;
         Math<double>::sincos_(x[i], &s, &c);
@@ -1029,7 +1035,7 @@ int h3_closed_loop_info(const H3Config* cfg, int32_t phase2, int32_t* block, int
 }
 
 int h3_math_probe(int32_t fn, const double* x, double* y, double* y2, int64_t n, void* stream) {
-    if ((fn < 0 || fn > 2) || !x || !y || (fn == 1 && !y2)) {
+    if ((fn < 0 || fn > 5) || !x || !y || ((fn == 1 || fn == 3 || fn == 4) && !y2)) {
         set_error("h3_math_probe: bad argument");
         return H3_E_ARG;
     }

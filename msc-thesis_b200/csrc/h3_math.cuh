@@ -51,6 +51,28 @@ H3_DEV double sqrt_nr(double a) {
     return (a < 1.0e-290 && a >= 0.0) ? 0.0 : g;
 }
 
+// atan2 with ONE division and no call site: the quotient min / max of the magnitudes is reduced to |t| <= tan(pi/8)
+// through atan(q) = pi/4 + atan((q - 1) / (q + 1)) applied to numerator and denominator BEFORE dividing
+// ((mn - mx) / (mn + mx)), then t + t z A(z); octant and sign fixed up by selects.  <= 2 ulp (tests/test_gpu_math.py);
+// atan2(0, 0) = 0; NaN in, NaN out; infinite arguments give NaN (no live state is infinite).
+H3_DEV double atan2_nr(double y, double x) {
+    const double ax = ::fabs(x), ay = ::fabs(y);
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const bool hi = mn > 0.41421356237309503 * mx;
+    double t = div_nr(hi ? mn - mx : mn, hi ? mn + mx : mx);
+    t = (mx == 0.0) ? 0.0 : t;
+    const double z = t * t;
+    double p = H3_ATAN_C[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, z, H3_ATAN_C[i]);
+    double a = fma(t * z, p, t);
+    a = hi ? a + 0.78539816339744831 : a;
+    a = swap ? 1.5707963267948966 - a : a;
+    a = (x < 0.0) ? 3.1415926535897931 - a : a;
+    return ::copysign(a, y);
+}
+
 // Full-range tanh from a 313-entry table in shared memory (2.5 KB per CTA, staged by tanh_table_stage()):
 //   x0 = floor(16 |x|) / 16, d = |x| - x0 in [0, 1/16]      (exact: DFMA.RM with the 1.5 * 2^52 constant, one DFMA)
 //   tanh(x0 + d) = t0 + (1 - t0^2) p / (1 + t0 p),  t0 = tanh(x0) (table),  p = tanh(d) = d + d z Q(z), z = d^2
@@ -215,7 +237,9 @@ struct Math<double> {
     static H3_DEV double div_(double a, double b) { return div_nr(a, b); }
     static H3_DEV double abs_(double x) { return ::fabs(x); }
     static H3_DEV void sincos_(double x, double* s, double* c) { sincos_f64(x, s, c); }
-    static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }     // (IEEE: exp overflows to inf -> 0)
+    // (IEEE division on purpose: exp overflows to inf -> 0; and with an inlined division the compiler predicates the
+    // tanh / sigmoid choice of the final activation, i.e. evaluates both for every lane: -2 % in the 3-DOF kernels)
+    static H3_DEV double sigmoid_(double x) { return 1.0 / (1.0 + ::exp(-x)); }
 };
 
 // fp64 math without the shared-memory table (tanh_exp): nothing to stage

@@ -120,8 +120,8 @@ H3_DEV Controls make_controls(const ModelK& K, double coll, double lng, double l
 }
 
 H3_DEV double air_density(const ModelK& K, double z) {      // heli_models.py:818-826 with altitude = -z
-    const double x = 0.0065 * z / 288.15;
-    if (fabs(x) > 0.04) return 1.225 * pow(1.0 + x, K.rho_expo);
+    const double x = h3::div_nr(0.0065 * z, 288.15);
+    if (fabs(x) > 0.04) return 1.225 * exp(K.rho_expo * log(1.0 + x));     // (pow has an out-of-line slow path)
     double r = K.rho_c[9];
 #pragma unroll
     for (int k = 8; k >= 0; --k) r = r * x + K.rho_c[k];
@@ -136,16 +136,16 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
                  z = s[11], l0mr = s[12], l0tr = s[13], omega = s[14];
     const double rho = air_density(K, z);
     const double gamma = rho * K.Kgamma;
-    const double alpha_fus = atan2(w, u);                               // :572
-    const double V2 = u * u + v * v + w * w, V = sqrt(V2);
-    const double omega_r = omega * K.R_mr, inv_or = 1.0 / omega_r, inv_om = K.R_mr * inv_or;
+    const double alpha_fus = h3::atan2_nr(w, u);                               // :572
+    const double V2 = u * u + v * v + w * w, V = h3::sqrt_nr(V2);
+    const double omega_r = omega * K.R_mr, inv_or = h3::div_nr(1.0, omega_r), inv_om = K.R_mr * inv_or;
     double sa, ca, sf, cf;
     h3::sincos_f64(c.theta_1s - alpha_fus, &sa, &ca);                   // alpha_cp, :513
     h3::sincos_f64(alpha_fus, &sf, &cf);
     const double mu_x = V * ca * inv_or, mu_z = -V * sa * inv_or, mu2 = mu_x * mu_x;
     // flapping (:522-547): rows of A x = b, only a1 and b1 are used
     const double den1 = gamma * K.den1_c, den2 = gamma * mu2 * K.den2_c;
-    const double i12 = 1.0 / (den1 - den2), i2 = -1.0 / (den1 + den2);
+    const double i12 = h3::div_nr(1.0, den1 - den2), i2 = -h3::div_nr(1.0, den1 + den2);
     const double A01 = gamma * mu_x * K.A01_c, A12 = K.one_m_nu2 * i12, A20 = gamma * mu_x * K.A20_c * i2,
                  A21 = K.one_m_nu2 * i2;
     const double lam = l0mr - mu_z, p_om = p * inv_om, q_om = q * inv_om;
@@ -155,7 +155,7 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
                                  mu_x * 0.25 * (K.b1_tw * K.twist - K.b1_lam * lam) + K.b1_p * p_om) - 2 * q_om) * i12;
     const double b2 = (gamma * ((K.b2_t1ca + mu2 * K.b2_t1cb) * c.theta_1c + K.b2_q * q_om) + 2 * p_om) * i2;
     const double m = A21 - A20 * A01;
-    const double b1 = (b2 - A20 * b0 - m * b1v) / (1.0 - m * A12);
+    const double b1 = h3::div_nr(b2 - A20 * b0 - m * b1v, 1.0 - m * A12);
     const double a1 = b1v - A12 * b1;
     const double Ct = K.Ct_c * (2 * (2.0 / 3 + mu2) * c.theta_0 + (2 * c.theta_1s + p_om) * mu_x + 2 * (mu_z - l0mr) +
                                 (1 + mu2) * K.twist);                    // :548-552
@@ -166,7 +166,7 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     h3::sincos_f64(a1 - c.theta_1s + K.gamma_s, &s1, &c1);              // a1t1s
     h3::sincos_f64(b1 + c.theta_1c, &s2, &c2);                          // b1t1c
     const double Le = or2 * K.ecc * s2, Me = or2 * K.ecc * s1;          // :561-562
-    const double Ct_gl_mr = 2 * l0mr * sqrt(mu2 + lam * lam);           // :566
+    const double Ct_gl_mr = 2 * l0mr * h3::sqrt_nr(mu2 + lam * lam);           // :566
     // tail rotor (:572-589)
     const double omegar_tr = K.gear_Rtr * omega, inv_otr = K.inv_gear_Rtr * inv_om;
     const double wq = w + K.k1tr * l0mr * omega_r + q * K.x_tr;
@@ -174,7 +174,7 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     const double mu_z_tr = -(v - K.x_tr * r + K.z_tr * p) * inv_otr;
     const double Ct_bem_tr = K.Cttr_c * (c.theta_0_tr * (2 + 3 * mu_x_tr2) + 3 * mu_z_tr - 6 * l0tr);
     const double dl = mu_z_tr - l0tr;
-    const double Ct_gl_tr = 2 * l0tr * sqrt(mu_x_tr2 + dl * dl);
+    const double Ct_gl_tr = 2 * l0tr * h3::sqrt_nr(mu_x_tr2 + dl * dl);
     const double T_tr = Ct_bem_tr * rho * omegar_tr * omegar_tr * K.disc_tr;
     const double Y_tr = T_tr * K.f_tr, L_tr = Y_tr * K.z_tr, N_tr = -Y_tr * K.x_tr;
     // fuselage (:595-601)
@@ -183,17 +183,17 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     const double M_fus = rho * V2 * K.Mfus_c * alpha_fus;
     // horizontal stabilizer (:607-612), fin (:615-621)
     const double w_hs = w + q * K.x_hs;
-    const double Z_hs = K.Zhs_c * rho * (u * u + w_hs * w_hs) * (K.alpha0_hs + atan2(w_hs, u));
+    const double Z_hs = K.Zhs_c * rho * (u * u + w_hs * w_hs) * (K.alpha0_hs + h3::atan2_nr(w_hs, u));
     const double M_hs = Z_hs * K.x_hs;
     const double v_fin = v - r * K.x_fin + p * K.z_fin;
-    const double Y_fin = K.Yfin_c * rho * (u * u + v_fin * v_fin) * (K.beta0_fin + atan2(v_fin, u));
+    const double Y_fin = K.Yfin_c * rho * (u * u + v_fin * v_fin) * (K.beta0_fin + h3::atan2_nr(v_fin, u));
     const double L_fin = K.z_fin * Y_fin, N_fin = -K.x_fin * Y_fin;
     // power (:626-643)
     const double P_par = K.CDS_half * rho * V2 * V;
     const double P_i = fabs(K.kind * T_mr * l0mr * omega_r);
     const double PpPd = K.PpPd_c * Cd * rho * or2 * omega_r * (1 + K.n_pd * mu2);
     const double P_c = -w * K.W;
-    const double P_tr = fabs(T_tr * K.inv_Mtr * sqrt(fabs(T_tr * K.inv_2disc_tr / rho)));
+    const double P_tr = fabs(T_tr * K.inv_Mtr * h3::sqrt_nr(fabs(h3::div_nr(T_tr * K.inv_2disc_tr, rho))));
     const double P_req = P_par + P_i + PpPd + P_c + P_tr;
     double P_eng = K.Keng * (omega - K.omega_set);
     if (trimming) {
@@ -224,7 +224,7 @@ H3_DEV void derivatives(const ModelK& K, const Controls& c, const double (&s)[15
     d[5] = rdot;
     d[4] = (M - K.Ixx_m_Izz * r * p - K.Jxz * (p * p - r * r)) * K.inv_Iyy;
     d[3] = (Lq + K.Jxz * (rdot + p * q)) * K.inv_Ixx;
-    const double psidot = (q * sph + r * cph) / cth;                    // :681-683
+    const double psidot = h3::div_nr(q * sph + r * cph, cth);                    // :681-683
     d[8] = psidot;
     d[7] = q * cph - r * sph;
     d[6] = p + psidot * sth;
@@ -259,7 +259,7 @@ H3_DEV void rk4_step(const ModelK& K, const Controls& c, const double (&old)[15]
         }
     }
 #pragma unroll
-    for (int i = 0; i < 15; ++i) nw[i] = old[i] + acc[i] / 6;
+    for (int i = 0; i < 15; ++i) nw[i] = old[i] + h3::div_nr(acc[i], 6.0);
 }
 
 // The same step with the two arrays that live across the four stages (the step's initial state and the weighted
@@ -283,7 +283,7 @@ H3_DEV void rk4_step_smem(const ModelK& K, const Controls& c, const double (&old
         }
     }
 #pragma unroll
-    for (int i = 0; i < 15; ++i) nw[i] = sm[i * stride] + sm[(15 + i) * stride] / 6;
+    for (int i = 0; i < 15; ++i) nw[i] = sm[i * stride] + h3::div_nr(sm[(15 + i) * stride], 6.0);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -9,12 +9,12 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _probe(fn, x):
+def _probe(fn, x, x2=None):
     import msc_thesis_b200 as h3
     L = h3._lib
     xd = torch.as_tensor(x, device="cuda")
     y = torch.empty_like(xd)
-    y2 = torch.empty_like(xd)
+    y2 = torch.empty_like(xd) if x2 is None else torch.as_tensor(x2, device="cuda")     # fn 3 / 4: the second input
     L.check(h3.lib().h3_math_probe(fn, L.ptr(xd), L.ptr(y), L.ptr(y2), xd.numel(), L.stream_ptr(xd.device)))
     return y.cpu().numpy(), y2.cpu().numpy()
 
@@ -65,6 +65,36 @@ def test_sincos_accuracy():
     assert np.all(np.abs(s) <= 1.0) and np.all(np.abs(c) <= 1.0)
     s, c = _probe(1, np.array([np.nan, np.inf, -np.inf]))
     assert np.isnan(s).all() and np.isnan(c).all()
+
+
+def test_atan2_division_sqrt_accuracy():
+    """The call-free replacements of atan2, / and sqrt (h3_math.cuh: atan2_nr, div_nr, sqrt_nr) over the magnitudes the
+    models produce, every octant, the hand-over ratio tan(pi/8), exact zeros and NaN."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    rng = np.random.default_rng(2)
+    n = 200000
+    r = 10.0 ** rng.uniform(-6, 3, n)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    yy = np.concatenate([r * np.sin(ang), [0.0, 1.0, -1.0, 0.0, 3.0, -3.0, np.tan(np.pi / 8), 1e-300, 0.0]])
+    xx = np.concatenate([r * np.cos(ang), [1.0, 0.0, 0.0, -2.0, 3.0, 3.0, 1.0, 1e-300, 0.0]])
+    got, _ = _probe(3, yy, xx)
+    want = np.arctan2(yy, xx)
+    nz = want != 0
+    assert float(np.nanmax(_ulps(got[nz], want[nz]))) <= 3.0 and np.all(got[~nz] == 0.0)
+    assert np.isnan(_probe(3, np.array([np.nan, 1.0]), np.array([1.0, np.nan]))[0]).all()
+    a = np.concatenate([rng.normal(size=n) * 10.0 ** rng.uniform(-8, 8, n), [0.0, 1.0, -7.0]])
+    b = np.concatenate([rng.normal(size=n) * 10.0 ** rng.uniform(-8, 8, n), [3.0, 3.0, 6.0]])
+    b[b == 0] = 1.0
+    q, _ = _probe(4, a, b)
+    w = a / b
+    assert float(np.nanmax(_ulps(q[w != 0], w[w != 0]))) <= 1.0 and np.all(q[w == 0] == 0.0)
+    v = np.concatenate([10.0 ** rng.uniform(-200, 200, n), rng.uniform(0, 4, n), [0.0, 1.0, 4.0, 2.0, 1e-300, 5e-324]])
+    sq, _ = _probe(5, v)
+    w = np.sqrt(v)
+    big = v >= 1e-290
+    assert float(np.nanmax(_ulps(sq[big], w[big]))) <= 1.0 and np.all(sq[~big] == 0.0)
+    assert np.isnan(_probe(5, np.array([-1.0, np.nan]))[0]).all()
 
 
 @pytest.mark.parametrize("warps,blocks", [(4, 1), (8, 1), (4, 2 * 148), (8, 148), (4, 8 * 148)])

@@ -64,6 +64,13 @@ def f_exp(r):       # exp(r) = 1 + r + r^2 Q(r)
     return (mp.exp(r) - 1 - r) / (r * r)
 
 
+def f_atan(z):      # atan(t) = t + t z A(z), z = t^2
+    if z == 0:
+        return mp.mpf(-1) / 3
+    t = mp.sqrt(z)
+    return (mp.atan(t) / t - 1) / z
+
+
 def horner(coef, z):
     acc = np.float64(coef[-1])
     for c in coef[-2::-1]:
@@ -105,6 +112,12 @@ def main():
     ln2_hi = float(ln2)
     ln2_lo = float(ln2 - mp.mpf(ln2_hi))
     spec.append(("H3_LN2", [ln2_hi, ln2_lo, float(1 / ln2)], 0.0))
+    # atan on |t| <= tan(pi/8) (h3_math.cuh: atan2_nr reduces every quotient to this range with ONE division)
+    tmax = mp.tan(mp.pi / 8)
+    ca = [float(c) for c in cheb_fit(f_atan, mp.mpf(0), tmax ** 2, 11)]
+    xs = rng.uniform(-float(tmax), float(tmax), 5000)
+    z = xs * xs
+    spec.append(("H3_ATAN_C", ca, ulp_err(xs + xs * (z * horner(ca, z)), mp.atan, xs)))
     # pi/2 in three double pieces (Cody-Waite reduction with FMAs) and 2/pi
     pio2 = mp.pi / 2
     p1 = float(pio2)
