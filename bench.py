@@ -593,7 +593,7 @@ def main():
             swr = h3.EpisodeRunner(n, device=device, precision=a.precision, per_episode_hyper=True, switch_step=a.switch,
                                    score_window=(a.switch - 1000, a.switch), ticks_per_launch=a.launch_ticks)
             lo, hi = h3.shard_range(n_total, rank, world)
-            p4, setting_of = S.sweep_params(keys, settings, n_seeds, lo, hi, device)
+            p4, setting_of = S.sweep_params(keys, settings, n_seeds, lo, hi, device, interleave=True)   # balanced shards
             swr.params.copy_(p4)
             S.use_rows(swr, ("lon",))           # main.py:56-62 sweeps the cyclic agent only: the collective agent's rows stay uniform
             lp = swr.loop

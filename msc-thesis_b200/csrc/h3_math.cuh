@@ -53,7 +53,7 @@ H3_DEV double sqrt_nr(double a) {
 
 // atan2 with ONE division and no call site: the quotient min / max of the magnitudes is reduced to |t| <= tan(pi/8)
 // through atan(q) = pi/4 + atan((q - 1) / (q + 1)) applied to numerator and denominator BEFORE dividing
-// ((mn - mx) / (mn + mx)), then t + t z A(z); octant and sign fixed up by selects.  <= 2 ulp (tests/test_gpu_math.py);
+// ((mn - mx) / (mn + mx)), then t + t z A(z); octant and sign fixed up by selects.  <= 3 ulp (tests/test_gpu_math.py);
 // atan2(0, 0) = 0; NaN in, NaN out; infinite arguments give NaN (no live state is infinite).
 H3_DEV double atan2_nr(double y, double x) {
     const double ax = ::fabs(x), ay = ::fabs(y);

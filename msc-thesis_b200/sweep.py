@@ -36,11 +36,15 @@ def expand_grid(grid, n_seeds):
     return keys, settings, len(settings) * int(n_seeds)
 
 
-def sweep_params(keys, settings, n_seeds, lo, hi, device, agents=("lon",)):
+def sweep_params(keys, settings, n_seeds, lo, hi, device, agents=("lon",), interleave=False):
     """(19, hi - lo) device parameter block (episodes.PARAM_ROWS) of the global episodes [lo, hi): main_3dof.py's values
-    with the swept ones replaced for the agents in `agents` -- main.py:56-62 sets them on ac_params['lon'] only."""
+    with the swept ones replaced for the agents in `agents` -- main.py:56-62 sets them on ac_params['lon'] only.
+
+    interleave: episode g belongs to setting g % S (S settings) and is seed g // S of it, instead of setting
+    g // n_seeds: every contiguous shard of a multi-GPU job then holds the same mix of settings, hence the same share of
+    episodes that survive (settings differ a lot in that), and no rank waits for the one that drew the benign settings."""
     g = torch.arange(lo, hi, device=device, dtype=torch.int64)
-    setting_of = torch.div(g, int(n_seeds), rounding_mode="floor")
+    setting_of = g % len(settings) if interleave else torch.div(g, int(n_seeds), rounding_mode="floor")
     table = torch.as_tensor(settings, device=device, dtype=torch.float64)           # (S, K)
     p = torch.empty(N_PARAMS, hi - lo, dtype=torch.float64, device=device)
     for k, i in ROW.items():

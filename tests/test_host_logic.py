@@ -362,6 +362,12 @@ def test_sweep_grid_and_compat_modules():
     R = h3.episodes.ROW
     assert set(whole[R["lon_tau"]].tolist()) == {0.01, 1.0} and set(whole[R["col_tau"]].tolist()) == {0.01}
     assert set(whole[R["sigma_lon_critic"]].tolist()) == {0.1, 0.2, 0.4} and set(whole[R["sigma_col_actor"]].tolist()) == {0.1}
+    # interleaved order (setting = global index % S): every contiguous shard holds the same mix of settings
+    wi, si = h3.sweep.sweep_params(k2, s2, 5, 0, n2, "cpu", interleave=True)
+    pi, si_p = h3.sweep.sweep_params(k2, s2, 5, 12, 24, "cpu", interleave=True)
+    assert torch.equal(pi, wi[:, 12:24]) and torch.equal(si_p, si[12:24]) and list(si[:7]) == [0, 1, 2, 3, 4, 5, 0]
+    assert torch.bincount(si).tolist() == [5] * 6 and torch.bincount(si_p).tolist() == [2] * 6
+    assert sorted(wi[R["lon_tau"]].tolist()) == sorted(whole[R["lon_tau"]].tolist())
     # the reference's module names resolve to the batched classes when compat/ is on sys.path
     import importlib
     import sys
