@@ -101,10 +101,10 @@ def sweep_results(loop, setting_of_shard, n_settings, window_len, group=None):
 
 def run_sweep(grid=None, n_seeds=40, n_ticks=12000, rank=0, world_size=1, out_json=None, seed=0, device=None,
               precision="f64", switch_step=6000, score_window=(5000, 6000), ticks_per_launch=1000, agents=("lon",),
-              compact_every=0, runner=None, n_total=None):
+              compact_every=0, runner=None, n_total=None, interleave=False):
     """The whole sweep on this rank's shard; returns (keys, settings, per-setting results, loop).  n_total (<= settings x
     n_seeds) truncates the expanded list, e.g. to a fixed number of episodes per GPU: the last setting(s) then get fewer
-    seeds."""
+    seeds.  interleave: the balanced episode order of sweep_params (recommended with world_size > 1)."""
     grid = DEFAULT_GRID if grid is None else grid
     keys, settings, n_full = expand_grid(grid, n_seeds)
     n_total = n_full if n_total is None else min(int(n_total), n_full)
@@ -114,7 +114,7 @@ def run_sweep(grid=None, n_seeds=40, n_ticks=12000, rank=0, world_size=1, out_js
                                switch_step=switch_step, score_window=score_window, ticks_per_launch=ticks_per_launch)
     loop = runner.loop
     use_rows(runner, agents)
-    params, setting_of = sweep_params(keys, settings, n_seeds, lo, hi, runner.device, agents=agents)
+    params, setting_of = sweep_params(keys, settings, n_seeds, lo, hi, runner.device, agents=agents, interleave=interleave)
     runner.params.copy_(params)
     loop.init_episodes(seed, episode0=lo, v_trim=runner.params[ROW["v_trim"]],
                        sigma=runner.params[ROW["sigma_col_actor"]:ROW["sigma_lon_critic"] + 1])
