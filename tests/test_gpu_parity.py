@@ -464,12 +464,14 @@ def test_log_export_matches_reference_columns(h3):
     assert np.max(np.abs(df["cyclic"].to_numpy() - g["actions"][:300, 1])) < 1e-12
 
 
-def test_sweep_is_shard_independent(h3):
+@pytest.mark.parametrize("interleave", [False, True])
+def test_sweep_is_shard_independent(h3, interleave):
     """main.py-style sweep: per-setting success counts / scores must not depend on how the expanded
-    (setting, seed) list is sharded over ranks."""
+    (setting, seed) list is sharded over ranks -- in the setting-major order and in the interleaved one (every shard
+    holds the same mix of settings)."""
     grid = {"tau_target_critic": [0.01, 1.0], "learning_rate_actor": [0.1, 0.4], "nn_stdev": [0.1, 0.2]}
     kw = dict(grid=grid, n_seeds=6, n_ticks=120, device="cuda", switch_step=60, score_window=(20, 120), ticks_per_launch=40,
-              seed=5)
+              seed=5, interleave=interleave)
     keys, settings, res, whole = h3.sweep.run_sweep(**kw)
     n = 8 * 6
     parts = []
@@ -479,8 +481,10 @@ def test_sweep_is_shard_independent(h3):
         assert torch.equal(lp.env.state, whole.env.state[:, lo:hi])
         assert torch.equal(lp.acc, whole.acc[:, lo:hi])
         parts.append(part)
-    assert np.array_equal(sum(p["n"] for p in parts), res["n"]) and res["n"].sum() == n
+    assert np.array_equal(sum(p["n"] for p in parts), res["n"]) and res["n"].sum() == n and np.all(res["n"] == 6)
     assert np.array_equal(sum(p["success"] for p in parts), res["success"])
+    if interleave:
+        assert all(p["n"].min() >= 1 for p in parts)        # every shard sees every setting
     assert np.all(res["success"] <= res["n"]) and np.isfinite(res["mean_score_of_successes"][res["success"] > 0]).all()
     st = whole.stats()
     assert st["n"] == n and st["n_alive"] == res["success"].sum()
